@@ -1,0 +1,137 @@
+/*
+ * jne.h -- C ABI of the B200-native Johansen null-eigenspectra hot path.
+ *
+ * Drop-in boundary.  The reference (Kuan-Lun/johansen-null-eigenspectra
+ * v0.8.0, paths relative to its root) has no FFI today; these entry points are what a thin
+ * `extern "C"` block in the Rust crate would bind so that
+ *     src/data_storage/parallel_compute.rs:14-41  calculate_eigenvalues_parallel
+ * calls the GPU instead of
+ *     src/johansen_statistics.rs:59-85            calculate_eigenvalues
+ * once per seed.  INTEGRATION.md shows that binding.
+ *
+ * Conventions: plain pointers and sizes, no structs by value; every function returns
+ * JNE_OK (0) or a negative jne_status and never aborts; the message of the last failure on a
+ * context is available through jne_last_error().  The caller owns every buffer it passes in;
+ * the library keeps no caller pointer after a synchronous call returns.  One host thread per
+ * context at a time.  There is NO CPU fallback: without a usable CUDA device jne_init fails.
+ */
+#ifndef JNE_H
+#define JNE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jne_ctx jne_ctx;
+
+typedef enum jne_status {
+  JNE_OK = 0,
+  JNE_ERR_INVALID_ARG = -1,  /* model > 4, dim outside 1..JNE_MAX_DIM, steps < 1, null pointer ... */
+  JNE_ERR_CUDA = -2,         /* any CUDA runtime failure (no device, OOM, launch failure, ECC ...) */
+  JNE_ERR_NONFINITE = -3,    /* a run produced a NaN/Inf eigenvalue; the reference panics at
+                                src/johansen_statistics.rs:45 (partial_cmp().unwrap()) */
+  JNE_ERR_UNSUPPORTED = -4,  /* dim > JNE_MAX_DIM */
+  JNE_ERR_IO = -5            /* .dat writer / reader failures (jne_dat_* functions) */
+} jne_status;
+
+#define JNE_MAX_DIM 15
+
+/* ---- library / device ------------------------------------------------------------------ */
+
+/* Version string "jne-b200 <semver> (sm_100a)". */
+const char* jne_version(void);
+
+/* Number of visible CUDA devices (0 when none / no driver). */
+int jne_device_count(void);
+
+/* Create a context over `n_devices` devices (device_ids == NULL: devices 0..n-1; n_devices == 0:
+ * all visible devices).  Seed lists are sharded contiguously over the context's devices with no
+ * collective.  Replaces nothing in the reference (rayon's global pool,
+ * src/cli.rs:311-329, plays this role there). */
+int jne_init(const int* device_ids, int n_devices, jne_ctx** out);
+void jne_shutdown(jne_ctx* ctx);
+const char* jne_last_error(const jne_ctx* ctx);   /* ctx may be NULL: last jne_init failure */
+
+/* Eigenvalues per run: dim+1 for models 1 and 3, else dim; negative status on invalid input.
+ * Mirrors src/data_storage/thread_manager.rs:40-44. */
+int jne_num_eigs(uint8_t model, uint32_t dim);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+
+/* Batched calculate_eigenvalues (src/johansen_statistics.rs:59-85) for an arbitrary list of
+ * seeds (src/data_storage/progress.rs:56-61 hands out arbitrary subsets of 1..=num_runs).
+ * out: n x p doubles, row i = eigenvalues of seeds[i], descending (:45).  Host buffers; the
+ * call copies seeds H2D, runs the fused kernels on every device of the context, and copies the
+ * eigenvalues D2H before returning.  Same (model, dim, steps, seed) => bit-identical row,
+ * whatever n, the batch split or the number of devices. */
+int jne_eigs_batch(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps,
+                   const uint32_t* seeds, uint64_t n, double* out);
+
+/* Asynchronous pair: jne_submit enqueues the batch (seeds are copied before it returns; `out`
+ * must stay valid until jne_wait) and returns a ticket > 0, or a negative status.  jne_wait
+ * blocks until that batch's eigenvalues are in `out`.  At most one ticket may be outstanding
+ * per context; lets the caller overlap GPU work with the .dat writer thread
+ * (src/data_storage/thread_manager.rs:25-92). */
+int64_t jne_submit(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps,
+                   const uint32_t* seeds, uint64_t n, double* out);
+int jne_wait(jne_ctx* ctx, int64_t ticket);
+
+/* Same computation with everything already resident on device 0 of the context: d_seeds and
+ * d_out are DEVICE pointers, `stream` is a cudaStream_t (NULL = default stream).  Enqueues only;
+ * the caller synchronises.  Non-finite runs are counted and reported by the next synchronous
+ * call or by jne_check_async(). */
+int jne_eigs_batch_device(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps,
+                          const void* d_seeds, uint64_t n, void* d_out, void* stream);
+int jne_check_async(jne_ctx* ctx);   /* syncs device 0; JNE_ERR_NONFINITE if any run since the last check failed */
+
+/* calculate_eigenvalues_from_matrices fed by caller-supplied increments (parity gate 1):
+ * dB holds n runs, each dim x steps column-major (element (r, t) at t*dim + r, the layout of
+ * src/rng_matrix.rs:36), already scaled (dB = sqrt(dt) z).  The Brownian path is rebuilt as
+ * the reference does: B_0 = 0, naive cumulative sum (src/matrix_utils.rs:51-63), dB re-derived
+ * by subtraction (src/johansen_statistics.rs:80-82), delta_t = 1/steps (:70). */
+int jne_eigs_from_increments(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps,
+                             const double* dB, uint64_t n, double* out);
+
+/* ---- pieces of the path exposed for parity tests ------------------------------------------ */
+
+/* gen_normal_matrix(nrows = dim, ncols = steps, seed) (src/rng_matrix.rs:11-37): dim x steps
+ * column-major standard normals of the device stream (Philox4x32-10 + Box-Muller). */
+int jne_gen_normal_matrix(jne_ctx* ctx, uint32_t dim, uint32_t steps, uint32_t seed, double* out);
+
+/* brownian_motion_matrix(dim, steps, delta_t, AlongColumns, zeros, seed) (src/rng_matrix.rs:57-141):
+ * dim x (steps+1) column-major, first column zero. */
+int jne_brownian_motion_matrix(jne_ctx* ctx, uint32_t dim, uint32_t steps, double delta_t,
+                               uint32_t seed, double* out);
+
+/* The eigen-solve alone: for each of n problems, eigenvalues |alpha|/beta of the pencil
+ * (S1' S1, S2), descending -- what GeneralizedEigen::new + raw_eigenvalues + sort compute at
+ * src/johansen_statistics.rs:35-46.  S1: d x p column-major per problem (sum dB F'),
+ * S2: p x p symmetric positive definite.  1 <= d <= p <= 16. */
+int jne_pencil_eigs_batch(jne_ctx* ctx, uint32_t p, uint32_t d, const double* S1, const double* S2,
+                          uint64_t n, double* out);
+
+/* Debug: like jne_eigs_batch on device 0, additionally returning per run the assembled
+ * S2 (16 x 16, row-major, zero padded) followed by R = S1' (16 x 16): 512 doubles per run. */
+int jne_eigs_batch_debug(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps,
+                         const uint32_t* seeds, uint64_t n, double* out, double* mats);
+
+/* ---- measurement helpers ------------------------------------------------------------------ */
+
+/* Register-resident DFMA (mode 0) or mma.sync.m8n8k4.f64 (mode 1) throughput on device 0 of the
+ * context, in TFLOP/s, timed with CUDA events over `ms_target` milliseconds of work.  This is the
+ * FP64 roofline denominator (MEASURED_PEAKS.json holds no FP64 figure). */
+int jne_fp64_peak_tflops(jne_ctx* ctx, int mode, double ms_target, double* tflops);
+
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+uint64_t jne_launch_count(const jne_ctx* ctx);
+
+/* Algorithmic flops per run: 2 T [p(p+1)/2 + p d]. */
+double jne_flops_per_run(uint8_t model, uint32_t dim, uint32_t steps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JNE_H */

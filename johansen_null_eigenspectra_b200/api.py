@@ -1,0 +1,291 @@
+"""ctypes binding of include/jne.h plus the Python mirror of the reference's call sites."""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+from pathlib import Path
+from typing import Callable, Iterable, Optional, Sequence
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+_LIB_PATH = Path(os.environ.get("JNE_LIBRARY", _PKG / "libjne.so"))
+
+
+class JneError(RuntimeError):
+    """Raised for any negative jne_status; carries the library's message."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"jne status {status}: {message}")
+        self.status = status
+
+
+def _load() -> C.CDLL:
+    if not _LIB_PATH.exists():
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python -m johansen_null_eigenspectra_b200.build` "
+            "(or __graft_entry__.build()).  There is no CPU fallback for the hot path."
+        )
+    lib = C.CDLL(str(_LIB_PATH))
+    u8, u32, u64, i64, dbl = C.c_uint8, C.c_uint32, C.c_uint64, C.c_int64, C.c_double
+    vp, ip = C.c_void_p, C.POINTER(C.c_int)
+    sig = {
+        "jne_version": (C.c_char_p, []),
+        "jne_device_count": (C.c_int, []),
+        "jne_init": (C.c_int, [ip, C.c_int, C.POINTER(vp)]),
+        "jne_shutdown": (None, [vp]),
+        "jne_last_error": (C.c_char_p, [vp]),
+        "jne_num_eigs": (C.c_int, [u8, u32]),
+        "jne_eigs_batch": (C.c_int, [vp, u8, u32, u32, vp, u64, vp]),
+        "jne_submit": (i64, [vp, u8, u32, u32, vp, u64, vp]),
+        "jne_wait": (C.c_int, [vp, i64]),
+        "jne_eigs_batch_device": (C.c_int, [vp, u8, u32, u32, vp, u64, vp, vp]),
+        "jne_check_async": (C.c_int, [vp]),
+        "jne_eigs_from_increments": (C.c_int, [vp, u8, u32, u32, vp, u64, vp]),
+        "jne_gen_normal_matrix": (C.c_int, [vp, u32, u32, u32, vp]),
+        "jne_brownian_motion_matrix": (C.c_int, [vp, u32, u32, dbl, u32, vp]),
+        "jne_pencil_eigs_batch": (C.c_int, [vp, u32, u32, vp, vp, u64, vp]),
+        "jne_eigs_batch_debug": (C.c_int, [vp, u8, u32, u32, vp, u64, vp, vp]),
+        "jne_fp64_peak_tflops": (C.c_int, [vp, C.c_int, dbl, C.POINTER(dbl)]),
+        "jne_launch_count": (u64, [vp]),
+        "jne_flops_per_run": (dbl, [u8, u32, u32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def version() -> str:
+    return lib.jne_version().decode()
+
+
+def num_eigs(model: int, dim: int) -> int:
+    r = lib.jne_num_eigs(int(model), int(dim))
+    if r < 0:
+        raise JneError(r, "invalid model/dim")
+    return r
+
+
+def flops_per_run(model: int, dim: int, steps: int) -> float:
+    return float(lib.jne_flops_per_run(int(model), int(dim), int(steps)))
+
+
+class JohansenModel(enum.IntEnum):
+    """src/johansen_models.rs:6-51 -- number <-> variant is part of the .dat contract."""
+
+    NoInterceptNoTrend = 0
+    InterceptNoTrendWithInterceptInCoint = 1
+    InterceptNoTrendUnrestrictedIntercept = 2
+    InterceptTrendUnrestrictedInterceptRestrictedTrend = 3
+    InterceptTrendUnrestrictedBoth = 4
+
+    def to_number(self) -> int:
+        return int(self)
+
+    @classmethod
+    def from_number(cls, n: int) -> Optional["JohansenModel"]:
+        try:
+            return cls(n)
+        except ValueError:
+            return None
+
+    @classmethod
+    def all_models(cls):
+        return list(cls)
+
+    @classmethod
+    def default(cls) -> "JohansenModel":  # src/johansen_models.rs: Default = model 2
+        return cls.InterceptNoTrendUnrestrictedIntercept
+
+    def has_intercept(self) -> bool:
+        return self != JohansenModel.NoInterceptNoTrend
+
+    def has_trend(self) -> bool:
+        return self in (JohansenModel.InterceptTrendUnrestrictedInterceptRestrictedTrend,
+                        JohansenModel.InterceptTrendUnrestrictedBoth)
+
+    def num_eigs(self, dim: int) -> int:
+        return num_eigs(int(self), dim)
+
+
+def _model_number(model) -> int:
+    return int(model)
+
+
+class Engine:
+    """Owns a ``jne_ctx``.  ``devices=None`` uses every visible GPU; a list pins device ids."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None):
+        self._ctx = C.c_void_p()
+        if devices is None:
+            rc = lib.jne_init(None, 0, C.byref(self._ctx))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = lib.jne_init(arr, len(devices), C.byref(self._ctx))
+        if rc != 0:
+            msg = lib.jne_last_error(None).decode()
+            self._ctx = C.c_void_p()
+            raise JneError(rc, msg)
+
+    # -- plumbing -------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            lib.jne_shutdown(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc < 0:
+            raise JneError(rc, lib.jne_last_error(self._ctx).decode())
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib.jne_launch_count(self._ctx))
+
+    # -- the hot path ---------------------------------------------------------------------
+    def eigs_batch(self, model, dim: int, steps: int, seeds) -> np.ndarray:
+        """(n, p) float64, row i = descending eigenvalues of seeds[i]."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        p = num_eigs(_model_number(model), dim)
+        out = np.empty((seeds.size, p), dtype=np.float64)
+        self._check(lib.jne_eigs_batch(self._ctx, _model_number(model), dim, steps,
+                                       seeds.ctypes.data, seeds.size, out.ctypes.data))
+        return out
+
+    def submit(self, model, dim: int, steps: int, seeds, out: np.ndarray) -> int:
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        assert out.flags.c_contiguous and out.dtype == np.float64
+        t = lib.jne_submit(self._ctx, _model_number(model), dim, steps, seeds.ctypes.data, seeds.size,
+                           out.ctypes.data)
+        self._check(t)
+        return int(t)
+
+    def wait(self, ticket: int) -> None:
+        self._check(lib.jne_wait(self._ctx, ticket))
+
+    def eigs_batch_device(self, model, dim: int, steps: int, d_seeds_ptr: int, n: int, d_out_ptr: int,
+                          stream_ptr: int = 0) -> None:
+        """Raw device pointers (e.g. torch ``tensor.data_ptr()``); enqueue only."""
+        self._check(lib.jne_eigs_batch_device(self._ctx, _model_number(model), dim, steps,
+                                              C.c_void_p(d_seeds_ptr), n, C.c_void_p(d_out_ptr),
+                                              C.c_void_p(stream_ptr)))
+
+    def check_async(self) -> None:
+        self._check(lib.jne_check_async(self._ctx))
+
+    def eigs_from_increments(self, model, dB: np.ndarray) -> np.ndarray:
+        """dB: (n, steps, dim) C-order == per-run column-major dim x steps (src/rng_matrix.rs:36)."""
+        dB = np.ascontiguousarray(dB, dtype=np.float64)
+        if dB.ndim != 3:
+            raise ValueError("dB must have shape (n, steps, dim)")
+        n, steps, dim = dB.shape
+        p = num_eigs(_model_number(model), dim)
+        out = np.empty((n, p), dtype=np.float64)
+        self._check(lib.jne_eigs_from_increments(self._ctx, _model_number(model), dim, steps,
+                                                 dB.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def eigs_batch_debug(self, model, dim: int, steps: int, seeds):
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        p = num_eigs(_model_number(model), dim)
+        out = np.empty((seeds.size, p), dtype=np.float64)
+        mats = np.empty((seeds.size, 2, 16, 16), dtype=np.float64)
+        self._check(lib.jne_eigs_batch_debug(self._ctx, _model_number(model), dim, steps,
+                                             seeds.ctypes.data, seeds.size, out.ctypes.data, mats.ctypes.data))
+        return out, mats[:, 0], mats[:, 1]
+
+    # -- exposed pieces ---------------------------------------------------------------------
+    def gen_normal_matrix(self, nrows: int, ncols: int, seed: int) -> np.ndarray:
+        """dim x steps matrix (numpy view of the column-major buffer)."""
+        buf = np.empty((ncols, nrows), dtype=np.float64)
+        self._check(lib.jne_gen_normal_matrix(self._ctx, nrows, ncols, seed & 0xFFFFFFFF, buf.ctypes.data))
+        return buf.T
+
+    def brownian_motion_matrix(self, dim: int, steps: int, delta_t: float, seed: int) -> np.ndarray:
+        buf = np.empty((steps + 1, dim), dtype=np.float64)
+        self._check(lib.jne_brownian_motion_matrix(self._ctx, dim, steps, float(delta_t), seed & 0xFFFFFFFF,
+                                                   buf.ctypes.data))
+        return buf.T
+
+    def pencil_eigs_batch(self, S1: np.ndarray, S2: np.ndarray) -> np.ndarray:
+        """S1: (n, d, p) [sum dB F'], S2: (n, p, p).  Returns (n, p) descending."""
+        S1 = np.asarray(S1, dtype=np.float64)
+        S2 = np.ascontiguousarray(S2, dtype=np.float64)
+        n, d, p = S1.shape
+        s1t = np.ascontiguousarray(np.transpose(S1, (0, 2, 1)))  # (n, p, d) row-major == d x p column-major
+        out = np.empty((n, p), dtype=np.float64)
+        self._check(lib.jne_pencil_eigs_batch(self._ctx, p, d, s1t.ctypes.data, S2.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def fp64_peak_tflops(self, mode: int = 0, ms_target: float = 200.0) -> float:
+        v = C.c_double()
+        self._check(lib.jne_fp64_peak_tflops(self._ctx, mode, ms_target, C.byref(v)))
+        return v.value
+
+
+_default: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    global _default
+    if _default is None:
+        _default = Engine()
+    return _default
+
+
+# ---- mirrors of the reference's functions ------------------------------------------------------
+
+def calculate_eigenvalues(dim: int, steps: int, seed: int, model) -> list:
+    """src/johansen_statistics.rs:59-85 -- one run, eigenvalues descending."""
+    return default_engine().eigs_batch(model, dim, steps, [seed])[0].tolist()
+
+
+def calculate_eigenvalues_parallel(dim: int, steps: int, seeds: Iterable[int], model,
+                                   sender: Callable[[int, list], None], quiet: bool = True,
+                                   engine: Optional[Engine] = None, batch: int = 1 << 20) -> None:
+    """src/data_storage/parallel_compute.rs:14-41 -- for every seed, send (seed, eigenvalues).
+    The reference walks 10 000-seed chunks through rayon; here each (large) chunk is one
+    jne_submit, overlapped with delivering the previous chunk to ``sender``."""
+    eng = engine or default_engine()
+    seeds = np.ascontiguousarray(list(seeds) if not isinstance(seeds, np.ndarray) else seeds, dtype=np.uint32)
+    p = num_eigs(_model_number(model), dim)
+    prev = None
+    for a in range(0, seeds.size, batch):
+        chunk = seeds[a:a + batch]
+        out = np.empty((chunk.size, p), dtype=np.float64)
+        ticket = eng.submit(model, dim, steps, chunk, out)
+        if prev is not None:
+            for s, row in zip(prev[0].tolist(), prev[1]):
+                sender(s, row.tolist())
+        eng.wait(ticket)
+        prev = (chunk, out)
+    if prev is not None:
+        for s, row in zip(prev[0].tolist(), prev[1]):
+            sender(s, row.tolist())
+
+
+def gen_normal_matrix(nrows: int, ncols: int, seed: int) -> np.ndarray:
+    """src/rng_matrix.rs:11-37."""
+    return default_engine().gen_normal_matrix(nrows, ncols, seed)
+
+
+def brownian_motion_matrix(dim: int, steps: int, delta_t: float, seed: int) -> np.ndarray:
+    """src/rng_matrix.rs:57-141 with AlongColumns and a zero start column."""
+    return default_engine().brownian_motion_matrix(dim, steps, delta_t, seed)

@@ -1,0 +1,616 @@
+// Host side of the C ABI declared in include/jne.h: context, device sharding, chunked
+// double-buffered transfers, kernel dispatch.  No CPU fallback anywhere in this file: every
+// numeric result is produced by the kernels of jne_kernels.cuh.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/jne.h"
+#include "jne_kernels.cuh"
+
+#define JNE_VERSION_STR "jne-b200 0.1.0 (sm_100a)"
+
+namespace {
+
+constexpr uint64_t kChunkRuns = 1ull << 18;   // runs per launch on the host-buffer path
+
+std::mutex g_init_err_mu;
+std::string g_init_err;
+
+struct Slot {
+  uint32_t* d_seeds = nullptr;
+  double* d_out = nullptr;
+  uint32_t* h_seeds = nullptr;   // pinned
+  double* h_out = nullptr;       // pinned
+  cudaEvent_t done = nullptr;
+  uint64_t n = 0, offset = 0;    // runs in flight and their position in the caller's arrays
+  bool busy = false;
+};
+
+struct Device {
+  int id = -1;
+  cudaStream_t stream = nullptr;
+  Slot slot[2];
+  unsigned int* d_err = nullptr;
+  unsigned int* h_err = nullptr;  // pinned
+  double* d_scratch = nullptr;    // increments / pencil inputs, grown on demand
+  size_t scratch_bytes = 0;
+};
+
+}  // namespace
+
+struct jne_ctx {
+  std::vector<Device> devs;
+  std::string err;
+  std::mutex err_mu;
+  std::atomic<uint64_t> launches{0};
+  // async ticket
+  std::thread worker;
+  int64_t next_ticket = 1, pending_ticket = 0;
+  int pending_status = JNE_OK;
+};
+
+namespace {
+
+int fail(jne_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) { std::lock_guard<std::mutex> lk(ctx->err_mu); ctx->err = msg; }
+  else { std::lock_guard<std::mutex> lk(g_init_err_mu); g_init_err = msg; }
+  return code;
+}
+
+#define JNE_CUDA(ctx, call)                                                                         \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      char b_[512];                                                                                 \
+      snprintf(b_, sizeof b_, "CUDA error %s (%s) at %s:%d: %s", cudaGetErrorName(e_),              \
+               cudaGetErrorString(e_), __FILE__, __LINE__, #call);                                  \
+      return fail(ctx, JNE_ERR_CUDA, b_);                                                           \
+    }                                                                                               \
+  } while (0)
+
+int validate(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps) {
+  if (model > 4) return fail(ctx, JNE_ERR_INVALID_ARG, "model must be 0..4");
+  if (dim < 1 || dim > 255) return fail(ctx, JNE_ERR_INVALID_ARG, "dim must be 1..255");
+  if (dim > JNE_MAX_DIM) return fail(ctx, JNE_ERR_UNSUPPORTED, "dim > JNE_MAX_DIM (15) is not supported");
+  if (steps < 1 || steps > (1u << 30)) return fail(ctx, JNE_ERR_INVALID_ARG, "steps must be 1..2^30");
+  if (model == 4 && steps < 2)
+    return fail(ctx, JNE_ERR_INVALID_ARG, "model 4 needs steps >= 2 (singular Z Z', src/johansen_statistics.rs:191-192)");
+  return JNE_OK;
+}
+
+// sum_{i=a}^{b-1} of (2i+1-T)  and of  3(2i+1-T)^2 - (T^2-1), exactly, in 128-bit integers.
+void segment_weights(uint64_t a, uint64_t b, uint64_t T, double* w1, double* w2) {
+  const __int128 A = a, B = b, TT = T, n = B - A;
+  *w1 = (double)(n * (A + B - TT));
+  auto sum1 = [](__int128 m) { return m * (m - 1) / 2; };                 // sum_{i<m} i
+  auto sum2 = [](__int128 m) { return (m - 1) * m * (2 * m - 1) / 6; };   // sum_{i<m} i^2
+  const __int128 S1 = sum1(B) - sum1(A), S2 = sum2(B) - sum2(A);
+  const __int128 q = 1 - TT;
+  const __int128 m2 = 4 * S2 + 4 * q * S1 + q * q * n;                    // sum (2i+1-T)^2
+  *w2 = (double)(3 * m2 - (TT * TT - 1) * n);
+}
+
+JneRunParams make_params(uint8_t model, uint32_t dim, uint32_t steps, bool from_increments) {
+  JneRunParams p{};
+  p.dim = dim; p.steps = steps; p.model = model;
+  p.p = (model == 1 || model == 3) ? dim + 1 : dim;
+  p.seg_len = 4u * ((steps + 15u) / 16u);
+  p.T = (double)steps;
+  p.factor = from_increments ? (double)steps : 1.0;
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t a = std::min<uint64_t>((uint64_t)k * p.seg_len, steps);
+    const uint64_t b = std::min<uint64_t>(a + p.seg_len, steps);
+    p.seg_n[k] = (double)(b - a);
+    segment_weights(a, b, steps, &p.seg_w1[k], &p.seg_w2[k]);
+  }
+  return p;
+}
+
+template <int DP> constexpr size_t cta_smem() {
+  return (size_t)JNE_WARPS_PER_CTA * (JneGeo<DP>::WARP_SMEM + 7 * 16) * sizeof(double);
+}
+constexpr size_t pencil_smem() { return (size_t)JNE_WARPS_PER_CTA * (2 * 16 * JNE_LD + 64) * sizeof(double); }
+
+template <int DP, int DET, bool RNG>
+cudaError_t launch_one(const uint32_t* d_seeds, const double* d_dB, uint64_t n, const JneRunParams& prm,
+                       double* d_out, unsigned int* d_err, double* d_dbg, cudaStream_t st) {
+  auto kern = jne_run_kernel<DP, DET, RNG>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem<DP>());
+  if (e != cudaSuccess) return e;
+  const unsigned grid = (unsigned)((n + JNE_WARPS_PER_CTA - 1) / JNE_WARPS_PER_CTA);
+  kern<<<grid, 32 * JNE_WARPS_PER_CTA, cta_smem<DP>(), st>>>(d_seeds, d_dB, n, prm, d_out, d_err, d_dbg);
+  return cudaGetLastError();
+}
+
+template <int DP, bool RNG>
+cudaError_t launch_det(int det, const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm, double* o,
+                       unsigned int* e, double* dbg, cudaStream_t st) {
+  switch (det) {
+    case 0: return launch_one<DP, 0, RNG>(s, b, n, prm, o, e, dbg, st);
+    case 1: return launch_one<DP, 1, RNG>(s, b, n, prm, o, e, dbg, st);
+    default: return launch_one<DP, 2, RNG>(s, b, n, prm, o, e, dbg, st);
+  }
+}
+
+template <bool RNG>
+cudaError_t launch_run(const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm, double* o,
+                       unsigned int* e, double* dbg, cudaStream_t st) {
+  const int det = (prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2);
+  if (prm.dim <= 4) return launch_det<4, RNG>(det, s, b, n, prm, o, e, dbg, st);
+  if (prm.dim <= 8) return launch_det<8, RNG>(det, s, b, n, prm, o, e, dbg, st);
+  if (prm.dim <= 12) return launch_det<12, RNG>(det, s, b, n, prm, o, e, dbg, st);
+  return launch_det<16, RNG>(det, s, b, n, prm, o, e, dbg, st);
+}
+
+int ensure_scratch(jne_ctx* ctx, Device& dv, size_t bytes) {
+  if (dv.scratch_bytes >= bytes) return JNE_OK;
+  if (dv.d_scratch) { cudaFree(dv.d_scratch); dv.d_scratch = nullptr; dv.scratch_bytes = 0; }
+  JNE_CUDA(ctx, cudaMalloc(&dv.d_scratch, bytes));
+  dv.scratch_bytes = bytes;
+  return JNE_OK;
+}
+
+// Drain one slot: wait for its D2H, hand the rows to the caller's array.
+int drain(jne_ctx* ctx, Slot& s, uint32_t p, double* out) {
+  if (!s.busy) return JNE_OK;
+  JNE_CUDA(ctx, cudaEventSynchronize(s.done));
+  std::memcpy(out + s.offset * p, s.h_out, s.n * p * sizeof(double));
+  s.busy = false;
+  return JNE_OK;
+}
+
+// One device's share of a host-buffer batch (called on its own host thread).
+int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm, const uint32_t* seeds, uint64_t n, double* out,
+              std::string* err_out) {
+  auto body = [&]() -> int {
+    JNE_CUDA(ctx, cudaSetDevice(dv.id));
+    *dv.h_err = 0;
+    JNE_CUDA(ctx, cudaMemsetAsync(dv.d_err, 0, sizeof(unsigned int), dv.stream));
+    uint64_t done = 0;
+    int which = 0;
+    while (done < n) {
+      Slot& s = dv.slot[which];
+      int rc = drain(ctx, s, prm.p, out);
+      if (rc) return rc;
+      const uint64_t m = std::min<uint64_t>(kChunkRuns, n - done);
+      std::memcpy(s.h_seeds, seeds + done, m * sizeof(uint32_t));
+      JNE_CUDA(ctx, cudaMemcpyAsync(s.d_seeds, s.h_seeds, m * sizeof(uint32_t), cudaMemcpyHostToDevice, dv.stream));
+      JNE_CUDA(ctx, launch_run<true>(s.d_seeds, nullptr, m, prm, s.d_out, dv.d_err, nullptr, dv.stream));
+      ctx->launches.fetch_add(1);
+      JNE_CUDA(ctx, cudaMemcpyAsync(s.h_out, s.d_out, m * prm.p * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
+      JNE_CUDA(ctx, cudaEventRecord(s.done, dv.stream));
+      s.n = m; s.offset = done; s.busy = true;
+      done += m;
+      which ^= 1;
+    }
+    for (int i = 0; i < 2; ++i) {
+      int rc = drain(ctx, dv.slot[which ^ i], prm.p, out);
+      if (rc) return rc;
+    }
+    JNE_CUDA(ctx, cudaMemcpyAsync(dv.h_err, dv.d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, dv.stream));
+    JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+    if (*dv.h_err) {
+      char b[160];
+      snprintf(b, sizeof b, "%u run(s) produced non-finite eigenvalues (the reference panics at src/johansen_statistics.rs:45)", *dv.h_err);
+      return fail(ctx, JNE_ERR_NONFINITE, b);
+    }
+    return JNE_OK;
+  };
+  // ctx->err is shared between device threads: serialise through a local copy
+  int rc = body();
+  if (rc && err_out) { std::lock_guard<std::mutex> lk(ctx->err_mu); *err_out = ctx->err; }
+  return rc;
+}
+
+int eigs_batch_sync(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
+                    double* out) {
+  const JneRunParams prm = make_params(model, dim, steps, false);
+  const size_t nd = ctx->devs.size();
+  if (n == 0) return JNE_OK;
+  if (nd == 1) return run_share(ctx, ctx->devs[0], prm, seeds, n, out, nullptr);
+  // contiguous slices, one host thread per device, no collective
+  std::vector<std::thread> th;
+  std::vector<int> rc(nd, JNE_OK);
+  std::vector<std::string> errs(nd);
+  const uint64_t per = (n + nd - 1) / nd;
+  for (size_t i = 0; i < nd; ++i) {
+    const uint64_t a = std::min<uint64_t>(i * per, n), b = std::min<uint64_t>(a + per, n);
+    if (a == b) continue;
+    th.emplace_back([&, i, a, b]() {
+      rc[i] = run_share(ctx, ctx->devs[i], prm, seeds + a, b - a, out + a * prm.p, &errs[i]);
+    });
+  }
+  for (auto& t : th) t.join();
+  for (size_t i = 0; i < nd; ++i)
+    if (rc[i]) { ctx->err = errs[i]; return rc[i]; }
+  return JNE_OK;
+}
+
+void join_worker(jne_ctx* ctx) {
+  if (ctx->worker.joinable()) ctx->worker.join();
+}
+
+// ---- FP64 peak microbenchmark (roofline denominator) ----
+template <int MODE>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, double* sink) {
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = seed * (i + threadIdx.x);
+  const double a = seed + threadIdx.x * 1e-9, b = seed * 0.5;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) jne_dmma(acc[2 * i], acc[2 * i + 1], a, b);
+      }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 123.456) sink[0] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* jne_version(void) { return JNE_VERSION_STR; }
+
+int jne_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int jne_num_eigs(uint8_t model, uint32_t dim) {
+  if (model > 4 || dim < 1 || dim > 255) return JNE_ERR_INVALID_ARG;
+  return (model == 1 || model == 3) ? (int)dim + 1 : (int)dim;
+}
+
+double jne_flops_per_run(uint8_t model, uint32_t dim, uint32_t steps) {
+  const double p = (model == 1 || model == 3) ? dim + 1.0 : dim;
+  return 2.0 * steps * (p * (p + 1.0) / 2.0 + p * dim);
+}
+
+const char* jne_last_error(const jne_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  std::lock_guard<std::mutex> lk(g_init_err_mu);
+  static thread_local std::string copy;
+  copy = g_init_err;
+  return copy.c_str();
+}
+
+uint64_t jne_launch_count(const jne_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+void jne_shutdown(jne_ctx* ctx) {
+  if (!ctx) return;
+  join_worker(ctx);
+  for (auto& dv : ctx->devs) {
+    if (cudaSetDevice(dv.id) != cudaSuccess) continue;
+    for (auto& s : dv.slot) {
+      if (s.d_seeds) cudaFree(s.d_seeds);
+      if (s.d_out) cudaFree(s.d_out);
+      if (s.h_seeds) cudaFreeHost(s.h_seeds);
+      if (s.h_out) cudaFreeHost(s.h_out);
+      if (s.done) cudaEventDestroy(s.done);
+    }
+    if (dv.d_err) cudaFree(dv.d_err);
+    if (dv.h_err) cudaFreeHost(dv.h_err);
+    if (dv.d_scratch) cudaFree(dv.d_scratch);
+    if (dv.stream) cudaStreamDestroy(dv.stream);
+  }
+  delete ctx;
+}
+
+int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
+  if (!out) return fail(nullptr, JNE_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  int visible = 0;
+  cudaError_t e = cudaGetDeviceCount(&visible);
+  if (e != cudaSuccess || visible == 0) {
+    cudaGetLastError();
+    return fail(nullptr, JNE_ERR_CUDA,
+                std::string("no usable CUDA device (") + (e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)) +
+                    "); this library has no CPU fallback");
+  }
+  if (n_devices < 0) return fail(nullptr, JNE_ERR_INVALID_ARG, "n_devices < 0");
+  if (n_devices == 0) n_devices = visible;
+  jne_ctx* ctx = new jne_ctx();
+  ctx->devs.resize(n_devices);
+  for (int i = 0; i < n_devices; ++i) {
+    Device& dv = ctx->devs[i];
+    dv.id = device_ids ? device_ids[i] : i;
+    if (dv.id < 0 || dv.id >= visible) {
+      fail(nullptr, JNE_ERR_INVALID_ARG, "device id out of range");
+      jne_shutdown(ctx);
+      return JNE_ERR_INVALID_ARG;
+    }
+    auto setup = [&]() -> int {
+      JNE_CUDA(nullptr, cudaSetDevice(dv.id));
+      cudaDeviceProp prop;
+      JNE_CUDA(nullptr, cudaGetDeviceProperties(&prop, dv.id));
+      if (prop.major != 10)
+        return fail(nullptr, JNE_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100 (B200); the kernels are built for sm_100a only");
+      JNE_CUDA(nullptr, cudaStreamCreateWithFlags(&dv.stream, cudaStreamNonBlocking));
+      for (auto& s : dv.slot) {
+        JNE_CUDA(nullptr, cudaMalloc(&s.d_seeds, kChunkRuns * sizeof(uint32_t)));
+        JNE_CUDA(nullptr, cudaMalloc(&s.d_out, kChunkRuns * 16 * sizeof(double)));
+        JNE_CUDA(nullptr, cudaMallocHost(&s.h_seeds, kChunkRuns * sizeof(uint32_t)));
+        JNE_CUDA(nullptr, cudaMallocHost(&s.h_out, kChunkRuns * 16 * sizeof(double)));
+        JNE_CUDA(nullptr, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+      }
+      JNE_CUDA(nullptr, cudaMalloc(&dv.d_err, sizeof(unsigned int)));
+      JNE_CUDA(nullptr, cudaMemset(dv.d_err, 0, sizeof(unsigned int)));
+      JNE_CUDA(nullptr, cudaMallocHost(&dv.h_err, sizeof(unsigned int)));
+      *dv.h_err = 0;
+      return JNE_OK;
+    };
+    int rc = setup();
+    if (rc) { jne_shutdown(ctx); return rc; }
+  }
+  *out = ctx;
+  return JNE_OK;
+}
+
+int jne_eigs_batch(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
+                   double* out) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  join_worker(ctx);
+  int rc = validate(ctx, model, dim, steps);
+  if (rc) return rc;
+  if (n && (!seeds || !out)) return fail(ctx, JNE_ERR_INVALID_ARG, "seeds/out is NULL");
+  return eigs_batch_sync(ctx, model, dim, steps, seeds, n, out);
+}
+
+int64_t jne_submit(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
+                   double* out) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  if (ctx->pending_ticket) return fail(ctx, JNE_ERR_INVALID_ARG, "a ticket is already outstanding; call jne_wait first");
+  int rc = validate(ctx, model, dim, steps);
+  if (rc) return rc;
+  if (n && (!seeds || !out)) return fail(ctx, JNE_ERR_INVALID_ARG, "seeds/out is NULL");
+  join_worker(ctx);
+  auto copy = std::make_shared<std::vector<uint32_t>>(seeds, seeds + n);
+  ctx->pending_ticket = ctx->next_ticket++;
+  ctx->worker = std::thread([ctx, model, dim, steps, copy, n, out]() {
+    ctx->pending_status = eigs_batch_sync(ctx, model, dim, steps, copy->data(), n, out);
+  });
+  return ctx->pending_ticket;
+}
+
+int jne_wait(jne_ctx* ctx, int64_t ticket) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  if (ticket <= 0 || ticket != ctx->pending_ticket) return fail(ctx, JNE_ERR_INVALID_ARG, "unknown ticket");
+  join_worker(ctx);
+  ctx->pending_ticket = 0;
+  return ctx->pending_status;
+}
+
+int jne_eigs_batch_device(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, const void* d_seeds, uint64_t n,
+                          void* d_out, void* stream) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  int rc = validate(ctx, model, dim, steps);
+  if (rc) return rc;
+  if (n == 0) return JNE_OK;
+  if (!d_seeds || !d_out) return fail(ctx, JNE_ERR_INVALID_ARG, "d_seeds/d_out is NULL");
+  Device& dv = ctx->devs[0];
+  JNE_CUDA(ctx, cudaSetDevice(dv.id));
+  const JneRunParams prm = make_params(model, dim, steps, false);
+  // grid.x is 32-bit: split very large batches
+  const uint64_t max_runs = (uint64_t)0x7fffffffu * JNE_WARPS_PER_CTA;
+  for (uint64_t off = 0; off < n; off += max_runs) {
+    const uint64_t m = std::min(max_runs, n - off);
+    JNE_CUDA(ctx, launch_run<true>((const uint32_t*)d_seeds + off, nullptr, m, prm, (double*)d_out + off * prm.p,
+                                   dv.d_err, nullptr, (cudaStream_t)stream));
+    ctx->launches.fetch_add(1);
+  }
+  return JNE_OK;
+}
+
+int jne_check_async(jne_ctx* ctx) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  Device& dv = ctx->devs[0];
+  JNE_CUDA(ctx, cudaSetDevice(dv.id));
+  JNE_CUDA(ctx, cudaDeviceSynchronize());
+  unsigned int h = 0;
+  JNE_CUDA(ctx, cudaMemcpy(&h, dv.d_err, sizeof h, cudaMemcpyDeviceToHost));
+  JNE_CUDA(ctx, cudaMemset(dv.d_err, 0, sizeof h));
+  if (h) {
+    char b[128];
+    snprintf(b, sizeof b, "%u run(s) produced non-finite eigenvalues", h);
+    return fail(ctx, JNE_ERR_NONFINITE, b);
+  }
+  return JNE_OK;
+}
+
+static int single_device_run(jne_ctx* ctx, const JneRunParams& prm, const uint32_t* seeds, const double* dB,
+                             uint64_t n, double* out, double* mats) {
+  Device& dv = ctx->devs[0];
+  JNE_CUDA(ctx, cudaSetDevice(dv.id));
+  const bool rng = dB == nullptr;
+  const uint64_t per_run_in = rng ? 0 : (uint64_t)prm.dim * prm.steps;
+  // bound the scratch: <= 1 GiB of increments, <= 2^18 runs per launch
+  uint64_t chunk = kChunkRuns;
+  if (!rng) chunk = std::max<uint64_t>(1, std::min<uint64_t>(chunk, (1ull << 27) / std::max<uint64_t>(1, per_run_in)));
+  if (mats) chunk = std::min<uint64_t>(chunk, 1ull << 14);
+  const size_t in_bytes = rng ? chunk * sizeof(uint32_t) : chunk * per_run_in * sizeof(double);
+  const size_t out_bytes = chunk * prm.p * sizeof(double);
+  const size_t dbg_bytes = mats ? chunk * 512 * sizeof(double) : 0;
+  int rc = ensure_scratch(ctx, dv, in_bytes + out_bytes + dbg_bytes + 512);
+  if (rc) return rc;
+  char* base = (char*)dv.d_scratch;
+  double* d_out = (double*)base;
+  double* d_dbg = mats ? (double*)(base + out_bytes) : nullptr;
+  void* d_in = base + out_bytes + dbg_bytes;
+  JNE_CUDA(ctx, cudaMemsetAsync(dv.d_err, 0, sizeof(unsigned int), dv.stream));
+  for (uint64_t off = 0; off < n; off += chunk) {
+    const uint64_t m = std::min(chunk, n - off);
+    if (rng) {
+      JNE_CUDA(ctx, cudaMemcpyAsync(d_in, seeds + off, m * sizeof(uint32_t), cudaMemcpyHostToDevice, dv.stream));
+      JNE_CUDA(ctx, launch_run<true>((const uint32_t*)d_in, nullptr, m, prm, d_out, dv.d_err, d_dbg, dv.stream));
+    } else {
+      JNE_CUDA(ctx, cudaMemcpyAsync(d_in, dB + off * per_run_in, m * per_run_in * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
+      JNE_CUDA(ctx, launch_run<false>(nullptr, (const double*)d_in, m, prm, d_out, dv.d_err, d_dbg, dv.stream));
+    }
+    ctx->launches.fetch_add(1);
+    JNE_CUDA(ctx, cudaMemcpyAsync(out + off * prm.p, d_out, m * prm.p * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
+    if (mats) JNE_CUDA(ctx, cudaMemcpyAsync(mats + off * 512, d_dbg, m * 512 * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
+    JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+  }
+  JNE_CUDA(ctx, cudaMemcpyAsync(dv.h_err, dv.d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, dv.stream));
+  JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+  if (*dv.h_err) {
+    char b[128];
+    snprintf(b, sizeof b, "%u run(s) produced non-finite eigenvalues", *dv.h_err);
+    return fail(ctx, JNE_ERR_NONFINITE, b);
+  }
+  return JNE_OK;
+}
+
+int jne_eigs_from_increments(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, const double* dB, uint64_t n,
+                             double* out) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  join_worker(ctx);
+  int rc = validate(ctx, model, dim, steps);
+  if (rc) return rc;
+  if (n == 0) return JNE_OK;
+  if (!dB || !out) return fail(ctx, JNE_ERR_INVALID_ARG, "dB/out is NULL");
+  return single_device_run(ctx, make_params(model, dim, steps, true), nullptr, dB, n, out, nullptr);
+}
+
+int jne_eigs_batch_debug(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
+                         double* out, double* mats) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  join_worker(ctx);
+  int rc = validate(ctx, model, dim, steps);
+  if (rc) return rc;
+  if (n == 0) return JNE_OK;
+  if (!seeds || !out || !mats) return fail(ctx, JNE_ERR_INVALID_ARG, "seeds/out/mats is NULL");
+  return single_device_run(ctx, make_params(model, dim, steps, false), seeds, nullptr, n, out, mats);
+}
+
+int jne_gen_normal_matrix(jne_ctx* ctx, uint32_t dim, uint32_t steps, uint32_t seed, double* out) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  join_worker(ctx);
+  if (dim < 1 || steps < 1 || !out) return fail(ctx, JNE_ERR_INVALID_ARG, "dim/steps/out invalid");
+  if ((uint64_t)dim * steps > (1ull << 31)) return fail(ctx, JNE_ERR_INVALID_ARG, "Matrix too large");  // src/rng_matrix.rs:12
+  Device& dv = ctx->devs[0];
+  JNE_CUDA(ctx, cudaSetDevice(dv.id));
+  const size_t bytes = (size_t)dim * steps * sizeof(double);
+  int rc = ensure_scratch(ctx, dv, bytes);
+  if (rc) return rc;
+  const uint64_t items = (uint64_t)((steps + 3) / 4) * dim;
+  jne_normal_matrix_kernel<<<(unsigned)((items + 255) / 256), 256, 0, dv.stream>>>(seed, dim, steps, dv.d_scratch);
+  JNE_CUDA(ctx, cudaGetLastError());
+  ctx->launches.fetch_add(1);
+  JNE_CUDA(ctx, cudaMemcpyAsync(out, dv.d_scratch, bytes, cudaMemcpyDeviceToHost, dv.stream));
+  JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+  return JNE_OK;
+}
+
+int jne_brownian_motion_matrix(jne_ctx* ctx, uint32_t dim, uint32_t steps, double delta_t, uint32_t seed, double* out) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  join_worker(ctx);
+  if (dim < 1 || steps < 1 || !out) return fail(ctx, JNE_ERR_INVALID_ARG, "dim/steps/out invalid");
+  if ((uint64_t)dim * ((uint64_t)steps + 1) > (1ull << 31)) return fail(ctx, JNE_ERR_INVALID_ARG, "Matrix too large");
+  Device& dv = ctx->devs[0];
+  JNE_CUDA(ctx, cudaSetDevice(dv.id));
+  const size_t bytes = (size_t)dim * ((size_t)steps + 1) * sizeof(double);
+  int rc = ensure_scratch(ctx, dv, bytes);
+  if (rc) return rc;
+  jne_brownian_kernel<<<(dim + 31) / 32, 32, 0, dv.stream>>>(seed, dim, steps, delta_t, dv.d_scratch);
+  JNE_CUDA(ctx, cudaGetLastError());
+  ctx->launches.fetch_add(1);
+  JNE_CUDA(ctx, cudaMemcpyAsync(out, dv.d_scratch, bytes, cudaMemcpyDeviceToHost, dv.stream));
+  JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+  return JNE_OK;
+}
+
+int jne_pencil_eigs_batch(jne_ctx* ctx, uint32_t p, uint32_t d, const double* S1, const double* S2, uint64_t n,
+                          double* out) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  join_worker(ctx);
+  if (p < 1 || p > 16 || d < 1 || d > p) return fail(ctx, JNE_ERR_INVALID_ARG, "need 1 <= d <= p <= 16");
+  if (n == 0) return JNE_OK;
+  if (!S1 || !S2 || !out) return fail(ctx, JNE_ERR_INVALID_ARG, "S1/S2/out is NULL");
+  Device& dv = ctx->devs[0];
+  JNE_CUDA(ctx, cudaSetDevice(dv.id));
+  JNE_CUDA(ctx, cudaFuncSetAttribute(jne_pencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pencil_smem()));
+  const uint64_t chunk = 1ull << 16;
+  const size_t b1 = chunk * p * d * sizeof(double), b2 = chunk * p * p * sizeof(double), bo = chunk * p * sizeof(double);
+  int rc = ensure_scratch(ctx, dv, b1 + b2 + bo);
+  if (rc) return rc;
+  double* d1 = dv.d_scratch;
+  double* d2 = d1 + chunk * p * d;
+  double* dout = d2 + chunk * p * p;
+  JNE_CUDA(ctx, cudaMemsetAsync(dv.d_err, 0, sizeof(unsigned int), dv.stream));
+  for (uint64_t off = 0; off < n; off += chunk) {
+    const uint64_t m = std::min(chunk, n - off);
+    JNE_CUDA(ctx, cudaMemcpyAsync(d1, S1 + off * p * d, m * p * d * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
+    JNE_CUDA(ctx, cudaMemcpyAsync(d2, S2 + off * p * p, m * p * p * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
+    jne_pencil_kernel<<<(unsigned)((m + JNE_WARPS_PER_CTA - 1) / JNE_WARPS_PER_CTA), 32 * JNE_WARPS_PER_CTA, pencil_smem(), dv.stream>>>(
+        d1, d2, m, (int)p, (int)d, 1.0, dout, dv.d_err);
+    JNE_CUDA(ctx, cudaGetLastError());
+    ctx->launches.fetch_add(1);
+    JNE_CUDA(ctx, cudaMemcpyAsync(out + off * p, dout, m * p * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
+    JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+  }
+  JNE_CUDA(ctx, cudaMemcpyAsync(dv.h_err, dv.d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, dv.stream));
+  JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+  if (*dv.h_err) return fail(ctx, JNE_ERR_NONFINITE, "non-finite eigenvalues (S2 not positive definite?)");
+  return JNE_OK;
+}
+
+int jne_fp64_peak_tflops(jne_ctx* ctx, int mode, double ms_target, double* tflops) {
+  if (!ctx || !tflops) return JNE_ERR_INVALID_ARG;
+  join_worker(ctx);
+  Device& dv = ctx->devs[0];
+  JNE_CUDA(ctx, cudaSetDevice(dv.id));
+  cudaDeviceProp prop;
+  JNE_CUDA(ctx, cudaGetDeviceProperties(&prop, dv.id));
+  int rc = ensure_scratch(ctx, dv, 4096);
+  if (rc) return rc;
+  const int blocks = prop.multiProcessorCount * 2;
+  cudaEvent_t e0, e1;
+  JNE_CUDA(ctx, cudaEventCreate(&e0));
+  JNE_CUDA(ctx, cudaEventCreate(&e1));
+  auto launch = [&](int iters) {
+    if (mode == 0) fp64_peak_kernel<0><<<blocks, 256, 0, dv.stream>>>(iters, 1.0000001, dv.d_scratch);
+    else fp64_peak_kernel<1><<<blocks, 256, 0, dv.stream>>>(iters, 1.0000001, dv.d_scratch);
+    ctx->launches.fetch_add(1);
+  };
+  // flops per thread per iter: mode 0: 64 FMA; mode 1: 32 DMMA x 256 FMA / 32 lanes = 256 FMA
+  const double fma_per_thread_iter = mode == 0 ? 64.0 : 256.0;
+  int iters = mode == 0 ? 4000 : 1000;
+  launch(iters);  // warm-up + calibration
+  JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+  float ms = 0.f;
+  for (int rep = 0; rep < 2; ++rep) {
+    JNE_CUDA(ctx, cudaEventRecord(e0, dv.stream));
+    launch(iters);
+    JNE_CUDA(ctx, cudaEventRecord(e1, dv.stream));
+    JNE_CUDA(ctx, cudaEventSynchronize(e1));
+    JNE_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep == 0) iters = (int)std::max(1.0, std::min(2.0e6, iters * (ms_target / std::max(1e-3f, ms))));
+  }
+  JNE_CUDA(ctx, cudaGetLastError());
+  *tflops = 2.0 * fma_per_thread_iter * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return JNE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,510 @@
+// Device side of the Johansen null-eigenspectra hot path (sm_100a).
+//
+//   K1  jne_normals4            (jne_rng.cuh)  replaces gen_normal_matrix        src/rng_matrix.rs:11-37
+//   K2  jne_run_kernel main loop               replaces brownian_motion_matrix   src/rng_matrix.rs:57-141,
+//                                              dmatrix_cumsum RowWise            src/matrix_utils.rs:51-63,
+//                                              construct_f_matrix                src/johansen_statistics.rs:102-197,
+//                                              2 x sum_of_outer_products         src/matrix_utils.rs:67-85
+//   K3  jne_warp_pencil_solve                  replaces GeneralizedEigen::new + |alpha|/beta + sort
+//                                                                                src/johansen_statistics.rs:35-46
+//
+// One warp owns one run.  Lane (g = lane>>2, k = lane&3) owns Brownian rows g, g+8 of time
+// SEGMENT k (the T steps are cut into 4 contiguous segments, one per MMA k-slot), carries the
+// segment-local cumulative sum c in registers and feeds V = [F ; dB] straight into
+// mma.sync.m8n8k4.f64 fragments: for that shape the A fragment (row g, k) and the B fragment
+// (k, col g) are both "the lane's own value", so sum_t V V' needs no operand staging at all.
+// The deterministic regressors (1, tau, tau^2) never enter the MMA: their cross moments are
+// five FP64 FMAs per row and step, and demeaning / detrending is applied once per run as a
+// Schur complement in the epilogue (SURVEY.md section 7 hard part 4).  Segment-local sums are stitched
+// with the rank-one corrections of SURVEY.md section 5 ("long-context") in the epilogue.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "jne_rng.cuh"
+
+#define JNE_MAX_DIM 15           // p = dim+1 <= 16 fits one half-warp column per Jacobi pair slot
+#define JNE_WARPS_PER_CTA 4
+#define JNE_LD 17                // leading dimension of the 16x16 work matrices (bank-conflict padding)
+
+struct JneRunParams {
+  uint32_t dim;        // d
+  uint32_t steps;      // T
+  uint32_t seg_len;    // steps per segment, multiple of 4
+  uint32_t model;      // 0..4
+  uint32_t p;          // eigenvalues per run
+  uint32_t pad_;
+  double T;            // (double)steps
+  double factor;       // s^2 * T: 1 for the RNG path (s^2 = dt), T for caller-supplied increments
+  double seg_n[4];     // steps in segment k
+  double seg_w1[4];    // sum over segment k of w1_i = 2i + 1 - T
+  double seg_w2[4];    // sum over segment k of w2_i = 3 w1_i^2 - (T^2 - 1)
+};
+
+template <int DP> struct JneGeo {
+  static constexpr int A = DP / 8, B = DP % 8;
+  static constexpr int NRT = (DP + 7) / 8;       // row tiles == Brownian rows per lane
+  static constexpr int NCT = (2 * DP + 7) / 8;   // column tiles of V = [F ; dB]
+  static constexpr int NT = NRT * NCT - NRT * (NRT - 1) / 2;  // tiles (a, b >= a)
+  static constexpr int VV_LD = 8 * NCT + 1;
+  // per-warp shared memory, in doubles
+  static constexpr int VV_SZ = 8 * NRT * VV_LD;
+  static constexpr int VEC_SZ = 6 * 4 * 16;
+  static constexpr int MAT_SZ = 16 * JNE_LD;
+  static constexpr int MISC_SZ = 64;
+  static constexpr int WARP_SMEM = VV_SZ + VEC_SZ + 2 * MAT_SZ + MISC_SZ;
+};
+
+__device__ __forceinline__ void jne_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: eigenvalues of the pencil (S1'S1, S2) for one run, one warp.
+//   S2 : p x p symmetric positive definite, full storage, ld JNE_LD   (destroyed)
+//   R  : p x d  = S1' (row j = sum_t F_j dB_t'), ld JNE_LD               (destroyed)
+// Cholesky S2 = L L', W = L^-1 R, A = W W' (same eigenvalues as the pencil), cyclic two-sided
+// Jacobi with a round-robin parallel ordering (disjoint pairs rotate concurrently), then
+// lambda_i = factor * |a_ii| sorted descending (src/johansen_statistics.rs:40-45).
+// Returns false when a value is not finite (the reference panics at :45).
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, double* __restrict__ R,
+                                                   double* __restrict__ misc, int p, int d, double factor,
+                                                   double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  double* invd = misc;        // [16]
+  double* cs = misc + 16;     // [8][2]
+  double* ev = misc + 32;     // [16]
+
+  // --- Cholesky, right-looking, lower triangle in place ---
+  for (int j = 0; j < p; ++j) {
+    const double djj = S2[j * JNE_LD + j];
+    const double ljj = sqrt(djj);
+    const double inv = 1.0 / ljj;
+    __syncwarp();
+    if (lane == 0) invd[j] = inv;
+    for (int i = j + 1 + lane; i < p; i += 32) S2[i * JNE_LD + j] *= inv;
+    __syncwarp();
+    // trailing update of the lower triangle: rows i in (j, p), cols k in (j, i]
+    const int i = j + 1 + (lane & 15);
+    if (i < p) {
+      const double lij = S2[i * JNE_LD + j];
+      for (int kk = j + 1 + (lane >> 4); kk <= i; kk += 2)
+        S2[i * JNE_LD + kk] = fma(-lij, S2[kk * JNE_LD + j], S2[i * JNE_LD + kk]);
+    }
+    __syncwarp();
+  }
+  // --- W = L^-1 R : lane c solves column c by forward substitution ---
+  if (lane < d) {
+    for (int i = 0; i < p; ++i) {
+      double w = R[i * JNE_LD + lane];
+      for (int kk = 0; kk < i; ++kk) w = fma(-S2[i * JNE_LD + kk], R[kk * JNE_LD + lane], w);
+      R[i * JNE_LD + lane] = w * invd[i];
+    }
+  }
+  __syncwarp();
+  // --- A = W W' into the S2 storage (L is dead now); two rows per pass ---
+  double tr = 0.0;
+  for (int i0 = 0; i0 < p; i0 += 2) {
+    const int i = i0 + (lane >> 4), j = lane & 15;
+    if (i < p && j <= i) {
+      double a = 0.0;
+      for (int c = 0; c < d; ++c) a = fma(R[i * JNE_LD + c], R[j * JNE_LD + c], a);
+      if (i == j) tr += a;
+      // this phase only reads R and only writes S2 (L is dead), so the store needs no staging
+      S2[i * JNE_LD + j] = a;
+      S2[j * JNE_LD + i] = a;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
+  __syncwarp();
+  // --- cyclic Jacobi, round-robin ordering over n_even players ---
+  const int ne = (p + 1) & ~1;          // even number of players; index >= p is a bye
+  const int npairs = ne >> 1;
+  const double tol = fabs(tr) * 1.3877787807814457e-17;   // 2^-56 * trace (>= ||A||_F / sqrt(p) scale)
+  for (int sweep = 0; sweep < 24; ++sweep) {
+    int rotated = 0;
+    for (int step = 0; step < ne - 1; ++step) {
+      // pair `lane` of this step: player 0 fixed, others rotate (circle method)
+      if (lane < npairs) {
+        int a = (lane == 0) ? ne - 1 : (step + lane) % (ne - 1);
+        int b = (step + (ne - 1) - lane) % (ne - 1);
+        int pp = min(a, b), qq = max(a, b);
+        double c = 1.0, s = 0.0;
+        if (qq < p) {
+          const double apq = S2[pp * JNE_LD + qq];
+          if (fabs(apq) > tol) {
+            const double app = S2[pp * JNE_LD + pp], aqq = S2[qq * JNE_LD + qq];
+            const double theta = (aqq - app) / (2.0 * apq);
+            const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+            c = rsqrt(fma(t, t, 1.0));
+            s = t * c;
+            rotated = 1;
+          }
+        }
+        cs[2 * lane] = c;
+        cs[2 * lane + 1] = s;
+        ev[16 + lane] = __hiloint2double(pp, qq);   // pair indices, packed
+      }
+      __syncwarp();
+      // row phase: A <- J' A   (two pairs per pass: half-warp h handles pair 2*it+h, lane m a column)
+      for (int it = 0; it < npairs; it += 2) {
+        const int pr = it + (lane >> 4), m = lane & 15;
+        if (pr < npairs && m < p) {
+          const double pk = ev[16 + pr];
+          const int pp = __double2hiint(pk), qq = __double2loint(pk);
+          const double c = cs[2 * pr], s = cs[2 * pr + 1];
+          if (qq < p && s != 0.0) {
+            const double x = S2[pp * JNE_LD + m], y = S2[qq * JNE_LD + m];
+            S2[pp * JNE_LD + m] = fma(c, x, -s * y);
+            S2[qq * JNE_LD + m] = fma(s, x, c * y);
+          }
+        }
+      }
+      __syncwarp();
+      // column phase: A <- A J
+      for (int it = 0; it < npairs; it += 2) {
+        const int pr = it + (lane >> 4), m = lane & 15;
+        if (pr < npairs && m < p) {
+          const double pk = ev[16 + pr];
+          const int pp = __double2hiint(pk), qq = __double2loint(pk);
+          const double c = cs[2 * pr], s = cs[2 * pr + 1];
+          if (qq < p && s != 0.0) {
+            const double x = S2[m * JNE_LD + pp], y = S2[m * JNE_LD + qq];
+            S2[m * JNE_LD + pp] = fma(c, x, -s * y);
+            S2[m * JNE_LD + qq] = fma(s, x, c * y);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (!__any_sync(0xffffffffu, rotated)) break;
+  }
+  // --- eigenvalues = factor * |diag|, sorted descending by rank counting ---
+  double v = 0.0;
+  if (lane < p) {
+    v = fabs(S2[lane * JNE_LD + lane]) * factor;
+    ev[lane] = v;
+  }
+  __syncwarp();
+  bool finite = true;
+  if (lane < p) {
+    int rank = 0;
+    for (int j = 0; j < p; ++j) {
+      const double u = ev[j];
+      rank += (u > v) || (u == v && j < lane);
+    }
+    finite = isfinite(v);
+    if (!finite) rank = lane;   // NaN compares false everywhere: keep slots distinct
+    out[rank] = v;
+  }
+  return __all_sync(0xffffffffu, finite);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Assembly: raw segment moments (shared memory) -> per-model S2 (p x p) and R = S1' (p x d).
+//   VV  [8*NRT][VV_LD] : sum over segments and steps of V V', V = [c (DP rows) ; z (DP rows)]
+//   vec [6][4][16]     : per segment k and row r:  0 e = c_end, 1 s0 = sum c, 2 s1 = sum w1 c,
+//                        3 s2 = sum w2 c, 4 u1 = sum w1 z, 5 u2 = sum w2 z
+// F per model follows src/johansen_statistics.rs:102-197.  Row scalings of
+// F leave the pencil's eigenvalues unchanged, so the trend row is carried as (w1+1)/T
+// (= 2 (tau - 1/2)) and the detrended tau^2 row as w2/T^2 (= 12 x its residual on [1, tau]).
+// ---------------------------------------------------------------------------------------------
+template <int DP>
+__device__ __forceinline__ void jne_warp_assemble(const double* __restrict__ VV, const double* __restrict__ vec,
+                                                  double* __restrict__ S2, double* __restrict__ R,
+                                                  double* __restrict__ misc, const JneRunParams& prm) {
+  using G = JneGeo<DP>;
+  const int lane = threadIdx.x & 31;
+  const int d = prm.dim, model = prm.model, p = prm.p;
+  const double T = prm.T;
+  // whole-run totals live behind the 64 misc doubles (the caller reserves 7*16 more);
+  // the segment start values b0[k][r] are recomputed on the fly from e.
+  double* tot = misc + 64;
+  // tot[0]=S_B, [1]=S_1B, [2]=S_2B, [3]=S_z, [4]=S_1z, [5]=S_2z
+  if (lane < 16) {
+    const int r = lane;
+    double b0 = 0.0, sB = 0.0, s1B = 0.0, s2B = 0.0, sz = 0.0, s1z = 0.0, s2z = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double e = vec[(0 * 4 + k) * 16 + r];
+      sB += vec[(1 * 4 + k) * 16 + r] + prm.seg_n[k] * b0;
+      s1B += vec[(2 * 4 + k) * 16 + r] + prm.seg_w1[k] * b0;
+      s2B += vec[(3 * 4 + k) * 16 + r] + prm.seg_w2[k] * b0;
+      s1z += vec[(4 * 4 + k) * 16 + r];
+      s2z += vec[(5 * 4 + k) * 16 + r];
+      sz += e;
+      b0 += e;
+    }
+    tot[0 * 16 + r] = sB;  tot[1 * 16 + r] = s1B; tot[2 * 16 + r] = s2B;
+    tot[3 * 16 + r] = sz;  tot[4 * 16 + r] = s1z; tot[5 * 16 + r] = s2z;
+  }
+  __syncwarp();
+  const int nb = (model == 2 || model == 4) ? d - 1 : d;   // Brownian rows kept in F
+  const double invT = 1.0 / T;
+  const double nu = T * (T * T - 1.0) / 3.0;               // sum w1^2
+  const double inv_nu = 1.0 / nu;                          // inf at T = 1 (model 4 needs T >= 3)
+  // --- Brownian block: i, j < nb (S2) and i < nb, j < d (R); lane pairs (i = it*2 + half, j) ---
+  for (int i0 = 0; i0 < nb; i0 += 2) {
+    const int i = i0 + (lane >> 4), j = lane & 15;
+    if (i < nb) {
+      // segment start values and stitched raw moments
+      double bi = 0.0, bj = 0.0, mbb = 0.0, mbz = 0.0;
+      const bool jb = j < nb, jz = j < d;
+      if (jb) mbb = (i <= j) ? VV[i * G::VV_LD + j] : VV[j * G::VV_LD + i];
+      if (jz) mbz = VV[i * G::VV_LD + DP + j];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double ei = vec[(0 * 4 + k) * 16 + i], ej = vec[(0 * 4 + k) * 16 + j];
+        const double s0i = vec[(1 * 4 + k) * 16 + i], s0j = vec[(1 * 4 + k) * 16 + j];
+        mbb += prm.seg_n[k] * bi * bj + bi * s0j + s0i * bj;
+        mbz += bi * ej;
+        bi += ei; bj += ej;
+      }
+      const double SBi = tot[0 * 16 + i], S1Bi = tot[1 * 16 + i];
+      if (model >= 2) {   // demean (models 2,3,4)  src/johansen_statistics.rs:120-125,145-150,186-194
+        mbb -= SBi * tot[0 * 16 + j] * invT;
+        mbz -= SBi * tot[3 * 16 + j] * invT;
+      }
+      if (model == 4) {   // detrend: residual on [1, tau]   :186-194
+        mbb -= S1Bi * tot[1 * 16 + j] * inv_nu;
+        mbz -= S1Bi * tot[4 * 16 + j] * inv_nu;
+      }
+      if (jb) S2[i * JNE_LD + j] = mbb;
+      if (jz) R[i * JNE_LD + j] = mbz;
+    }
+  }
+  // --- deterministic row (index nb) ---
+  if (p > nb && lane < 16) {
+    const int j = lane;
+    double s2v = 0.0, rv = 0.0, dg = 0.0;
+    if (model == 1) {                 // constant row  :108-113
+      s2v = tot[0 * 16 + j];          // sum B_j
+      rv = tot[3 * 16 + j];           // sum dB_j
+      dg = T;
+    } else if (model == 2 || model == 3) {   // trend row (i+1)/T - 1/2 = (w1+1)/(2T)  :127-135,152-160
+      s2v = tot[1 * 16 + j] * invT;                   // sum (B_j - mean) (w1+1)/T = S_1B/T
+      rv = (tot[4 * 16 + j] + tot[3 * 16 + j]) * invT;
+      dg = (nu + T) * invT * invT;                    // sum (w1+1)^2 / T^2
+    } else if (model == 4) {          // tau^2 residual on [1, tau] = w2 / (12 T^2)  :170-194
+      s2v = tot[2 * 16 + j] * invT * invT;
+      rv = tot[5 * 16 + j] * invT * invT;
+      dg = 0.8 * T * (T * T - 1.0) * (T * T - 4.0) * invT * invT * invT * invT;   // sum w2^2 / T^4
+    }
+    if (j < nb) { S2[nb * JNE_LD + j] = s2v; S2[j * JNE_LD + nb] = s2v; }
+    if (j == nb) S2[nb * JNE_LD + nb] = dg;
+    if (j < d) R[nb * JNE_LD + j] = rv;
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused per-run kernel.  SRC_RNG: increments come from the Philox stream keyed by seeds[run];
+// otherwise from caller-supplied dB (n runs x (dim x steps) column-major per run, the layout of
+// src/rng_matrix.rs:36) and the path is rebuilt exactly as src/johansen_statistics.rs:80-82 does.
+// DET: 0 = models 0,1 (sum c only), 1 = models 2,3 (+ w1 moments), 2 = model 4 (+ w2 moments).
+// ---------------------------------------------------------------------------------------------
+template <int DP, int DET, bool SRC_RNG>
+__global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA)
+jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB, uint64_t n,
+               JneRunParams prm, double* __restrict__ out, unsigned int* __restrict__ err_count,
+               double* __restrict__ dbg /* optional: per run S2 (16x16) then R (16x16) */) {
+  using G = JneGeo<DP>;
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t run = (uint64_t)blockIdx.x * JNE_WARPS_PER_CTA + warp;
+  if (run >= n) return;
+  double* wsm = smem + (size_t)warp * (G::WARP_SMEM + 7 * 16);
+  double* VV = wsm;
+  double* vec = VV + G::VV_SZ;
+  double* S2 = vec + G::VEC_SZ;
+  double* R = S2 + G::MAT_SZ;
+  double* misc = R + G::MAT_SZ;     // 64 + 7*16 doubles
+
+  const int g = lane >> 2, k = lane & 3;
+  const uint32_t d = prm.dim, T = prm.steps;
+  const uint32_t t_begin = min((uint32_t)k * prm.seg_len, T);
+  const uint32_t t_end = min(T, t_begin + prm.seg_len);
+  const uint32_t seed = SRC_RNG ? seeds[run] : 0u;
+  const double* dBrun = SRC_RNG ? nullptr : dB + run * (uint64_t)d * T;
+
+  double c[G::NRT], s0[G::NRT], s1[G::NRT], s2[G::NRT], u1[G::NRT], u2[G::NRT];
+#pragma unroll
+  for (int j = 0; j < G::NRT; ++j) { c[j] = s0[j] = s1[j] = s2[j] = u1[j] = u2[j] = 0.0; }
+  double acc[G::NT][2];
+#pragma unroll
+  for (int i = 0; i < G::NT; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+
+  double w1 = 2.0 * (double)t_begin + 1.0 - prm.T;
+  const double w2c = -(prm.T * prm.T - 1.0);
+  const int src_lane = (((g - G::B) & 7) << 2) | k;
+
+  for (uint32_t t = t_begin; t < t_begin + prm.seg_len; t += 4) {
+    double z[G::NRT][4];
+#pragma unroll
+    for (int j = 0; j < G::NRT; ++j) {
+      const uint32_t row = 8 * j + g;
+      if (SRC_RNG) {
+        float zf[4] = {0.f, 0.f, 0.f, 0.f};
+        if (row < d) jne_normals4(seed, row, t >> 2, zf);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) z[j][s] = (double)zf[s];
+      } else {
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          z[j][s] = (row < d && t + s < t_end) ? dBrun[(uint64_t)(t + s) * d + row] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const bool active = (t + s) < t_end;
+      double f[G::NRT], dz[G::NRT], cn[G::NRT];
+#pragma unroll
+      for (int j = 0; j < G::NRT; ++j) {
+        f[j] = active ? c[j] : 0.0;
+        dz[j] = active ? z[j][s] : 0.0;
+        cn[j] = c[j] + dz[j];                  // B_t = B_{t-1} + dB_t   (src/matrix_utils.rs:51-63)
+        if (!SRC_RNG) dz[j] = cn[j] - c[j];    // dB re-derived by subtraction (src/johansen_statistics.rs:80-82)
+      }
+      // V tiles: index i = 8*jt + g;  i < DP -> F_i (own), DP <= i < 2DP -> dB_{i-DP} (shuffled)
+      double V[G::NCT];
+#pragma unroll
+      for (int jt = 0; jt < G::NCT; ++jt) {
+        double own = (jt < G::NRT) ? f[jt < G::NRT ? jt : 0] : 0.0;
+        double recv = 0.0;
+        if (jt >= G::A) {
+          if (G::B == 0) {
+            recv = (jt - G::A < G::NRT) ? dz[(jt - G::A < G::NRT) ? jt - G::A : 0] : 0.0;
+          } else {
+            // sender side: lanes g' <= 7-B serve slot jt-A, lanes g' >= 8-B serve slot jt-A-1
+            const int ja = jt - G::A, jb = jt - G::A - 1;
+            const double va = (ja >= 0 && ja < G::NRT) ? dz[(ja >= 0 && ja < G::NRT) ? ja : 0] : 0.0;
+            const double vb = (jb >= 0 && jb < G::NRT) ? dz[(jb >= 0 && jb < G::NRT) ? jb : 0] : 0.0;
+            const double send = (g <= 7 - G::B) ? va : vb;
+            recv = __shfl_sync(0xffffffffu, send, src_lane);
+          }
+        }
+        const int i = 8 * jt + g;
+        V[jt] = (i < DP) ? own : ((i < 2 * DP) ? recv : 0.0);
+      }
+      int ti = 0;
+#pragma unroll
+      for (int a = 0; a < G::NRT; ++a)
+#pragma unroll
+        for (int b = a; b < G::NCT; ++b) {
+          jne_dmma(acc[ti][0], acc[ti][1], V[a], V[b]);
+          ++ti;
+        }
+      // deterministic cross moments and the running path
+      double w2 = 0.0;
+      if (DET >= 2) w2 = fma(3.0 * w1, w1, w2c);
+#pragma unroll
+      for (int j = 0; j < G::NRT; ++j) {
+        s0[j] += f[j];
+        if (DET >= 1) { s1[j] = fma(w1, f[j], s1[j]); u1[j] = fma(w1, dz[j], u1[j]); }
+        if (DET >= 2) { s2[j] = fma(w2, f[j], s2[j]); u2[j] = fma(w2, dz[j], u2[j]); }
+        c[j] = cn[j];
+      }
+      w1 += 2.0;
+    }
+  }
+
+  // ---- dump raw moments to the warp's shared memory ----
+  {
+    int ti = 0;
+#pragma unroll
+    for (int a = 0; a < G::NRT; ++a)
+#pragma unroll
+      for (int b = a; b < G::NCT; ++b) {
+        VV[(8 * a + g) * G::VV_LD + 8 * b + 2 * k] = acc[ti][0];
+        VV[(8 * a + g) * G::VV_LD + 8 * b + 2 * k + 1] = acc[ti][1];
+        ++ti;
+      }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int r = 8 * j + g;
+      const bool has = j < G::NRT;
+      vec[(0 * 4 + k) * 16 + r] = has ? c[has ? j : 0] : 0.0;
+      vec[(1 * 4 + k) * 16 + r] = has ? s0[has ? j : 0] : 0.0;
+      vec[(2 * 4 + k) * 16 + r] = has ? s1[has ? j : 0] : 0.0;
+      vec[(3 * 4 + k) * 16 + r] = has ? s2[has ? j : 0] : 0.0;
+      vec[(4 * 4 + k) * 16 + r] = has ? u1[has ? j : 0] : 0.0;
+      vec[(5 * 4 + k) * 16 + r] = has ? u2[has ? j : 0] : 0.0;
+    }
+  }
+  __syncwarp();
+  jne_warp_assemble<DP>(VV, vec, S2, R, misc, prm);
+  if (dbg != nullptr) {
+    double* o = dbg + run * 512;
+    for (int e = lane; e < 256; e += 32) {
+      const int i = e >> 4, j = e & 15;
+      o[e] = (i < (int)prm.p && j < (int)prm.p) ? S2[i * JNE_LD + j] : 0.0;
+      o[256 + e] = (i < (int)prm.p && j < (int)d) ? R[i * JNE_LD + j] : 0.0;
+    }
+    __syncwarp();
+  }
+  const bool ok = jne_warp_pencil_solve(S2, R, misc, prm.p, d, prm.factor, out + run * prm.p);
+  if (!ok && lane == 0) atomicAdd(err_count, 1u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Standalone K3: batched pencil solve on caller-supplied matrices (parity with dggev, the routine
+// behind GeneralizedEigen::new at src/johansen_statistics.rs:35-38).
+//   S1 : n x (d x p) column-major per problem  (== p x d row-major S1')
+//   S2 : n x (p x p) symmetric
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA)
+jne_pencil_kernel(const double* __restrict__ S1, const double* __restrict__ S2in, uint64_t n, int p, int d,
+                  double factor, double* __restrict__ out, unsigned int* __restrict__ err_count) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t run = (uint64_t)blockIdx.x * JNE_WARPS_PER_CTA + warp;
+  if (run >= n) return;
+  double* S2 = smem + (size_t)warp * (2 * 16 * JNE_LD + 64);
+  double* R = S2 + 16 * JNE_LD;
+  double* misc = R + 16 * JNE_LD;
+  for (int e = lane; e < p * p; e += 32) S2[(e / p) * JNE_LD + (e % p)] = S2in[run * p * p + e];
+  for (int e = lane; e < p * d; e += 32) R[(e / d) * JNE_LD + (e % d)] = S1[run * p * d + e];
+  __syncwarp();
+  const bool ok = jne_warp_pencil_solve(S2, R, misc, p, d, factor, out + run * p);
+  if (!ok && lane == 0) atomicAdd(err_count, 1u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exposed pieces of the stream (parity with the reference's RNG / Brownian tests).
+//   jne_normal_matrix_kernel : gen_normal_matrix(nrows = d, ncols = T, seed)   src/rng_matrix.rs:11-37
+//   jne_brownian_kernel      : brownian_motion_matrix(..., AlongColumns, 0)    src/rng_matrix.rs:57-141
+// Output column-major d x T (resp. d x (T+1)), like DMatrix::from_vec.
+// ---------------------------------------------------------------------------------------------
+__global__ void jne_normal_matrix_kernel(uint32_t seed, uint32_t d, uint32_t T, double* __restrict__ out) {
+  const uint32_t nb = (T + 3) / 4;
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (uint64_t)nb * d) return;
+  const uint32_t row = idx % d, tb = idx / d;
+  float z[4];
+  jne_normals4(seed, row, tb, z);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const uint32_t t = 4 * tb + s;
+    if (t < T) out[(uint64_t)t * d + row] = (double)z[s];
+  }
+}
+
+// One thread per row: sequential left-to-right cumsum of sqrt(dt) * z (src/matrix_utils.rs:51-63).
+__global__ void jne_brownian_kernel(uint32_t seed, uint32_t d, uint32_t T, double delta_t, double* __restrict__ out) {
+  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= d) return;
+  const double sq = sqrt(delta_t);
+  double acc = 0.0;
+  out[row] = acc;
+  for (uint32_t tb = 0; tb < (T + 3) / 4; ++tb) {
+    float z[4];
+    jne_normals4(seed, row, tb, z);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const uint32_t t = 4 * tb + s;
+      if (t < T) { acc += (double)z[s] * sq; out[(uint64_t)(t + 1) * d + row] = acc; }
+    }
+  }
+}

@@ -1,0 +1,56 @@
+// Counter-based Gaussian stream, in registers (sm_100a).
+//
+// Replaces gen_normal_matrix (reference src/rng_matrix.rs:11-37: per-chunk Xoshiro256++ +
+// ziggurat StandardNormal, whose stream depends on the machine's physical core count,
+// :16-20).  Here element (row r, step t) of the d x T normal matrix is a pure function of
+// (seed, r, t):   Philox4x32-10(key = (seed, JNE_KEY1), ctr = (t >> 2, r, 0, 0))
+// yields four 32-bit words; words (0,1) -> Box-Muller pair for steps 4b, 4b+1 and words
+// (2,3) -> steps 4b+2, 4b+3.  The stream does not depend on model, dim, batch size, GPU
+// count or launch geometry (SURVEY.md section 8b "semantics that must hold").
+//
+// Pipes (measured, profiles/r1_microbench_pipes.txt): IMAD.WIDE 32 lanes/clk/SM, MUFU 16,
+// F2F.F64.F32 16; FP64 37.0 TFLOP/s.  The transform therefore stays in FP32 + MUFU and never
+// touches the FP64 pipe until the final widening.
+#pragma once
+#include <cstdint>
+
+#define JNE_KEY1 0x4A4E4531u  // "JNE1"
+
+struct jne_u4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ jne_u4 jne_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                    uint32_t k0, uint32_t k1) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0;
+    const uint64_t p1 = (uint64_t)M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ (k0 + (uint32_t)r * W0);
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ (k1 + (uint32_t)r * W1);
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+  }
+  return jne_u4{c0, c1, c2, c3};
+}
+
+// Two N(0,1) variates from two 32-bit words.  u = (wa + 1/2) 2^-32 in (0, 1], radius
+// r = sqrt(-2 ln u) <= 6.76; angle theta = 2 pi * int32(wb) * 2^-32 in [-pi, pi) so the MUFU
+// sin/cos see their most accurate range.
+__device__ __forceinline__ void jne_box_muller(uint32_t wa, uint32_t wb, float& z0, float& z1) {
+  const float u = fmaf(__uint2float_rn(wa), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float l = __log2f(u);                        // MUFU.LG2
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -1.3862943611198906f));  // MUFU.SQRT
+  const float th = __int2float_rn((int)wb) * 1.4629180792671596e-9f;  // 2 pi 2^-32
+  z0 = r * __cosf(th);
+  z1 = r * __sinf(th);
+}
+
+// The four normals of (row, time block tb = t >> 2) for one seed.
+__device__ __forceinline__ void jne_normals4(uint32_t seed, uint32_t row, uint32_t tb, float z[4]) {
+  const jne_u4 w = jne_philox4x32_10(tb, row, 0u, 0u, seed, JNE_KEY1);
+  jne_box_muller(w.x, w.y, z[0], z[1]);
+  jne_box_muller(w.z, w.w, z[2], z[3]);
+}
