@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- Monte Carlo runs/s of the Johansen null-eigenspectra hot path on B200.
+
+Workload (BASELINE.json metric: "Monte Carlo runs/sec at dim=12 T=10k (models 0-4)"): one STEP is
+one pass of the hot path over one batch of synthetic input = `--runs` seeds for EACH of the five
+models at dim 12, T 10 000 (five kernel launches).  A run is defined by (model, dim, steps, seed);
+there is no other input data.
+
+  value        device-resident: seeds and eigenvalue buffers live in HBM, launches go on torch's
+               current stream, timed with CUDA events, max over ranks
+  e2e          the same work through the public host-buffer API (jne_eigs_batch): seeds H2D and
+               eigenvalues D2H inside the timed region
+  roofline     FP64: F_alg = 2 T [p(p+1)/2 + p d] flop per run x runs per launch /
+               average launch duration (CUDA events around each launch), over the measured FP64 peak
+  cpu_baseline the CPU restatement of the reference path (oracle/jne_oracle.c, "port": the Rust
+               crate cannot be built in this image) on all host cores, bounded sample
+  --impl reference   times that CPU port instead (rank 0 only)
+
+Multi-GPU: one process per GPU under torchrun; ranks take disjoint seed ranges (weak scaling), no
+collective on the data path; torch.distributed only for the barrier and the max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "Monte Carlo runs/sec at dim=12 T=10k (models 0-4)"
+MODELS = (0, 1, 2, 3, 4)
+NOMINAL_FP64_TFLOPS = 37.2   # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5, help="timed steps K")
+    ap.add_argument("--warmup", type=int, default=3, help="untimed warm-up steps W")
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--dim", type=int, default=12)
+    ap.add_argument("--T", type=int, default=10000, help="time steps per run (the reference's --steps)")
+    ap.add_argument("--runs", type=int, default=1 << 17, help="runs per model per step per GPU")
+    ap.add_argument("--cpu-runs", type=int, default=0, help="CPU sample: runs per model (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(dim, T, runs_per_model, threads):
+    """Times the CPU port of the reference path (all five models).  Returns (runs/s, total runs, seconds)."""
+    from oracle import c_oracle
+    lib = c_oracle.load()
+    ncpu = c_oracle.physical_cores()
+    seeds = np.arange(1, runs_per_model + 1, dtype=np.uint32)
+    t0 = time.perf_counter()
+    for m in MODELS:
+        c_oracle.eigs_batch(lib, m, dim, T, seeds, threads, ncpu)
+    dt = time.perf_counter() - t0
+    return len(MODELS) * runs_per_model / dt, len(MODELS) * runs_per_model, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path, on the host cores.
+    The Rust crate cannot be built here (no cargo/rustc, un-vendored git dependencies, no system LAPACK), so this is
+    the C port oracle/jne_oracle.c (cpu_baseline.kind = "port")."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    runs = args.cpu_runs or max(threads * 4, 64)
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_rate(args.dim, args.T, max(threads, 8), threads)
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        _, n, _ = cpu_reference_rate(args.dim, args.T, runs, threads)
+        total += n
+    dt = time.perf_counter() - t0
+    value = total / dt
+    sample = f"{runs} runs x 5 models per step, dim {args.dim}, T {args.T}, seeds 1..{runs}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "runs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"models 0-4, dim {args.dim}, T {args.T}, CPU port of the reference path, {threads} threads"},
+        "cpu_baseline": {"value": value, "unit": "runs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "runs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import johansen_null_eigenspectra_b200 as jne
+    from johansen_null_eigenspectra_b200.sharding import weak_scaling_seeds
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng = jne.Engine([local_rank])
+    dim, T, R = args.dim, args.T, args.runs
+    stream = torch.cuda.current_stream()
+    seeds_np = weak_scaling_seeds(R, world, rank)          # disjoint seed ranges per rank
+    d_seeds = torch.from_numpy(seeds_np.astype(np.int64)).to(torch.int32).cuda()
+    d_out = {m: torch.empty((R, jne.num_eigs(m, dim)), dtype=torch.float64, device="cuda") for m in MODELS}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    flops_step = sum(jne.flops_per_run(m, dim, T) for m in MODELS) * R
+
+    ev_pairs = []
+
+    def device_step(record):
+        flush.zero_()                                      # L2 flush between steps
+        for m in MODELS:
+            if record:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            eng.eigs_batch_device(m, dim, T, d_seeds.data_ptr(), R, d_out[m].data_ptr(), stream.cuda_stream)
+            if record:
+                e1.record(stream)
+                ev_pairs.append((m, e0, e1))
+
+    # FP64 roofline denominator: measured here (MEASURED_PEAKS.json carries no FP64 figure)
+    peak_dfma = eng.fp64_peak_tflops(0, 300.0)
+    peak_dmma = eng.fp64_peak_tflops(1, 300.0)
+    peak = max(peak_dfma, peak_dmma)
+
+    for _ in range(args.warmup):
+        device_step(False)
+    eng.check_async()
+    launches0 = eng.launch_count
+    barrier()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        t_start.record(stream)
+        for _ in range(args.steps):
+            device_step(True)
+        t_end.record(stream)
+        barrier()
+    gpu_launches = eng.launch_count - launches0 + args.steps   # + the L2-flush memset per step
+    eng.check_async()
+    ms = t_start.elapsed_time(t_end)
+    kern_ms = {m: [] for m in MODELS}
+    for m, e0, e1 in ev_pairs:
+        kern_ms[m].append(e0.elapsed_time(e1))
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_runs = len(MODELS) * R * args.steps * world
+    value = total_runs / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers through the public API (H2D seeds + D2H eigenvalues inside) ----
+    for m in MODELS[:1]:
+        eng.eigs_batch(m, dim, T, seeds_np[: min(R, 4096)])
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        for m in MODELS:
+            out = eng.eigs_batch(m, dim, T, seeds_np)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_runs / float(te.item())
+    h2d = 4 * R * len(MODELS)
+    d2h = 8 * R * sum(jne.num_eigs(m, dim) for m in MODELS)
+
+    if rank == 0:
+        # dominant kernel = the fused per-run kernel; report the launch mix of the step (all five models)
+        dur_ms = sum(float(np.mean(kern_ms[m])) for m in MODELS)
+        achieved = flops_step / (dur_ms * 1e-3) / 1e12
+        per_model = {str(m): round(jne.flops_per_run(m, dim, T) * R / (float(np.mean(kern_ms[m])) * 1e-3) / 1e12, 3)
+                     for m in MODELS}
+        traffic = None
+        tfile = ROOT / "profiles" / "traffic_bytes_per_launch.json"
+        if tfile.exists():
+            try:
+                traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": "runs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"models 0-4, dim {dim}, T {T}, {R} runs per model per step per GPU, seeds {int(seeds_np[0])}..",
+                "runs_per_step": len(MODELS) * R * world, "rng": "philox4x32-10 + box-muller, in registers",
+                "l2": "256 MiB buffer written between steps (inputs are 4 B per run; the path is FP64-bound)",
+                "parallelism": f"seed-sharded x{world}, no collective",
+            },
+            "roofline": {
+                "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic,
+                "peak_source": "measured in this run: register-resident DFMA / DMMA m8n8k4 chains (jne_fp64_peak_tflops); "
+                               "MEASURED_PEAKS.json holds no FP64 figure",
+                "peak_dfma": peak_dfma, "peak_dmma": peak_dmma, "peak_nominal": NOMINAL_FP64_TFLOPS,
+                "kernel": "jne_run_kernel<12,*,rng>", "flops_per_launch": flops_step / len(MODELS),
+                "achieved_per_model": per_model,
+                "kernel_share_of_step": dur_ms * args.steps / ms * 1.0 if ms > 0 else None,
+            },
+            "e2e": {"value": e2e_value, "unit": "runs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(gpu_launches),
+            "clocks": clocks.summary(),
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            runs = args.cpu_runs or max(threads * 16, 128)
+            cpu_value, n_cpu, cpu_s = cpu_reference_rate(dim, T, runs, threads)
+            line["cpu_baseline"] = {
+                "value": cpu_value, "unit": "runs/s", "cores": threads, "kind": "port",
+                "sample": f"{runs} runs x 5 models, dim {dim}, T {T}, {cpu_s:.1f} s on {threads} threads "
+                          "(C port of the reference path incl. xoshiro256++/ziggurat and LAPACK dggev)",
+            }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

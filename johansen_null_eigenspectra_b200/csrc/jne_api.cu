@@ -105,17 +105,20 @@ JneRunParams make_params(uint8_t model, uint32_t dim, uint32_t steps, bool from_
   p.seg_len = 4u * ((steps + 15u) / 16u);
   p.T = (double)steps;
   p.factor = from_increments ? (double)steps : 1.0;
+  uint64_t full = p.seg_len / 4;
   for (int k = 0; k < 4; ++k) {
     const uint64_t a = std::min<uint64_t>((uint64_t)k * p.seg_len, steps);
     const uint64_t b = std::min<uint64_t>(a + p.seg_len, steps);
     p.seg_n[k] = (double)(b - a);
+    full = std::min<uint64_t>(full, (b - a) / 4);
     segment_weights(a, b, steps, &p.seg_w1[k], &p.seg_w2[k]);
   }
+  p.full_blocks = (uint32_t)full;
   return p;
 }
 
 template <int DP> constexpr size_t cta_smem() {
-  return (size_t)JNE_WARPS_PER_CTA * (JneGeo<DP>::WARP_SMEM + 7 * 16) * sizeof(double);
+  return (size_t)JNE_WARPS_PER_CTA * JneGeo<DP>::WARP_SMEM * sizeof(double);
 }
 constexpr size_t pencil_smem() { return (size_t)JNE_WARPS_PER_CTA * (2 * 16 * JNE_LD + 64) * sizeof(double); }
 

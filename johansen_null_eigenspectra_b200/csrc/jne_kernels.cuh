@@ -32,7 +32,7 @@ struct JneRunParams {
   uint32_t seg_len;    // steps per segment, multiple of 4
   uint32_t model;      // 0..4
   uint32_t p;          // eigenvalues per run
-  uint32_t pad_;
+  uint32_t full_blocks;  // leading 4-step blocks that are inside the segment for every lane
   double T;            // (double)steps
   double factor;       // s^2 * T: 1 for the RNG path (s^2 = dt), T for caller-supplied increments
   double seg_n[4];     // steps in segment k
@@ -51,7 +51,10 @@ template <int DP> struct JneGeo {
   static constexpr int VEC_SZ = 6 * 4 * 16;
   static constexpr int MAT_SZ = 16 * JNE_LD;
   static constexpr int MISC_SZ = 64;
-  static constexpr int WARP_SMEM = VV_SZ + VEC_SZ + 2 * MAT_SZ + MISC_SZ;
+  static constexpr int TOT_SZ = 7 * 16;
+  static constexpr int RAW_SZ = VV_SZ + VEC_SZ + TOT_SZ;          // raw segment moments ...
+  static constexpr int WORK_SZ = 2 * MAT_SZ + MISC_SZ;            // ... aliased by the solver workspace
+  static constexpr int WARP_SMEM = RAW_SZ > WORK_SZ ? RAW_SZ : WORK_SZ;
 };
 
 __device__ __forceinline__ void jne_dmma(double& c0, double& c1, double a, double b) {
@@ -207,21 +210,20 @@ __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, doub
 //   VV  [8*NRT][VV_LD] : sum over segments and steps of V V', V = [c (DP rows) ; z (DP rows)]
 //   vec [6][4][16]     : per segment k and row r:  0 e = c_end, 1 s0 = sum c, 2 s1 = sum w1 c,
 //                        3 s2 = sum w2 c, 4 u1 = sum w1 z, 5 u2 = sum w2 z
+//   tot [7][16]        : whole-run totals (scratch)
+// S2 / R ALIAS the raw area: every entry is first computed into registers, then, after a warp
+// barrier, stored -- this halves the shared memory per warp and doubles the resident warps.
 // F per model follows src/johansen_statistics.rs:102-197.  Row scalings of
 // F leave the pencil's eigenvalues unchanged, so the trend row is carried as (w1+1)/T
 // (= 2 (tau - 1/2)) and the detrended tau^2 row as w2/T^2 (= 12 x its residual on [1, tau]).
 // ---------------------------------------------------------------------------------------------
 template <int DP>
-__device__ __forceinline__ void jne_warp_assemble(const double* __restrict__ VV, const double* __restrict__ vec,
-                                                  double* __restrict__ S2, double* __restrict__ R,
-                                                  double* __restrict__ misc, const JneRunParams& prm) {
+__device__ __forceinline__ void jne_warp_assemble(const double* VV, const double* vec, double* tot,
+                                                  double* S2, double* R, const JneRunParams& prm) {
   using G = JneGeo<DP>;
   const int lane = threadIdx.x & 31;
   const int d = prm.dim, model = prm.model, p = prm.p;
   const double T = prm.T;
-  // whole-run totals live behind the 64 misc doubles (the caller reserves 7*16 more);
-  // the segment start values b0[k][r] are recomputed on the fly from e.
-  double* tot = misc + 64;
   // tot[0]=S_B, [1]=S_1B, [2]=S_2B, [3]=S_z, [4]=S_1z, [5]=S_2z
   if (lane < 16) {
     const int r = lane;
@@ -245,12 +247,16 @@ __device__ __forceinline__ void jne_warp_assemble(const double* __restrict__ VV,
   const double invT = 1.0 / T;
   const double nu = T * (T * T - 1.0) / 3.0;               // sum w1^2
   const double inv_nu = 1.0 / nu;                          // inf at T = 1 (model 4 needs T >= 3)
-  // --- Brownian block: i, j < nb (S2) and i < nb, j < d (R); lane pairs (i = it*2 + half, j) ---
-  for (int i0 = 0; i0 < nb; i0 += 2) {
-    const int i = i0 + (lane >> 4), j = lane & 15;
+  // --- Brownian block: entry (i = 2q + half, j = lane & 15), kept in registers ---
+  constexpr int NQ = (DP + 1) / 2;
+  double r_bb[NQ], r_bz[NQ];
+  const int j = lane & 15;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int i = 2 * q + (lane >> 4);
+    double mbb = 0.0, mbz = 0.0;
     if (i < nb) {
-      // segment start values and stitched raw moments
-      double bi = 0.0, bj = 0.0, mbb = 0.0, mbz = 0.0;
+      double bi = 0.0, bj = 0.0;
       const bool jb = j < nb, jz = j < d;
       if (jb) mbb = (i <= j) ? VV[i * G::VV_LD + j] : VV[j * G::VV_LD + i];
       if (jz) mbz = VV[i * G::VV_LD + DP + j];
@@ -271,14 +277,13 @@ __device__ __forceinline__ void jne_warp_assemble(const double* __restrict__ VV,
         mbb -= S1Bi * tot[1 * 16 + j] * inv_nu;
         mbz -= S1Bi * tot[4 * 16 + j] * inv_nu;
       }
-      if (jb) S2[i * JNE_LD + j] = mbb;
-      if (jz) R[i * JNE_LD + j] = mbz;
     }
+    r_bb[q] = mbb;
+    r_bz[q] = mbz;
   }
-  // --- deterministic row (index nb) ---
+  // --- deterministic row (index nb), lanes 0..15 ---
+  double s2v = 0.0, rv = 0.0, dg = 0.0;
   if (p > nb && lane < 16) {
-    const int j = lane;
-    double s2v = 0.0, rv = 0.0, dg = 0.0;
     if (model == 1) {                 // constant row  :108-113
       s2v = tot[0 * 16 + j];          // sum B_j
       rv = tot[3 * 16 + j];           // sum dB_j
@@ -292,11 +297,100 @@ __device__ __forceinline__ void jne_warp_assemble(const double* __restrict__ VV,
       rv = tot[5 * 16 + j] * invT * invT;
       dg = 0.8 * T * (T * T - 1.0) * (T * T - 4.0) * invT * invT * invT * invT;   // sum w2^2 / T^4
     }
+  }
+  __syncwarp();   // all reads of the raw area are done: S2 / R may now overwrite it
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int i = 2 * q + (lane >> 4);
+    if (i < nb) {
+      if (j < nb) S2[i * JNE_LD + j] = r_bb[q];
+      if (j < d) R[i * JNE_LD + j] = r_bz[q];
+    }
+  }
+  if (p > nb && lane < 16) {
     if (j < nb) { S2[nb * JNE_LD + j] = s2v; S2[j * JNE_LD + nb] = s2v; }
     if (j == nb) S2[nb * JNE_LD + nb] = dg;
     if (j < d) R[nb * JNE_LD + j] = rv;
   }
   __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// One block of 4 consecutive steps of the lane's segment: generate / load the increments, feed the
+// MMAs, update the path and the deterministic cross moments.  MASKED blocks (only the ragged tail
+// of the last segment, or tiny T) zero the contributions of steps at or beyond t_end.
+// ---------------------------------------------------------------------------------------------
+template <int DP, int DET, bool SRC_RNG, bool MASKED>
+__device__ __forceinline__ void jne_block4(uint32_t t, uint32_t t_end, uint32_t d, int g, int src_lane,
+                                           const jne_keys& keys, const double* __restrict__ dBrun,
+                                           double (&c)[JneGeo<DP>::NRT], double (&s0)[JneGeo<DP>::NRT],
+                                           double (&s1)[JneGeo<DP>::NRT], double (&s2)[JneGeo<DP>::NRT],
+                                           double (&u1)[JneGeo<DP>::NRT], double (&u2)[JneGeo<DP>::NRT],
+                                           double (&acc)[JneGeo<DP>::NT][2], double& w1, double w2c) {
+  using G = JneGeo<DP>;
+  double z[G::NRT][4];
+#pragma unroll
+  for (int j = 0; j < G::NRT; ++j) {
+    const uint32_t row = 8 * j + g;
+    if (SRC_RNG) {
+      float zf[4] = {0.f, 0.f, 0.f, 0.f};
+      if (row < d) jne_normals4_keyed(keys, row, t >> 2, zf);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) z[j][s] = (double)zf[s];
+    } else {
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        z[j][s] = (row < d && (!MASKED || t + s < t_end)) ? dBrun[(uint64_t)(t + s) * d + row] : 0.0;
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const bool active = !MASKED || (t + s) < t_end;
+    double f[G::NRT], dz[G::NRT], cn[G::NRT];
+#pragma unroll
+    for (int j = 0; j < G::NRT; ++j) {
+      f[j] = active ? c[j] : 0.0;
+      dz[j] = active ? z[j][s] : 0.0;
+      cn[j] = c[j] + dz[j];                  // B_t = B_{t-1} + dB_t   (src/matrix_utils.rs:51-63)
+      if (!SRC_RNG) dz[j] = cn[j] - c[j];    // dB re-derived by subtraction (src/johansen_statistics.rs:80-82)
+    }
+    // V tiles: index i = 8*jt + g;  i < DP -> F_i (own);  DP <= i < 2DP -> dB_{i-DP}, owned by lane
+    // g' = (g - B) & 7 in its slot jt-A (receivers g >= B) or jt-A-1 (receivers g < B).  Every lane
+    // publishes each of its increments once; the receiver picks.
+    double recv[G::NRT];
+#pragma unroll
+    for (int m = 0; m < G::NRT; ++m) recv[m] = (G::B == 0) ? dz[m] : __shfl_sync(0xffffffffu, dz[m], src_lane);
+    double V[G::NCT];
+#pragma unroll
+    for (int jt = 0; jt < G::NCT; ++jt) {
+      const int i = 8 * jt + g;
+      const int ja = jt - G::A, jb = jt - G::A - 1;
+      const double ra = (ja >= 0 && ja < G::NRT) ? recv[(ja >= 0 && ja < G::NRT) ? ja : 0] : 0.0;
+      const double rb = (jb >= 0 && jb < G::NRT) ? recv[(jb >= 0 && jb < G::NRT) ? jb : 0] : 0.0;
+      const double r = (G::B == 0 || g >= G::B) ? ra : rb;
+      const double own = (jt < G::NRT) ? f[jt < G::NRT ? jt : 0] : 0.0;
+      V[jt] = (i < DP) ? own : ((i < 2 * DP) ? r : 0.0);
+    }
+    int ti = 0;
+#pragma unroll
+    for (int a = 0; a < G::NRT; ++a)
+#pragma unroll
+      for (int b = a; b < G::NCT; ++b) {
+        jne_dmma(acc[ti][0], acc[ti][1], V[a], V[b]);
+        ++ti;
+      }
+    // deterministic cross moments and the running path
+    double w2 = 0.0;
+    if (DET >= 2) w2 = fma(3.0 * w1, w1, w2c);
+#pragma unroll
+    for (int j = 0; j < G::NRT; ++j) {
+      s0[j] += f[j];
+      if (DET >= 1) { s1[j] = fma(w1, f[j], s1[j]); u1[j] = fma(w1, dz[j], u1[j]); }
+      if (DET >= 2) { s2[j] = fma(w2, f[j], s2[j]); u2[j] = fma(w2, dz[j], u2[j]); }
+      c[j] = cn[j];
+    }
+    w1 += 2.0;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -315,18 +409,19 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t run = (uint64_t)blockIdx.x * JNE_WARPS_PER_CTA + warp;
   if (run >= n) return;
-  double* wsm = smem + (size_t)warp * (G::WARP_SMEM + 7 * 16);
-  double* VV = wsm;
+  double* wsm = smem + (size_t)warp * G::WARP_SMEM;
+  double* VV = wsm;                 // raw view
   double* vec = VV + G::VV_SZ;
-  double* S2 = vec + G::VEC_SZ;
+  double* tot = vec + G::VEC_SZ;
+  double* S2 = wsm;                 // work view (aliases the raw view, see jne_warp_assemble)
   double* R = S2 + G::MAT_SZ;
-  double* misc = R + G::MAT_SZ;     // 64 + 7*16 doubles
+  double* misc = R + G::MAT_SZ;
 
   const int g = lane >> 2, k = lane & 3;
   const uint32_t d = prm.dim, T = prm.steps;
   const uint32_t t_begin = min((uint32_t)k * prm.seg_len, T);
   const uint32_t t_end = min(T, t_begin + prm.seg_len);
-  const uint32_t seed = SRC_RNG ? seeds[run] : 0u;
+  const jne_keys keys = jne_make_keys(SRC_RNG ? seeds[run] : 0u, reinterpret_cast<volatile uint32_t*>(wsm));
   const double* dBrun = SRC_RNG ? nullptr : dB + run * (uint64_t)d * T;
 
   double c[G::NRT], s0[G::NRT], s1[G::NRT], s2[G::NRT], u1[G::NRT], u2[G::NRT];
@@ -340,75 +435,13 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   const double w2c = -(prm.T * prm.T - 1.0);
   const int src_lane = (((g - G::B) & 7) << 2) | k;
 
-  for (uint32_t t = t_begin; t < t_begin + prm.seg_len; t += 4) {
-    double z[G::NRT][4];
-#pragma unroll
-    for (int j = 0; j < G::NRT; ++j) {
-      const uint32_t row = 8 * j + g;
-      if (SRC_RNG) {
-        float zf[4] = {0.f, 0.f, 0.f, 0.f};
-        if (row < d) jne_normals4(seed, row, t >> 2, zf);
-#pragma unroll
-        for (int s = 0; s < 4; ++s) z[j][s] = (double)zf[s];
-      } else {
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-          z[j][s] = (row < d && t + s < t_end) ? dBrun[(uint64_t)(t + s) * d + row] : 0.0;
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const bool active = (t + s) < t_end;
-      double f[G::NRT], dz[G::NRT], cn[G::NRT];
-#pragma unroll
-      for (int j = 0; j < G::NRT; ++j) {
-        f[j] = active ? c[j] : 0.0;
-        dz[j] = active ? z[j][s] : 0.0;
-        cn[j] = c[j] + dz[j];                  // B_t = B_{t-1} + dB_t   (src/matrix_utils.rs:51-63)
-        if (!SRC_RNG) dz[j] = cn[j] - c[j];    // dB re-derived by subtraction (src/johansen_statistics.rs:80-82)
-      }
-      // V tiles: index i = 8*jt + g;  i < DP -> F_i (own), DP <= i < 2DP -> dB_{i-DP} (shuffled)
-      double V[G::NCT];
-#pragma unroll
-      for (int jt = 0; jt < G::NCT; ++jt) {
-        double own = (jt < G::NRT) ? f[jt < G::NRT ? jt : 0] : 0.0;
-        double recv = 0.0;
-        if (jt >= G::A) {
-          if (G::B == 0) {
-            recv = (jt - G::A < G::NRT) ? dz[(jt - G::A < G::NRT) ? jt - G::A : 0] : 0.0;
-          } else {
-            // sender side: lanes g' <= 7-B serve slot jt-A, lanes g' >= 8-B serve slot jt-A-1
-            const int ja = jt - G::A, jb = jt - G::A - 1;
-            const double va = (ja >= 0 && ja < G::NRT) ? dz[(ja >= 0 && ja < G::NRT) ? ja : 0] : 0.0;
-            const double vb = (jb >= 0 && jb < G::NRT) ? dz[(jb >= 0 && jb < G::NRT) ? jb : 0] : 0.0;
-            const double send = (g <= 7 - G::B) ? va : vb;
-            recv = __shfl_sync(0xffffffffu, send, src_lane);
-          }
-        }
-        const int i = 8 * jt + g;
-        V[jt] = (i < DP) ? own : ((i < 2 * DP) ? recv : 0.0);
-      }
-      int ti = 0;
-#pragma unroll
-      for (int a = 0; a < G::NRT; ++a)
-#pragma unroll
-        for (int b = a; b < G::NCT; ++b) {
-          jne_dmma(acc[ti][0], acc[ti][1], V[a], V[b]);
-          ++ti;
-        }
-      // deterministic cross moments and the running path
-      double w2 = 0.0;
-      if (DET >= 2) w2 = fma(3.0 * w1, w1, w2c);
-#pragma unroll
-      for (int j = 0; j < G::NRT; ++j) {
-        s0[j] += f[j];
-        if (DET >= 1) { s1[j] = fma(w1, f[j], s1[j]); u1[j] = fma(w1, dz[j], u1[j]); }
-        if (DET >= 2) { s2[j] = fma(w2, f[j], s2[j]); u2[j] = fma(w2, dz[j], u2[j]); }
-        c[j] = cn[j];
-      }
-      w1 += 2.0;
-    }
-  }
+  // blocks in which every lane's four steps are inside its segment need no masking
+  uint32_t t = t_begin;
+  const uint32_t t_full = t_begin + 4u * prm.full_blocks;
+  for (; t < t_full; t += 4)
+    jne_block4<DP, DET, SRC_RNG, false>(t, t_end, d, g, src_lane, keys, dBrun, c, s0, s1, s2, u1, u2, acc, w1, w2c);
+  for (; t < t_begin + prm.seg_len; t += 4)
+    jne_block4<DP, DET, SRC_RNG, true>(t, t_end, d, g, src_lane, keys, dBrun, c, s0, s1, s2, u1, u2, acc, w1, w2c);
 
   // ---- dump raw moments to the warp's shared memory ----
   {
@@ -434,7 +467,7 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
     }
   }
   __syncwarp();
-  jne_warp_assemble<DP>(VV, vec, S2, R, misc, prm);
+  jne_warp_assemble<DP>(VV, vec, tot, S2, R, prm);
   if (dbg != nullptr) {
     double* o = dbg + run * 512;
     for (int e = lane; e < 256; e += 32) {
@@ -504,7 +537,10 @@ __global__ void jne_brownian_kernel(uint32_t seed, uint32_t d, uint32_t T, doubl
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const uint32_t t = 4 * tb + s;
-      if (t < T) { acc += (double)z[s] * sq; out[(uint64_t)(t + 1) * d + row] = acc; }
+      if (t < T) {   // scaled = z * sqrt(dt), then acc += scaled: two roundings, never fused (src/rng_matrix.rs:138-140)
+        acc = __dadd_rn(acc, __dmul_rn((double)z[s], sq));
+        out[(uint64_t)(t + 1) * d + row] = acc;
+      }
     }
   }
 }

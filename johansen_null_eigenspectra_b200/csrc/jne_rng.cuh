@@ -18,6 +18,11 @@
 
 struct jne_u4 { uint32_t x, y, z, w; };
 
+// 32 x 32 -> (hi, lo) in one IMAD.WIDE.U32
+__device__ __forceinline__ void jne_mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+  asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%1, %0}, p;\n\t}" : "=r"(hi), "=r"(lo) : "r"(a), "r"(b));
+}
+
 __device__ __forceinline__ jne_u4 jne_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                     uint32_t k0, uint32_t k1) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -35,13 +40,46 @@ __device__ __forceinline__ jne_u4 jne_philox4x32_10(uint32_t c0, uint32_t c1, ui
   return jne_u4{c0, c1, c2, c3};
 }
 
+// Same function with the round keys of word 0 precomputed (key0[r] = seed + r * W0); the round keys of
+// word 1 are compile-time constants.  Lets the per-run key schedule live in registers across the time loop.
+struct jne_keys { uint32_t k[10]; };
+// `stage` is 10 words of the warp's shared memory: the round trip through memory stops ptxas from
+// rematerialising "seed + r*W0" inside the time loop (it re-added all nine keys on every call).
+__device__ __forceinline__ jne_keys jne_make_keys(uint32_t seed, volatile uint32_t* stage) {
+  jne_keys ks;
+  const int lane = threadIdx.x & 31;
+  if (lane < 10) stage[lane] = seed + (uint32_t)lane * 0x9E3779B9u;
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 10; ++r) ks.k[r] = stage[r];
+  __syncwarp();
+  return ks;
+}
+__device__ __forceinline__ jne_u4 jne_philox4x32_10_keyed(uint32_t c0, uint32_t c1, const jne_keys& ks) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W1 = 0xBB67AE85u;
+  uint32_t c2 = 0u, c3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t h0, l0, h1, l1;
+    jne_mulhilo(M0, c0, h0, l0);
+    jne_mulhilo(M1, c2, h1, l1);
+    const uint32_t n0 = h1 ^ c1 ^ ks.k[r];
+    const uint32_t n2 = h0 ^ c3 ^ (JNE_KEY1 + (uint32_t)r * W1);
+    c1 = l1;
+    c3 = l0;
+    c0 = n0;
+    c2 = n2;
+  }
+  return jne_u4{c0, c1, c2, c3};
+}
+
 // Two N(0,1) variates from two 32-bit words.  u = (wa + 1/2) 2^-32 in (0, 1], radius
 // r = sqrt(-2 ln u) <= 6.76; angle theta = 2 pi * int32(wb) * 2^-32 in [-pi, pi) so the MUFU
 // sin/cos see their most accurate range.
 __device__ __forceinline__ void jne_box_muller(uint32_t wa, uint32_t wb, float& z0, float& z1) {
   const float u = fmaf(__uint2float_rn(wa), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  const float l = __log2f(u);                        // MUFU.LG2
-  float r;
+  float l, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));   // MUFU.LG2 (u >= 2^-33: never denormal)
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -1.3862943611198906f));  // MUFU.SQRT
   const float th = __int2float_rn((int)wb) * 1.4629180792671596e-9f;  // 2 pi 2^-32
   z0 = r * __cosf(th);
@@ -51,6 +89,11 @@ __device__ __forceinline__ void jne_box_muller(uint32_t wa, uint32_t wb, float& 
 // The four normals of (row, time block tb = t >> 2) for one seed.
 __device__ __forceinline__ void jne_normals4(uint32_t seed, uint32_t row, uint32_t tb, float z[4]) {
   const jne_u4 w = jne_philox4x32_10(tb, row, 0u, 0u, seed, JNE_KEY1);
+  jne_box_muller(w.x, w.y, z[0], z[1]);
+  jne_box_muller(w.z, w.w, z[2], z[3]);
+}
+__device__ __forceinline__ void jne_normals4_keyed(const jne_keys& ks, uint32_t row, uint32_t tb, float z[4]) {
+  const jne_u4 w = jne_philox4x32_10_keyed(tb, row, ks);
   jne_box_muller(w.x, w.y, z[0], z[1]);
   jne_box_muller(w.z, w.w, z[2], z[3]);
 }

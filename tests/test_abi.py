@@ -1,0 +1,96 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/*.h declares,
+argument validation that needs no device, the Python mirror of the reference's interface.
+(-m "not gpu")"""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def declared_functions():
+    names = []
+    for h in sorted((ROOT / "include").glob("*.h")):
+        text = re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
+        names += re.findall(r"\b(jne_[a-z0-9_]+)\s*\(", text)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol():
+    import johansen_null_eigenspectra_b200 as jne
+    names = declared_functions()
+    assert len(names) >= 18
+    lib = ctypes.CDLL(str(Path(jne.__file__).parent / "libjne.so"))
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_header_is_plain_c():
+    """The boundary must be bindgen-trivial: compile the headers as C."""
+    import subprocess, tempfile
+    for h in sorted((ROOT / "include").glob("*.h")):
+        with tempfile.NamedTemporaryFile("w", suffix=".c") as f:
+            f.write(f'#include "{h}"\nint main(void) {{ return 0; }}\n')
+            f.flush()
+            subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", f.name], check=True)
+
+
+def test_deviceless_entry_points():
+    import johansen_null_eigenspectra_b200 as jne
+    assert "sm_100a" in jne.version()
+    # eigenvalues per run: src/data_storage/thread_manager.rs:40-44
+    assert [jne.num_eigs(m, 12) for m in range(5)] == [12, 13, 12, 13, 12]
+    assert jne.num_eigs(0, 2) == 2          # integration/basic_api.rs:35
+    with pytest.raises(jne.JneError):
+        jne.num_eigs(5, 3)
+    with pytest.raises(jne.JneError):
+        jne.num_eigs(0, 0)
+    # F_alg = 2 T [p(p+1)/2 + p d]  
+    assert jne.flops_per_run(0, 12, 10000) == 4.44e6
+    assert jne.flops_per_run(1, 12, 10000) == 4.94e6
+    assert jne.flops_per_run(0, 2, 1000) == 14e3
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never compute on the CPU."""
+    import johansen_null_eigenspectra_b200 as jne
+    if jne.lib.jne_device_count() > 0:
+        pytest.skip("a GPU is visible here")
+    with pytest.raises(jne.JneError) as e:
+        jne.Engine()
+    assert "no CPU fallback" in str(e.value)
+    with pytest.raises(jne.JneError):
+        jne.calculate_eigenvalues(2, 100, 1, 0)
+
+
+def test_product_never_imports_oracle():
+    pkg = ROOT / "johansen_null_eigenspectra_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.hpp")):
+        text = f.read_text()
+        assert not re.search(r"(import\s+oracle|from\s+oracle|libjne_oracle|oracle/)", text), f"{f} reaches into oracle/"
+
+
+def test_model_enum_mirror():
+    """src/tests/johansen_models_test.rs: numbers, predicates, Default = model 2."""
+    from johansen_null_eigenspectra_b200 import JohansenModel as M
+    assert [m.to_number() for m in M.all_models()] == [0, 1, 2, 3, 4]
+    assert M.from_number(3) is M.InterceptTrendUnrestrictedInterceptRestrictedTrend
+    assert M.from_number(5) is None
+    assert M.default() is M.InterceptNoTrendUnrestrictedIntercept
+    assert [m.has_intercept() for m in M] == [False, True, True, True, True]
+    assert [m.has_trend() for m in M] == [False, False, False, True, True]
+    assert [m.num_eigs(5) for m in M] == [5, 6, 5, 6, 5]
+
+
+def test_shard_bounds_cover_and_disjoint():
+    from johansen_null_eigenspectra_b200.sharding import shard_bounds, weak_scaling_seeds
+    for n in (0, 1, 7, 8, 1000003):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+    s = np.concatenate([weak_scaling_seeds(5, 4, r) for r in range(4)])
+    assert np.array_equal(s, np.arange(1, 21, dtype=np.uint32))

@@ -1,0 +1,254 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes -> libjne.so), against the
+CPU oracle on the same seeded inputs and against the committed golden fixtures.  (-m gpu)
+
+Tolerances (BASELINE.json north_star / BASELINE.md section 5):
+  gate (1) shared increments: |d| <= 1e-9 |lambda| + 1e-12 lambda_max   (eig_tol)
+  gate (2) GPU RNG: two-sample KS at alpha = 1e-3 on trace and max-eig; chi^2(1) law; MHM quantiles
+"""
+import numpy as np
+import pytest
+from scipy import stats
+
+from oracle import c_oracle, johansen_oracle as orc, philox_ref
+from tests.conftest import eig_tol
+from tests.golden import make_golden as mg
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_close(got, ref, what=""):
+    tol = eig_tol(ref)
+    bad = np.abs(got - ref) > tol
+    assert not bad.any(), f"{what}: max err/tol {np.max(np.abs(got - ref) / tol):.3g}"
+
+
+# ---- gate (1): shared increments ------------------------------------------------------------
+def test_golden_fixtures(engine):
+    g = np.load(mg.HERE / "eigs_from_increments.npz")
+    for key in g.files:
+        m, d, t = (int(s[1:]) for s in key.split("_"))
+        db = mg.increments(mg.case_seed(m, d, t), mg.N, t, d)
+        assert_close(engine.eigs_from_increments(m, db), g[key], key)
+
+
+def test_golden_full_size(engine):
+    """dim 12, T 10 000 (the metric's configuration), all five models."""
+    g = np.load(mg.HERE / "full_dim12_steps10000.npz")
+    for m in range(5):
+        db = mg.increments(mg.case_seed(m, 12, 10000), 2, 10000, 12)
+        assert_close(engine.eigs_from_increments(m, db), g[f"m{m}"], f"model {m}")
+
+
+def test_config_c1_shared_increments(engine):
+    """BASELINE.json configs[0]: model 0, dim 2, T 1000, 100 000 runs on shared increments
+    (chunked; the C port of the oracle is the checker, itself pinned to the numpy oracle)."""
+    lib = c_oracle.load()
+    c1 = np.load(mg.HERE / "c1_model0_dim2_steps1000.npz")["eigs"]
+    rng = np.random.default_rng(mg.SEED)
+    worst = 0.0
+    for chunk in range(10):
+        db = rng.standard_normal((10000, 1000, 2)) * np.sqrt(1.0 / 1000)
+        got = engine.eigs_from_increments(0, db)
+        if chunk == 0:
+            assert_close(got[:64], c1, "c1 golden")
+        ref = np.stack([c_oracle.eigs_from_increments(lib, db[i], 0) for i in range(db.shape[0])])
+        worst = max(worst, np.max(np.abs(got - ref) / eig_tol(ref)))
+    assert worst <= 1.0, worst
+
+
+@pytest.mark.parametrize("model", range(5))
+@pytest.mark.parametrize("dim", [1, 2, 3, 4, 5, 7, 8, 9, 11, 12, 13, 15])
+def test_all_dims_vs_oracle(engine, model, dim):
+    rng = np.random.default_rng(1000 * model + dim)
+    for T in (dim + 5, 64, 257, 1001):
+        db = rng.standard_normal((5, T, dim)) / np.sqrt(T)
+        assert_close(engine.eigs_from_increments(model, db), orc.eigs_batch_from_increments(db, model),
+                     f"model {model} dim {dim} T {T}")
+
+
+def test_ragged_step_counts(engine):
+    """Segment stitching: every T mod 16 residue, incl. T smaller than one segment block."""
+    rng = np.random.default_rng(77)
+    for T in list(range(8, 41)) + [99, 100, 101, 102, 103]:
+        for model in (0, 3, 4):
+            db = rng.standard_normal((3, T, 3)) / np.sqrt(T)
+            assert_close(engine.eigs_from_increments(model, db), orc.eigs_batch_from_increments(db, model),
+                         f"model {model} T {T}")
+
+
+def test_unscaled_increments_and_long_horizon(engine):
+    """Eigenvalues are invariant to the increment scale only through factor = T; check a
+    non-unit variance input and T = 100 000 (config c5: accumulation precision)."""
+    rng = np.random.default_rng(5)
+    db = rng.standard_normal((2, 500, 4)) * 3.7
+    assert_close(engine.eigs_from_increments(2, db), orc.eigs_batch_from_increments(db, 2))
+    for model in (3, 4):
+        db = rng.standard_normal((1, 100000, 12)) / np.sqrt(100000)
+        assert_close(engine.eigs_from_increments(model, db), orc.eigs_batch_from_increments(db, model),
+                     f"T=1e5 model {model}")
+
+
+# ---- the eigen-solve alone (reference a8: GeneralizedEigen::new -> dggev) ---------------------
+def test_pencil_solver_vs_dggev(engine):
+    from scipy.linalg import lapack
+    rng = np.random.default_rng(9)
+    for p, d in [(1, 1), (2, 2), (3, 2), (5, 5), (12, 12), (13, 12), (16, 15), (16, 16)]:
+        n = 40
+        S1 = rng.standard_normal((n, d, p))
+        F = rng.standard_normal((n, p, 3 * p + 2))
+        S2 = F @ np.transpose(F, (0, 2, 1)) / (3 * p)
+        got = engine.pencil_eigs_batch(S1, S2)
+        for i in range(n):
+            ar, ai, be, *_ = lapack.dggev(np.asfortranarray(S1[i].T @ S1[i]), np.asfortranarray(S2[i]))
+            ref = np.sort(np.hypot(ar, ai) / be)[::-1]
+            assert_close(got[i], ref, f"p {p} d {d}")
+
+
+# ---- gate (2): the GPU random stream -----------------------------------------------------------
+def test_device_normals_match_philox_restatement(engine):
+    """Uniform words are bit-exact; MUFU lg2/sqrt/sin/cos leave <= 5e-6 absolute on the normals."""
+    for dim, T, seed in [(12, 103, 7), (1, 1, 1), (5, 4001, 0xFFFFFFFF), (15, 64, 123456789)]:
+        z = engine.gen_normal_matrix(dim, T, seed)
+        assert z.shape == (dim, T)
+        assert np.abs(z - philox_ref.normal_matrix(dim, T, seed)).max() < 5e-6
+
+
+def test_reference_rng_tests_on_device_stream(engine):
+    import johansen_null_eigenspectra_b200 as jne
+    # src/tests/rng_matrix_test/gen_normal_matrix_test.rs:7-16 -- 200 x 300 normals, seed 42, CDF within 1e-2
+    z = engine.gen_normal_matrix(200, 300, 42)
+    qs = np.arange(1, 100) / 100
+    emp = np.searchsorted(np.sort(z.ravel()), stats.norm.ppf(qs)) / z.size
+    assert np.abs(emp - qs).max() < 1e-2
+    # brownian_motion_test.rs:9-44 shape dim x (steps+1); :47-96 increments / sqrt(dt) normal within 0.05
+    dim, steps, dt = 3, 1000, 0.01
+    bm = engine.brownian_motion_matrix(dim, steps, dt, 42)
+    assert bm.shape == (dim, steps + 1) and np.all(bm[:, 0] == 0.0)
+    inc = np.diff(bm, axis=1) / np.sqrt(dt)
+    emp = np.searchsorted(np.sort(inc.ravel()), stats.norm.ppf(qs)) / inc.size
+    assert np.abs(emp - qs).max() < 0.05
+    # :99-125 same seed => identical; :128-153 different seeds => different
+    assert np.array_equal(bm, engine.brownian_motion_matrix(dim, steps, dt, 42))
+    assert not np.array_equal(bm, engine.brownian_motion_matrix(dim, steps, dt, 43))
+    # cumulative sum of sqrt(dt) z, naive left to right (src/matrix_utils.rs:51-63)
+    z = engine.gen_normal_matrix(dim, steps, 42)
+    assert np.array_equal(bm[:, 1:], np.cumsum(z * np.sqrt(dt), axis=1))
+
+
+@pytest.mark.parametrize("model", range(5))
+def test_rng_path_pathwise_vs_oracle(engine, model):
+    """jne_eigs_batch == oracle(reference algorithm) fed the SAME normals the device stream produces:
+    checks the fused in-register generation + accumulation end to end, to gate-(1) tolerance."""
+    for dim, T in [(1, 50), (2, 103), (5, 1000), (12, 400), (12, 10000), (15, 257)]:
+        seeds = np.array([1, 2, 4294967295], dtype=np.uint32)
+        got = engine.eigs_batch(model, dim, T, seeds)
+        ref = np.stack([orc.eigs_from_normals(engine.gen_normal_matrix(dim, T, int(s)), model) for s in seeds])
+        assert_close(got, ref, f"model {model} dim {dim} T {T}")
+
+
+def test_determinism_and_geometry_independence(engine):
+    """Same (model, dim, steps, seed) => bit-identical record, whatever the batch, order or entry point
+    (stronger than src/tests/data_storage/integration/resumable.rs:62-70)."""
+    import torch
+    seeds = np.arange(1, 3001, dtype=np.uint32)
+    a = engine.eigs_batch(3, 5, 300, seeds)
+    perm = np.random.default_rng(0).permutation(seeds.size)
+    b = engine.eigs_batch(3, 5, 300, seeds[perm])
+    assert np.array_equal(a[perm], b)
+    c = np.concatenate([engine.eigs_batch(3, 5, 300, seeds[i:i + 7]) for i in range(0, 70, 7)])
+    assert np.array_equal(a[:70], c)
+    # resume-like subset (src/data_storage/progress.rs:56-61): arbitrary missing seeds
+    sub = seeds[[1, 3, 500, 2999]]
+    assert np.array_equal(engine.eigs_batch(3, 5, 300, sub), a[[1, 3, 500, 2999]])
+    # async pair and device-pointer entry give the same bits
+    out = np.empty_like(a)
+    engine.wait(engine.submit(3, 5, 300, seeds, out))
+    assert np.array_equal(out, a)
+    ds = torch.from_numpy(seeds.astype(np.int64)).to(torch.int32).cuda().contiguous()   # same 32 bits
+    do = torch.empty((seeds.size, 6), dtype=torch.float64, device="cuda")
+    engine.eigs_batch_device(3, 5, 300, ds.data_ptr(), seeds.size, do.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    engine.check_async()
+    assert np.array_equal(do.cpu().numpy(), a)
+    # the Brownian path does not depend on the model (common random numbers, src/rng_matrix.rs:11)
+    m0 = engine.eigs_batch(0, 4, 200, seeds[:50])
+    _, S2, _ = engine.eigs_batch_debug(0, 4, 200, seeds[:50])
+    _, S2b, _ = engine.eigs_batch_debug(1, 4, 200, seeds[:50])
+    assert np.allclose(S2[:, :4, :4], S2b[:, :4, :4], rtol=1e-14, atol=0)
+    assert m0.shape == (50, 4)
+
+
+@pytest.mark.parametrize("model", range(5))
+def test_ks_vs_oracle_with_independent_generator(engine, model):
+    """Gate (2): trace and max-eig of GPU-RNG runs vs the oracle driven by numpy's PCG64;
+    two-sample KS, alpha = 1e-3 per statistic (dim 3, T 200, 4000 vs 4000 runs)."""
+    dim, T, n = 3, 200, 4000
+    gpu = engine.eigs_batch(model, dim, T, np.arange(1, n + 1, dtype=np.uint32))
+    rng = np.random.default_rng(31337 + model)
+    cpu = np.stack([orc.eigs_from_normals(rng.standard_normal((dim, T)), model) for _ in range(n)])
+    assert stats.ks_2samp(gpu.sum(axis=1), cpu.sum(axis=1)).pvalue > 1e-3
+    assert stats.ks_2samp(gpu[:, 0], cpu[:, 0]).pvalue > 1e-3
+
+
+@pytest.mark.parametrize("model", [2, 4])
+def test_chi2_law_dim1_gpu(engine, model):
+    """Exact law: models 2 and 4 at dim 1 give lambda ~ chi^2(1) for every T."""
+    ev = engine.eigs_batch(model, 1, 1000, np.arange(1, 200001, dtype=np.uint32))[:, 0]
+    assert stats.kstest(ev, stats.chi2(1).cdf).pvalue > 1e-3
+    assert abs(np.quantile(ev, 0.95) - 3.841) < 0.05
+
+
+def test_mhm_critical_values_gpu(engine):
+    """95 % quantiles vs MacKinnon-Haug-Michelis, T = 2000, 200 000 runs:
+    MC error ~0.3 %, finite-T bias < 1 %; 2.5 % window."""
+    import johansen_null_eigenspectra_b200 as jne
+    seeds = np.arange(1, 200001, dtype=np.uint32)
+    table = {(0, 2): (12.32, 11.22), (1, 2): (20.26, 15.89), (2, 2): (15.49, 14.26),
+             (3, 2): (25.87, 19.39), (4, 2): (18.40, 17.15), (0, 3): (24.28, 17.80)}
+    for (model, dim), (tr, mx) in table.items():
+        ev = engine.eigs_batch(model, dim, 2000, seeds)
+        assert abs(orc.percentiles(ev.sum(axis=1), (0.95,))[0] - tr) / tr < 0.025, (model, dim)
+        assert abs(orc.percentiles(ev[:, 0], (0.95,))[0] - mx) / mx < 0.025, (model, dim)
+
+
+def test_full_size_properties(engine):
+    """BASELINE metric configuration (dim 12, T 10 000): size-independent properties on 20 000 runs per model."""
+    seeds = np.arange(1, 20001, dtype=np.uint32)
+    for model in range(5):
+        ev = engine.eigs_batch(model, 12, 10000, seeds)
+        p = 13 if model in (1, 3) else 12
+        assert ev.shape == (seeds.size, p)
+        assert np.all(np.isfinite(ev)) and np.all(ev >= 0) and np.all(np.diff(ev, axis=1) <= 0)
+        if model in (1, 3):   # rank-d pencil: the extra eigenvalue is numerical noise (Appendix A-5)
+            assert np.all(ev[:, -1] < 1e-9 * ev[:, 0])
+        assert ev.sum(axis=1).mean() > 100          # trace grows ~2 d^2
+
+
+# ---- error behaviour (SURVEY.md section 8b "Errors") ----------------------------------------
+def test_error_codes(engine):
+    import johansen_null_eigenspectra_b200 as jne
+    s = np.array([1], dtype=np.uint32)
+    for args in [(5, 2, 100), (0, 0, 100), (0, 2, 0), (4, 2, 1)]:
+        with pytest.raises(jne.JneError) as e:
+            engine.eigs_batch(*args, s)
+        assert e.value.status == -1
+    with pytest.raises(jne.JneError) as e:
+        engine.eigs_batch(0, 16, 100, s)
+    assert e.value.status == -4
+    with pytest.raises(jne.JneError) as e:      # T < p: singular S2 -> NaN (the reference panics at :45)
+        engine.eigs_batch(0, 8, 5, s)
+    assert e.value.status == -3
+    assert engine.eigs_batch(0, 2, 100, np.array([], dtype=np.uint32)).shape == (0, 2)   # empty input
+    assert engine.eigs_batch(0, 2, 100, s).shape == (1, 2)                               # still usable
+
+
+def test_python_mirror_of_reference_call_sites(engine):
+    """calculate_eigenvalues / calculate_eigenvalues_parallel keep the reference's shapes:
+    integration/basic_api.rs:35 (2 eigenvalues for model 0 dim 2), multiple_models.rs:32-37 (finite)."""
+    import johansen_null_eigenspectra_b200 as jne
+    ev = jne.calculate_eigenvalues(2, 103, 1, jne.JohansenModel.NoInterceptNoTrend)
+    assert len(ev) == 2 and ev[0] >= ev[1] and all(np.isfinite(ev))
+    got = {}
+    jne.calculate_eigenvalues_parallel(2, 103, range(1, 6), 0, lambda s, e: got.__setitem__(s, e), engine=engine, batch=2)
+    assert sorted(got) == [1, 2, 3, 4, 5] and got[1] == ev
+    for m in jne.JohansenModel:
+        assert all(np.isfinite(jne.calculate_eigenvalues(2, 103, 7, m)))
