@@ -66,18 +66,36 @@ __device__ __forceinline__ void jne_dmma(double& c0, double& c1, double a, doubl
 // K3: eigenvalues of the pencil (S1'S1, S2) for one run, one warp.
 //   S2 : p x p symmetric positive definite, full storage, ld JNE_LD   (destroyed)
 //   R  : p x d  = S1' (row j = sum_t F_j dB_t'), ld JNE_LD               (destroyed)
-// Cholesky S2 = L L', W = L^-1 R, A = W W' (same eigenvalues as the pencil), cyclic two-sided
-// Jacobi with a round-robin parallel ordering (disjoint pairs rotate concurrently), then
-// lambda_i = factor * |a_ii| sorted descending (src/johansen_statistics.rs:40-45).
-// Returns false when a value is not finite (the reference panics at :45).
+// Cholesky S2 = L L', W = L^-1 R, A = W W' (same eigenvalues as the pencil), then cyclic two-sided
+// Jacobi in a round-robin parallel ordering: the ne/2 disjoint pairs of a step rotate concurrently,
+// and the update A <- J'AJ is applied per 2x2 BLOCK (pair slot P1 x pair slot P2), one lane per
+// block, so a step costs one rotation pass + one block pass.  lambda_i = factor * |a_ii| sorted
+// descending (src/johansen_statistics.rs:40-45).  Returns false when a value is not finite (the
+// reference panics at :45).
 // ---------------------------------------------------------------------------------------------
+// 1/x and 1/sqrt(x) to ~1 ulp from an FP32 seed + two Newton steps; x must be inside the float range
+// (true for every call site below).  Avoids the ~35-instruction IEEE division / sqrt sequences.
+__device__ __forceinline__ double jne_rcp(double x) {
+  double r = (double)__frcp_rn((float)x);
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+__device__ __forceinline__ double jne_rsqrt(double x) {
+  double y = (double)rsqrtf((float)x);
+  const double hx = 0.5 * x;
+  y = fma(y, fma(-hx * y, y, 0.5), y);
+  y = fma(y, fma(-hx * y, y, 0.5), y);
+  return y;
+}
+
 __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, double* __restrict__ R,
                                                    double* __restrict__ misc, int p, int d, double factor,
                                                    double* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   double* invd = misc;        // [16]
   double* cs = misc + 16;     // [8][2]
-  double* ev = misc + 32;     // [16]
+  double* ev = misc + 32;     // [16] eigenvalues, [16..24) packed pair indices
 
   // --- Cholesky, right-looking, lower triangle in place ---
   for (int j = 0; j < p; ++j) {
@@ -106,77 +124,97 @@ __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, doub
     }
   }
   __syncwarp();
-  // --- A = W W' into the S2 storage (L is dead now); two rows per pass ---
+  // --- A = W W' into the S2 storage (L is dead now), zero-padded to ne x ne; two rows per pass ---
+  const int ne = (p + 1) & ~1;          // even number of players; for odd p index p is an all-zero row/col
+  const int npairs = ne >> 1;
   double tr = 0.0;
-  for (int i0 = 0; i0 < p; i0 += 2) {
+  for (int i0 = 0; i0 < ne; i0 += 2) {
     const int i = i0 + (lane >> 4), j = lane & 15;
-    if (i < p && j <= i) {
+    if (j <= i) {
       double a = 0.0;
-      for (int c = 0; c < d; ++c) a = fma(R[i * JNE_LD + c], R[j * JNE_LD + c], a);
+      if (i < p)
+        for (int c = 0; c < d; ++c) a = fma(R[i * JNE_LD + c], R[j * JNE_LD + c], a);
       if (i == j) tr += a;
-      // this phase only reads R and only writes S2 (L is dead), so the store needs no staging
+      // this phase only reads R and only writes S2, so the store needs no staging
       S2[i * JNE_LD + j] = a;
       S2[j * JNE_LD + i] = a;
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
+  // --- block ownership: lane -> (P1 <= P2) pair slots; a second block only when npairs == 8 ---
+  const int nblk = npairs * (npairs + 1) / 2;
+  int b1p = 0, b1q = 0, b2p = -1, b2q = 0;
+  {
+    int r = 0, k = lane;
+    while (r < npairs && k >= npairs - r) { k -= npairs - r; ++r; }
+    if (r < npairs) { b1p = r; b1q = r + k; } else { b1p = -1; }
+    if (lane + 32 < nblk) {
+      r = 0; k = lane + 32;
+      while (k >= npairs - r) { k -= npairs - r; ++r; }
+      b2p = r; b2q = r + k;
+    }
+  }
   __syncwarp();
-  // --- cyclic Jacobi, round-robin ordering over n_even players ---
-  const int ne = (p + 1) & ~1;          // even number of players; index >= p is a bye
-  const int npairs = ne >> 1;
-  const double tol = fabs(tr) * 1.3877787807814457e-17;   // 2^-56 * trace (>= ||A||_F / sqrt(p) scale)
+  // normalise to unit trace: makes the solve invariant to the scale of the caller's increments and keeps
+  // every quantity fed to the FP32-seeded reciprocals inside the float range
+  {
+    const double inv_tr = 1.0 / tr;
+    for (int e = lane; e < ne * ne; e += 32) {
+      const int i = e / ne, j = e - i * ne;
+      S2[i * JNE_LD + j] *= inv_tr;
+    }
+    factor *= tr;
+  }
+  __syncwarp();
+  const double tol = 1.3877787807814457e-17;   // 2^-56 (x trace = 1)
+  int* pq = reinterpret_cast<int*>(ev + 16);               // [8][2]
   for (int sweep = 0; sweep < 24; ++sweep) {
     int rotated = 0;
     for (int step = 0; step < ne - 1; ++step) {
-      // pair `lane` of this step: player 0 fixed, others rotate (circle method)
+      // rotation of pair slot `lane` (circle method: player ne-1 fixed, the others rotate)
       if (lane < npairs) {
-        int a = (lane == 0) ? ne - 1 : (step + lane) % (ne - 1);
-        int b = (step + (ne - 1) - lane) % (ne - 1);
-        int pp = min(a, b), qq = max(a, b);
+        const int a = (lane == 0) ? ne - 1 : (step + lane) % (ne - 1);
+        const int b = (step + (ne - 1) - lane) % (ne - 1);
+        const int pp = min(a, b), qq = max(a, b);
         double c = 1.0, s = 0.0;
-        if (qq < p) {
-          const double apq = S2[pp * JNE_LD + qq];
-          if (fabs(apq) > tol) {
-            const double app = S2[pp * JNE_LD + pp], aqq = S2[qq * JNE_LD + qq];
-            const double theta = (aqq - app) / (2.0 * apq);
-            const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-            c = rsqrt(fma(t, t, 1.0));
-            s = t * c;
-            rotated = 1;
-          }
+        const double apq = S2[pp * JNE_LD + qq];
+        if (fabs(apq) > tol) {
+          const double app = S2[pp * JNE_LD + pp], aqq = S2[qq * JNE_LD + qq];
+          const double theta = 0.5 * (aqq - app) * jne_rcp(apq);
+          const double h = fma(theta, theta, 1.0);
+          const double t = copysign(jne_rcp(fabs(theta) + h * jne_rsqrt(h)), theta);
+          c = jne_rsqrt(fma(t, t, 1.0));
+          s = t * c;
+          rotated = 1;
         }
         cs[2 * lane] = c;
         cs[2 * lane + 1] = s;
-        ev[16 + lane] = __hiloint2double(pp, qq);   // pair indices, packed
+        pq[2 * lane] = pp;
+        pq[2 * lane + 1] = qq;
       }
       __syncwarp();
-      // row phase: A <- J' A   (two pairs per pass: half-warp h handles pair 2*it+h, lane m a column)
-      for (int it = 0; it < npairs; it += 2) {
-        const int pr = it + (lane >> 4), m = lane & 15;
-        if (pr < npairs && m < p) {
-          const double pk = ev[16 + pr];
-          const int pp = __double2hiint(pk), qq = __double2loint(pk);
-          const double c = cs[2 * pr], s = cs[2 * pr + 1];
-          if (qq < p && s != 0.0) {
-            const double x = S2[pp * JNE_LD + m], y = S2[qq * JNE_LD + m];
-            S2[pp * JNE_LD + m] = fma(c, x, -s * y);
-            S2[qq * JNE_LD + m] = fma(s, x, c * y);
-          }
-        }
-      }
-      __syncwarp();
-      // column phase: A <- A J
-      for (int it = 0; it < npairs; it += 2) {
-        const int pr = it + (lane >> 4), m = lane & 15;
-        if (pr < npairs && m < p) {
-          const double pk = ev[16 + pr];
-          const int pp = __double2hiint(pk), qq = __double2loint(pk);
-          const double c = cs[2 * pr], s = cs[2 * pr + 1];
-          if (qq < p && s != 0.0) {
-            const double x = S2[m * JNE_LD + pp], y = S2[m * JNE_LD + qq];
-            S2[m * JNE_LD + pp] = fma(c, x, -s * y);
-            S2[m * JNE_LD + qq] = fma(s, x, c * y);
+      // block pass: B <- J1' B J2 for the 2x2 block (rows of slot P1) x (cols of slot P2)
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int P1 = pass ? b2p : b1p, P2 = pass ? b2q : b1q;
+        if (P1 >= 0) {
+          const double c1 = cs[2 * P1], s1 = cs[2 * P1 + 1], c2 = cs[2 * P2], s2 = cs[2 * P2 + 1];
+          if (s1 != 0.0 || s2 != 0.0) {
+            const int p1 = pq[2 * P1], q1 = pq[2 * P1 + 1], p2 = pq[2 * P2], q2 = pq[2 * P2 + 1];
+            const double x00 = S2[p1 * JNE_LD + p2], x01 = S2[p1 * JNE_LD + q2];
+            const double x10 = S2[q1 * JNE_LD + p2], x11 = S2[q1 * JNE_LD + q2];
+            const double r00 = fma(c1, x00, -s1 * x10), r01 = fma(c1, x01, -s1 * x11);   // J1' B
+            const double r10 = fma(s1, x00, c1 * x10), r11 = fma(s1, x01, c1 * x11);
+            double y00 = fma(c2, r00, -s2 * r01), y01 = fma(s2, r00, c2 * r01);          // (.) J2
+            double y10 = fma(c2, r10, -s2 * r11), y11 = fma(s2, r10, c2 * r11);
+            if (P1 == P2) { y01 = 0.0; y10 = 0.0; }        // the annihilated element, exactly
+            S2[p1 * JNE_LD + p2] = y00; S2[p1 * JNE_LD + q2] = y01;
+            S2[q1 * JNE_LD + p2] = y10; S2[q1 * JNE_LD + q2] = y11;
+            if (P1 != P2) {                                 // mirror: the matrix is kept in full storage
+              S2[p2 * JNE_LD + p1] = y00; S2[q2 * JNE_LD + p1] = y01;
+              S2[p2 * JNE_LD + q1] = y10; S2[q2 * JNE_LD + q1] = y11;
+            }
           }
         }
       }
