@@ -70,6 +70,18 @@ int jne_num_eigs(uint8_t model, uint32_t dim);
 int jne_eigs_batch(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps,
                    const uint32_t* seeds, uint64_t n, double* out);
 
+/* Fused multi-model batch.  The reference's Brownian path depends on
+ * (dim, steps, seed) only (src/rng_matrix.rs:11) and its CLI evaluates every model on the same seeds
+ * (src/main.rs:109), so one pass over the path yields the eigenvalues of every model selected in
+ * model_mask (bit m = model m).  out: n rows of jne_multi_width(model_mask, dim) doubles; within a row the
+ * selected models follow each other in ascending model order, each block descending.  Every block is
+ * bit-identical to what jne_eigs_batch returns for that (model, dim, steps, seed). */
+int jne_eigs_batch_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps,
+                         const uint32_t* seeds, uint64_t n, double* out);
+int jne_eigs_batch_multi_device(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps,
+                                const void* d_seeds, uint64_t n, void* d_out, void* stream);
+int jne_multi_width(uint32_t model_mask, uint32_t dim);   /* sum of jne_num_eigs over the selected models */
+
 /* Asynchronous pair: jne_submit enqueues the batch (seeds are copied before it returns; `out`
  * must stay valid until jne_wait) and returns a ticket > 0, or a negative status.  jne_wait
  * blocks until that batch's eigenvalues are in `out`.  At most one ticket may be outstanding

@@ -38,6 +38,9 @@ def _load() -> C.CDLL:
         "jne_last_error": (C.c_char_p, [vp]),
         "jne_num_eigs": (C.c_int, [u8, u32]),
         "jne_eigs_batch": (C.c_int, [vp, u8, u32, u32, vp, u64, vp]),
+        "jne_eigs_batch_multi": (C.c_int, [vp, u32, u32, u32, vp, u64, vp]),
+        "jne_eigs_batch_multi_device": (C.c_int, [vp, u32, u32, u32, vp, u64, vp, vp]),
+        "jne_multi_width": (C.c_int, [u32, u32]),
         "jne_submit": (i64, [vp, u8, u32, u32, vp, u64, vp]),
         "jne_wait": (C.c_int, [vp, i64]),
         "jne_eigs_batch_device": (C.c_int, [vp, u8, u32, u32, vp, u64, vp, vp]),
@@ -168,6 +171,37 @@ class Engine:
         self._check(lib.jne_eigs_batch(self._ctx, _model_number(model), dim, steps,
                                        seeds.ctypes.data, seeds.size, out.ctypes.data))
         return out
+
+    @staticmethod
+    def _mask(models) -> int:
+        mask = 0
+        for m in models:
+            mask |= 1 << _model_number(m)
+        return mask
+
+    def eigs_batch_multi(self, models, dim: int, steps: int, seeds) -> dict:
+        """One pass over each seed's Brownian path for all `models`; {model: (n, p) float64}."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        models = sorted({_model_number(m) for m in models})
+        mask = self._mask(models)
+        width = lib.jne_multi_width(mask, dim)
+        if width < 0:
+            raise JneError(width, "invalid model mask / dim")
+        out = np.empty((seeds.size, width), dtype=np.float64)
+        self._check(lib.jne_eigs_batch_multi(self._ctx, mask, dim, steps, seeds.ctypes.data, seeds.size,
+                                             out.ctypes.data))
+        res, off = {}, 0
+        for m in models:
+            p = num_eigs(m, dim)
+            res[m] = out[:, off:off + p]
+            off += p
+        return res
+
+    def eigs_batch_multi_device(self, models, dim: int, steps: int, d_seeds_ptr: int, n: int, d_out_ptr: int,
+                                stream_ptr: int = 0) -> None:
+        self._check(lib.jne_eigs_batch_multi_device(self._ctx, self._mask(models), dim, steps,
+                                                    C.c_void_p(d_seeds_ptr), n, C.c_void_p(d_out_ptr),
+                                                    C.c_void_p(stream_ptr)))
 
     def submit(self, model, dim: int, steps: int, seeds, out: np.ndarray) -> int:
         seeds = np.ascontiguousarray(seeds, dtype=np.uint32)

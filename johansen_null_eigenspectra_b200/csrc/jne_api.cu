@@ -19,7 +19,8 @@
 
 namespace {
 
-constexpr uint64_t kChunkRuns = 1ull << 18;   // runs per launch on the host-buffer path
+constexpr uint64_t kChunkRuns = 1ull << 16;   // runs per launch on the host-buffer path (D2H of chunk i overlaps the kernel of chunk i+1)
+constexpr uint64_t kMaxWidth = 5 * 16;        // doubles per run: all five models at dim 15
 
 std::mutex g_init_err_mu;
 std::string g_init_err;
@@ -98,10 +99,21 @@ void segment_weights(uint64_t a, uint64_t b, uint64_t T, double* w1, double* w2)
   *w2 = (double)(3 * m2 - (TT * TT - 1) * n);
 }
 
-JneRunParams make_params(uint8_t model, uint32_t dim, uint32_t steps, bool from_increments) {
+uint32_t mask_width(uint32_t mask, uint32_t dim) {
+  uint32_t w = 0;
+  for (int m = 0; m < 5; ++m)
+    if ((mask >> m) & 1u) w += (m == 1 || m == 3) ? dim + 1 : dim;
+  return w;
+}
+
+JneRunParams make_params_mask(uint32_t mask, uint32_t dim, uint32_t steps, bool from_increments) {
   JneRunParams p{};
-  p.dim = dim; p.steps = steps; p.model = model;
-  p.p = (model == 1 || model == 3) ? dim + 1 : dim;
+  p.dim = dim; p.steps = steps;
+  p.model_mask = mask;
+  p.out_stride = mask_width(mask, dim);
+  p.model = 0;
+  for (int m = 0; m < 5; ++m) if ((mask >> m) & 1u) p.model = m;   // highest selected model
+  p.p = p.out_stride;   // doubles per run (== eigenvalues per run for a single model)
   p.seg_len = 4u * ((steps + 15u) / 16u);
   p.T = (double)steps;
   p.factor = from_increments ? (double)steps : 1.0;
@@ -117,29 +129,35 @@ JneRunParams make_params(uint8_t model, uint32_t dim, uint32_t steps, bool from_
   return p;
 }
 
-template <int DP> constexpr size_t cta_smem() {
-  return (size_t)JNE_WARPS_PER_CTA * JneGeo<DP>::WARP_SMEM * sizeof(double);
+JneRunParams make_params(uint8_t model, uint32_t dim, uint32_t steps, bool from_increments) {
+  return make_params_mask(1u << model, dim, steps, from_increments);
+}
+
+template <int DP, bool MULTI> constexpr size_t cta_smem() {
+  return (size_t)JNE_WARPS_PER_CTA * (MULTI ? JneGeo<DP>::WARP_SMEM_MULTI : JneGeo<DP>::WARP_SMEM) * sizeof(double);
 }
 constexpr size_t pencil_smem() { return (size_t)JNE_WARPS_PER_CTA * (2 * 16 * JNE_LD + 64) * sizeof(double); }
 
-template <int DP, int DET, bool RNG>
+template <int DP, int DET, bool RNG, bool MULTI>
 cudaError_t launch_one(const uint32_t* d_seeds, const double* d_dB, uint64_t n, const JneRunParams& prm,
                        double* d_out, unsigned int* d_err, double* d_dbg, cudaStream_t st) {
-  auto kern = jne_run_kernel<DP, DET, RNG>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem<DP>());
+  auto kern = jne_run_kernel<DP, DET, RNG, MULTI>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem<DP, MULTI>());
   if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)((n + JNE_WARPS_PER_CTA - 1) / JNE_WARPS_PER_CTA);
-  kern<<<grid, 32 * JNE_WARPS_PER_CTA, cta_smem<DP>(), st>>>(d_seeds, d_dB, n, prm, d_out, d_err, d_dbg);
+  kern<<<grid, 32 * JNE_WARPS_PER_CTA, cta_smem<DP, MULTI>(), st>>>(d_seeds, d_dB, n, prm, d_out, d_err, d_dbg);
   return cudaGetLastError();
 }
 
 template <int DP, bool RNG>
 cudaError_t launch_det(int det, const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm, double* o,
                        unsigned int* e, double* dbg, cudaStream_t st) {
+  if (prm.model_mask & (prm.model_mask - 1u))   // more than one model: superset accumulation
+    return launch_one<DP, 2, RNG, true>(s, b, n, prm, o, e, dbg, st);
   switch (det) {
-    case 0: return launch_one<DP, 0, RNG>(s, b, n, prm, o, e, dbg, st);
-    case 1: return launch_one<DP, 1, RNG>(s, b, n, prm, o, e, dbg, st);
-    default: return launch_one<DP, 2, RNG>(s, b, n, prm, o, e, dbg, st);
+    case 0: return launch_one<DP, 0, RNG, false>(s, b, n, prm, o, e, dbg, st);
+    case 1: return launch_one<DP, 1, RNG, false>(s, b, n, prm, o, e, dbg, st);
+    default: return launch_one<DP, 2, RNG, false>(s, b, n, prm, o, e, dbg, st);
   }
 }
 
@@ -213,9 +231,9 @@ int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm, const uint32_t*
   return rc;
 }
 
-int eigs_batch_sync(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
+int eigs_batch_sync(jne_ctx* ctx, uint32_t mask, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
                     double* out) {
-  const JneRunParams prm = make_params(model, dim, steps, false);
+  const JneRunParams prm = make_params_mask(mask, dim, steps, false);
   const size_t nd = ctx->devs.size();
   if (n == 0) return JNE_OK;
   if (nd == 1) return run_share(ctx, ctx->devs[0], prm, seeds, n, out, nullptr);
@@ -350,9 +368,9 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
       JNE_CUDA(nullptr, cudaStreamCreateWithFlags(&dv.stream, cudaStreamNonBlocking));
       for (auto& s : dv.slot) {
         JNE_CUDA(nullptr, cudaMalloc(&s.d_seeds, kChunkRuns * sizeof(uint32_t)));
-        JNE_CUDA(nullptr, cudaMalloc(&s.d_out, kChunkRuns * 16 * sizeof(double)));
+        JNE_CUDA(nullptr, cudaMalloc(&s.d_out, kChunkRuns * kMaxWidth * sizeof(double)));
         JNE_CUDA(nullptr, cudaMallocHost(&s.h_seeds, kChunkRuns * sizeof(uint32_t)));
-        JNE_CUDA(nullptr, cudaMallocHost(&s.h_out, kChunkRuns * 16 * sizeof(double)));
+        JNE_CUDA(nullptr, cudaMallocHost(&s.h_out, kChunkRuns * kMaxWidth * sizeof(double)));
         JNE_CUDA(nullptr, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
       }
       JNE_CUDA(nullptr, cudaMalloc(&dv.d_err, sizeof(unsigned int)));
@@ -375,7 +393,44 @@ int jne_eigs_batch(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, co
   int rc = validate(ctx, model, dim, steps);
   if (rc) return rc;
   if (n && (!seeds || !out)) return fail(ctx, JNE_ERR_INVALID_ARG, "seeds/out is NULL");
-  return eigs_batch_sync(ctx, model, dim, steps, seeds, n, out);
+  return eigs_batch_sync(ctx, 1u << model, dim, steps, seeds, n, out);
+}
+
+int jne_eigs_batch_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps, const uint32_t* seeds,
+                         uint64_t n, double* out) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  join_worker(ctx);
+  if (model_mask == 0 || model_mask > 31u) return fail(ctx, JNE_ERR_INVALID_ARG, "model_mask must select models 0..4");
+  for (int m = 0; m < 5; ++m)
+    if ((model_mask >> m) & 1u) { int rc = validate(ctx, (uint8_t)m, dim, steps); if (rc) return rc; }
+  if (n && (!seeds || !out)) return fail(ctx, JNE_ERR_INVALID_ARG, "seeds/out is NULL");
+  return eigs_batch_sync(ctx, model_mask, dim, steps, seeds, n, out);
+}
+
+int jne_multi_width(uint32_t model_mask, uint32_t dim) {
+  if (model_mask == 0 || model_mask > 31u || dim < 1 || dim > 255) return JNE_ERR_INVALID_ARG;
+  return (int)mask_width(model_mask, dim);
+}
+
+int jne_eigs_batch_multi_device(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps, const void* d_seeds,
+                                uint64_t n, void* d_out, void* stream) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  if (model_mask == 0 || model_mask > 31u) return fail(ctx, JNE_ERR_INVALID_ARG, "model_mask must select models 0..4");
+  for (int m = 0; m < 5; ++m)
+    if ((model_mask >> m) & 1u) { int rc = validate(ctx, (uint8_t)m, dim, steps); if (rc) return rc; }
+  if (n == 0) return JNE_OK;
+  if (!d_seeds || !d_out) return fail(ctx, JNE_ERR_INVALID_ARG, "d_seeds/d_out is NULL");
+  Device& dv = ctx->devs[0];
+  JNE_CUDA(ctx, cudaSetDevice(dv.id));
+  const JneRunParams prm = make_params_mask(model_mask, dim, steps, false);
+  const uint64_t max_runs = (uint64_t)0x7fffffffu * JNE_WARPS_PER_CTA;
+  for (uint64_t off = 0; off < n; off += max_runs) {
+    const uint64_t m = std::min(max_runs, n - off);
+    JNE_CUDA(ctx, launch_run<true>((const uint32_t*)d_seeds + off, nullptr, m, prm, (double*)d_out + off * prm.out_stride,
+                                   dv.d_err, nullptr, (cudaStream_t)stream));
+    ctx->launches.fetch_add(1);
+  }
+  return JNE_OK;
 }
 
 int64_t jne_submit(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
@@ -389,7 +444,7 @@ int64_t jne_submit(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, co
   auto copy = std::make_shared<std::vector<uint32_t>>(seeds, seeds + n);
   ctx->pending_ticket = ctx->next_ticket++;
   ctx->worker = std::thread([ctx, model, dim, steps, copy, n, out]() {
-    ctx->pending_status = eigs_batch_sync(ctx, model, dim, steps, copy->data(), n, out);
+    ctx->pending_status = eigs_batch_sync(ctx, 1u << model, dim, steps, copy->data(), n, out);
   });
   return ctx->pending_ticket;
 }

@@ -33,6 +33,8 @@ struct JneRunParams {
   uint32_t model;      // 0..4
   uint32_t p;          // eigenvalues per run
   uint32_t full_blocks;  // leading 4-step blocks that are inside the segment for every lane
+  uint32_t model_mask;   // bit m set: solve model m (multi-model launches; single-model launches set one bit)
+  uint32_t out_stride;   // doubles per run in `out` (sum of p over the selected models)
   double T;            // (double)steps
   double factor;       // s^2 * T: 1 for the RNG path (s^2 = dt), T for caller-supplied increments
   double seg_n[4];     // steps in segment k
@@ -55,6 +57,7 @@ template <int DP> struct JneGeo {
   static constexpr int RAW_SZ = VV_SZ + VEC_SZ + TOT_SZ;          // raw segment moments ...
   static constexpr int WORK_SZ = 2 * MAT_SZ + MISC_SZ;            // ... aliased by the solver workspace
   static constexpr int WARP_SMEM = RAW_SZ > WORK_SZ ? RAW_SZ : WORK_SZ;
+  static constexpr int WARP_SMEM_MULTI = RAW_SZ + WORK_SZ;        // multi-model: raw moments stay live
 };
 
 __device__ __forceinline__ void jne_dmma(double& c0, double& c1, double a, double b) {
@@ -257,10 +260,10 @@ __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, doub
 // ---------------------------------------------------------------------------------------------
 template <int DP>
 __device__ __forceinline__ void jne_warp_assemble(const double* VV, const double* vec, double* tot,
-                                                  double* S2, double* R, const JneRunParams& prm) {
+                                                  double* S2, double* R, const JneRunParams& prm, int model, int p) {
   using G = JneGeo<DP>;
   const int lane = threadIdx.x & 31;
-  const int d = prm.dim, model = prm.model, p = prm.p;
+  const int d = prm.dim;
   const double T = prm.T;
   // tot[0]=S_B, [1]=S_1B, [2]=S_2B, [3]=S_z, [4]=S_1z, [5]=S_2z
   if (lane < 16) {
@@ -354,33 +357,43 @@ __device__ __forceinline__ void jne_warp_assemble(const double* VV, const double
 }
 
 // ---------------------------------------------------------------------------------------------
-// One block of 4 consecutive steps of the lane's segment: generate / load the increments, feed the
-// MMAs, update the path and the deterministic cross moments.  MASKED blocks (only the ragged tail
-// of the last segment, or tiny T) zero the contributions of steps at or beyond t_end.
+// The time loop works on blocks of 4 consecutive steps of the lane's segment, software-pipelined:
+// jne_gen4 produces the increments of block j+1 (Philox + Box-Muller, or global loads) while
+// jne_consume4 feeds block j to the MMAs.  The two are independent and branch-free, so ptxas
+// interleaves the RNG's IMAD.WIDE / MUFU chain with the DMMA stream of the same warp: both contend
+// for the shared FP64 pipe (profiles/r1_microbench_dmma_interference.txt), and a warp that only
+// alternates between the two phases leaves that pipe idle a quarter of the time.
 // ---------------------------------------------------------------------------------------------
-template <int DP, int DET, bool SRC_RNG, bool MASKED>
-__device__ __forceinline__ void jne_block4(uint32_t t, uint32_t t_end, uint32_t d, int g, int src_lane,
-                                           const jne_keys& keys, const double* __restrict__ dBrun,
-                                           double (&c)[JneGeo<DP>::NRT], double (&s0)[JneGeo<DP>::NRT],
-                                           double (&s1)[JneGeo<DP>::NRT], double (&s2)[JneGeo<DP>::NRT],
-                                           double (&u1)[JneGeo<DP>::NRT], double (&u2)[JneGeo<DP>::NRT],
-                                           double (&acc)[JneGeo<DP>::NT][2], double& w1, double w2c) {
+template <int DP, bool SRC_RNG> struct JneZ { using type = float; };
+template <int DP> struct JneZ<DP, false> { using type = double; };
+
+template <int DP, bool SRC_RNG>
+__device__ __forceinline__ void jne_gen4(uint32_t t, uint32_t t_end, uint32_t d, int g, const jne_keys& keys,
+                                         const float (&rowscale)[JneGeo<DP>::NRT], const double* __restrict__ dBrun,
+                                         typename JneZ<DP, SRC_RNG>::type (&z)[JneGeo<DP>::NRT][4]) {
   using G = JneGeo<DP>;
-  double z[G::NRT][4];
 #pragma unroll
   for (int j = 0; j < G::NRT; ++j) {
     const uint32_t row = 8 * j + g;
-    if (SRC_RNG) {
-      float zf[4] = {0.f, 0.f, 0.f, 0.f};
-      if (row < d) jne_normals4_keyed(keys, row, t >> 2, zf);
-#pragma unroll
-      for (int s = 0; s < 4; ++s) z[j][s] = (double)zf[s];
+    if constexpr (SRC_RNG) {
+      jne_normals4_keyed(keys, row, t >> 2, z[j], rowscale[j]);
     } else {
 #pragma unroll
-      for (int s = 0; s < 4; ++s)
-        z[j][s] = (row < d && (!MASKED || t + s < t_end)) ? dBrun[(uint64_t)(t + s) * d + row] : 0.0;
+      for (int s = 0; s < 4; ++s) z[j][s] = (row < d && t + s < t_end) ? dBrun[(uint64_t)(t + s) * d + row] : 0.0;
     }
   }
+}
+
+// MASKED blocks (only the ragged tail of the last segment, or tiny T) zero the contributions of
+// steps at or beyond t_end.
+template <int DP, int DET, bool SRC_RNG, bool MASKED>
+__device__ __forceinline__ void jne_consume4(uint32_t t, uint32_t t_end, int g, int src_lane,
+                                             const typename JneZ<DP, SRC_RNG>::type (&z)[JneGeo<DP>::NRT][4],
+                                             double (&c)[JneGeo<DP>::NRT], double (&s0)[JneGeo<DP>::NRT],
+                                             double (&s1)[JneGeo<DP>::NRT], double (&s2)[JneGeo<DP>::NRT],
+                                             double (&u1)[JneGeo<DP>::NRT], double (&u2)[JneGeo<DP>::NRT],
+                                             double (&acc)[JneGeo<DP>::NT][2], double& w1, double w2c) {
+  using G = JneGeo<DP>;
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
     const bool active = !MASKED || (t + s) < t_end;
@@ -388,7 +401,7 @@ __device__ __forceinline__ void jne_block4(uint32_t t, uint32_t t_end, uint32_t 
 #pragma unroll
     for (int j = 0; j < G::NRT; ++j) {
       f[j] = active ? c[j] : 0.0;
-      dz[j] = active ? z[j][s] : 0.0;
+      dz[j] = active ? (double)z[j][s] : 0.0;
       cn[j] = c[j] + dz[j];                  // B_t = B_{t-1} + dB_t   (src/matrix_utils.rs:51-63)
       if (!SRC_RNG) dz[j] = cn[j] - c[j];    // dB re-derived by subtraction (src/johansen_statistics.rs:80-82)
     }
@@ -414,7 +427,11 @@ __device__ __forceinline__ void jne_block4(uint32_t t, uint32_t t_end, uint32_t 
     for (int a = 0; a < G::NRT; ++a)
 #pragma unroll
       for (int b = a; b < G::NCT; ++b) {
+#ifdef JNE_EXP_NOMMA   // experiment only: no tensor work
+        acc[ti][0] += V[a]; acc[ti][1] += V[b];
+#else
         jne_dmma(acc[ti][0], acc[ti][1], V[a], V[b]);
+#endif
         ++ti;
       }
     // deterministic cross moments and the running path
@@ -437,21 +454,24 @@ __device__ __forceinline__ void jne_block4(uint32_t t, uint32_t t_end, uint32_t 
 // src/rng_matrix.rs:36) and the path is rebuilt exactly as src/johansen_statistics.rs:80-82 does.
 // DET: 0 = models 0,1 (sum c only), 1 = models 2,3 (+ w1 moments), 2 = model 4 (+ w2 moments).
 // ---------------------------------------------------------------------------------------------
-template <int DP, int DET, bool SRC_RNG>
+template <int DP, int DET, bool SRC_RNG, bool MULTI>
 __global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA)
 jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB, uint64_t n,
                JneRunParams prm, double* __restrict__ out, unsigned int* __restrict__ err_count,
                double* __restrict__ dbg /* optional: per run S2 (16x16) then R (16x16) */) {
   using G = JneGeo<DP>;
+  using ZT = typename JneZ<DP, SRC_RNG>::type;
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t run = (uint64_t)blockIdx.x * JNE_WARPS_PER_CTA + warp;
   if (run >= n) return;
-  double* wsm = smem + (size_t)warp * G::WARP_SMEM;
+  double* wsm = smem + (size_t)warp * (MULTI ? G::WARP_SMEM_MULTI : G::WARP_SMEM);
   double* VV = wsm;                 // raw view
   double* vec = VV + G::VV_SZ;
   double* tot = vec + G::VEC_SZ;
-  double* S2 = wsm;                 // work view (aliases the raw view, see jne_warp_assemble)
+  // work view: single-model launches alias it onto the raw view (see jne_warp_assemble); multi-model
+  // launches keep the raw moments live for the next model and place it behind them
+  double* S2 = MULTI ? wsm + G::RAW_SZ : wsm;
   double* R = S2 + G::MAT_SZ;
   double* misc = R + G::MAT_SZ;
 
@@ -461,6 +481,9 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   const uint32_t t_end = min(T, t_begin + prm.seg_len);
   const jne_keys keys = jne_make_keys(SRC_RNG ? seeds[run] : 0u, reinterpret_cast<volatile uint32_t*>(wsm));
   const double* dBrun = SRC_RNG ? nullptr : dB + run * (uint64_t)d * T;
+  float rowscale[G::NRT];
+#pragma unroll
+  for (int j = 0; j < G::NRT; ++j) rowscale[j] = (8u * j + g < d) ? 1.0f : 0.0f;
 
   double c[G::NRT], s0[G::NRT], s1[G::NRT], s2[G::NRT], u1[G::NRT], u2[G::NRT];
 #pragma unroll
@@ -474,12 +497,26 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   const int src_lane = (((g - G::B) & 7) << 2) | k;
 
   // blocks in which every lane's four steps are inside its segment need no masking
+  ZT zc[G::NRT][4], zn[G::NRT][4];
   uint32_t t = t_begin;
-  const uint32_t t_full = t_begin + 4u * prm.full_blocks;
-  for (; t < t_full; t += 4)
-    jne_block4<DP, DET, SRC_RNG, false>(t, t_end, d, g, src_lane, keys, dBrun, c, s0, s1, s2, u1, u2, acc, w1, w2c);
-  for (; t < t_begin + prm.seg_len; t += 4)
-    jne_block4<DP, DET, SRC_RNG, true>(t, t_end, d, g, src_lane, keys, dBrun, c, s0, s1, s2, u1, u2, acc, w1, w2c);
+  const uint32_t t_full = t_begin + 4u * prm.full_blocks, t_stop = t_begin + prm.seg_len;
+  jne_gen4<DP, SRC_RNG>(t, t_end, d, g, keys, rowscale, dBrun, zn);
+  for (; t < t_full; t += 4) {
+#pragma unroll
+    for (int j = 0; j < G::NRT; ++j)
+#pragma unroll
+      for (int s = 0; s < 4; ++s) zc[j][s] = zn[j][s];
+    jne_gen4<DP, SRC_RNG>(t + 4, t_end, d, g, keys, rowscale, dBrun, zn);
+    jne_consume4<DP, DET, SRC_RNG, false>(t, t_end, g, src_lane, zc, c, s0, s1, s2, u1, u2, acc, w1, w2c);
+  }
+  for (; t < t_stop; t += 4) {
+#pragma unroll
+    for (int j = 0; j < G::NRT; ++j)
+#pragma unroll
+      for (int s = 0; s < 4; ++s) zc[j][s] = zn[j][s];
+    jne_gen4<DP, SRC_RNG>(t + 4, t_end, d, g, keys, rowscale, dBrun, zn);
+    jne_consume4<DP, DET, SRC_RNG, true>(t, t_end, g, src_lane, zc, c, s0, s1, s2, u1, u2, acc, w1, w2c);
+  }
 
   // ---- dump raw moments to the warp's shared memory ----
   {
@@ -505,17 +542,30 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
     }
   }
   __syncwarp();
-  jne_warp_assemble<DP>(VV, vec, tot, S2, R, prm);
-  if (dbg != nullptr) {
-    double* o = dbg + run * 512;
-    for (int e = lane; e < 256; e += 32) {
-      const int i = e >> 4, j = e & 15;
-      o[e] = (i < (int)prm.p && j < (int)prm.p) ? S2[i * JNE_LD + j] : 0.0;
-      o[256 + e] = (i < (int)prm.p && j < (int)d) ? R[i * JNE_LD + j] : 0.0;
+  // ---- per model: assemble (Schur complements for the deterministic terms) and solve ----
+  // One Brownian path serves every selected model: the reference draws the path from (dim, steps, seed)
+  // only (src/rng_matrix.rs:11) and its CLI loops the models over the same seeds (src/main.rs:109).
+  bool ok = true;
+  uint32_t off = 0;
+#pragma unroll 1
+  for (int model = 0; model < 5; ++model) {
+    if (!((prm.model_mask >> model) & 1u)) continue;
+    const int p = (model == 1 || model == 3) ? (int)d + 1 : (int)d;
+    jne_warp_assemble<DP>(VV, vec, tot, S2, R, prm, model, p);
+    if (dbg != nullptr) {
+      double* o = dbg + run * 512;
+      for (int e = lane; e < 256; e += 32) {
+        const int i = e >> 4, j = e & 15;
+        o[e] = (i < p && j < p) ? S2[i * JNE_LD + j] : 0.0;
+        o[256 + e] = (i < p && j < (int)d) ? R[i * JNE_LD + j] : 0.0;
+      }
+      __syncwarp();
     }
+    ok &= jne_warp_pencil_solve(S2, R, misc, p, d, prm.factor, out + run * prm.out_stride + off);
+    off += p;
+    if (!MULTI) break;
     __syncwarp();
   }
-  const bool ok = jne_warp_pencil_solve(S2, R, misc, prm.p, d, prm.factor, out + run * prm.p);
   if (!ok && lane == 0) atomicAdd(err_count, 1u);
 }
 

@@ -76,11 +76,12 @@ __device__ __forceinline__ jne_u4 jne_philox4x32_10_keyed(uint32_t c0, uint32_t 
 // Two N(0,1) variates from two 32-bit words.  u = (wa + 1/2) 2^-32 in (0, 1], radius
 // r = sqrt(-2 ln u) <= 6.76; angle theta = 2 pi * int32(wb) * 2^-32 in [-pi, pi) so the MUFU
 // sin/cos see their most accurate range.
-__device__ __forceinline__ void jne_box_muller(uint32_t wa, uint32_t wb, float& z0, float& z1) {
+__device__ __forceinline__ void jne_box_muller(uint32_t wa, uint32_t wb, float& z0, float& z1, float scale = 1.0f) {
   const float u = fmaf(__uint2float_rn(wa), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
   float l, r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));   // MUFU.LG2 (u >= 2^-33: never denormal)
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -1.3862943611198906f));  // MUFU.SQRT
+  r *= scale;   // 1 (or 0 for a row the run does not have: keeps the generation branch-free)
   const float th = __int2float_rn((int)wb) * 1.4629180792671596e-9f;  // 2 pi 2^-32
   z0 = r * __cosf(th);
   z1 = r * __sinf(th);
@@ -92,8 +93,18 @@ __device__ __forceinline__ void jne_normals4(uint32_t seed, uint32_t row, uint32
   jne_box_muller(w.x, w.y, z[0], z[1]);
   jne_box_muller(w.z, w.w, z[2], z[3]);
 }
-__device__ __forceinline__ void jne_normals4_keyed(const jne_keys& ks, uint32_t row, uint32_t tb, float z[4]) {
+__device__ __forceinline__ void jne_normals4_keyed(const jne_keys& ks, uint32_t row, uint32_t tb, float z[4],
+                                                   float scale = 1.0f) {
+#ifdef JNE_EXP_NORNG   // experiment only: no Philox / Box-Muller (NOT a valid stream)
+  z[0] = scale * 0.5f; z[1] = -scale * (float)(row + 1) * 0.25f; z[2] = scale * 0.125f * (tb & 3); z[3] = -scale;
+  return;
+#endif
+#ifdef JNE_EXP_NOBM    // experiment only: Philox but no Box-Muller
+  { const jne_u4 w = jne_philox4x32_10_keyed(tb, row, ks);
+    z[0] = scale * __int_as_float((w.x >> 9) | 0x3f800000); z[1] = scale * __int_as_float((w.y >> 9) | 0x3f800000);
+    z[2] = scale * __int_as_float((w.z >> 9) | 0x3f800000); z[3] = scale * __int_as_float((w.w >> 9) | 0x3f800000); return; }
+#endif
   const jne_u4 w = jne_philox4x32_10_keyed(tb, row, ks);
-  jne_box_muller(w.x, w.y, z[0], z[1]);
-  jne_box_muller(w.z, w.w, z[2], z[3]);
+  jne_box_muller(w.x, w.y, z[0], z[1], scale);
+  jne_box_muller(w.z, w.w, z[2], z[3], scale);
 }

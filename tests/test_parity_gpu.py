@@ -252,3 +252,31 @@ def test_python_mirror_of_reference_call_sites(engine):
     assert sorted(got) == [1, 2, 3, 4, 5] and got[1] == ev
     for m in jne.JohansenModel:
         assert all(np.isfinite(jne.calculate_eigenvalues(2, 103, 7, m)))
+
+
+# ---- fused multi-model evaluation -----------------------------------
+def test_multi_model_is_bit_identical_to_per_model(engine):
+    """One pass over the path for several models == the per-model calls, bit for bit."""
+    seeds = np.arange(1, 2001, dtype=np.uint32)
+    for dim, T in [(1, 40), (3, 103), (5, 1000), (12, 500), (15, 64)]:
+        multi = engine.eigs_batch_multi(range(5), dim, T, seeds)
+        assert sorted(multi) == [0, 1, 2, 3, 4]
+        for m in range(5):
+            assert multi[m].shape == (seeds.size, dim + 1 if m in (1, 3) else dim)
+            assert np.array_equal(multi[m], engine.eigs_batch(m, dim, T, seeds)), (dim, T, m)
+    sub = engine.eigs_batch_multi([1, 4], 4, 200, seeds[:77])          # arbitrary subsets of models
+    assert sorted(sub) == [1, 4]
+    assert np.array_equal(sub[1], engine.eigs_batch(1, 4, 200, seeds[:77]))
+    assert np.array_equal(sub[4], engine.eigs_batch(4, 4, 200, seeds[:77]))
+    one = engine.eigs_batch_multi([3], 4, 200, seeds[:5])               # a single model through the multi entry
+    assert np.array_equal(one[3], engine.eigs_batch(3, 4, 200, seeds[:5]))
+
+
+def test_multi_model_full_size_vs_oracle(engine):
+    """dim 12, T 10 000: every model's block of the fused pass against the oracle fed the device normals."""
+    seeds = np.array([7, 8], dtype=np.uint32)
+    multi = engine.eigs_batch_multi(range(5), 12, 10000, seeds)
+    for i, s in enumerate(seeds):
+        z = engine.gen_normal_matrix(12, 10000, int(s))
+        for m in range(5):
+            assert_close(multi[m][i], orc.eigs_from_normals(z, m), f"model {m}")
