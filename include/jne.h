@@ -130,6 +130,15 @@ int jne_pencil_eigs_batch(jne_ctx* ctx, uint32_t p, uint32_t d, const double* S1
 int jne_eigs_batch_debug(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps,
                          const uint32_t* seeds, uint64_t n, double* out, double* mats);
 
+/* ---- orchestration helper (C++ mirror in csrc/jne_host.hpp) -------------------------------------- */
+
+/* run_model_simulation (src/data_storage/parallel_compute.rs:150-232) for one (model, dim, steps, num_runs) job:
+ * resume scan of `filename` -> remaining seeds of 1..=num_runs -> GPU batches -> batched EIGENVALS_V6 append ->
+ * trailer.  Creates its own context over device_ids (NULL / 0 = all GPUs); `ctx` is reserved and may be NULL.
+ * stats (3 x u64, may be NULL): records present before, records computed now, records in the file after. */
+int jne_run_model_simulation(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, uint64_t num_runs,
+                             const char* filename, int quiet, const int* device_ids, int n_devices, uint64_t* stats);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 
 /* Register-resident DFMA (mode 0) or mma.sync.m8n8k4.f64 (mode 1) throughput on device 0 of the

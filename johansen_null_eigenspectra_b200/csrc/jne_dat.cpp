@@ -1,0 +1,356 @@
+// Batched EIGENVALS_V6 writer / reader / resume scan (include/jne_dat.h).  Host-only.
+#include <cerrno>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "../../include/jne.h"
+#include "../../include/jne_dat.h"
+
+namespace {
+
+const char kMagic[12] = {'E', 'I', 'G', 'E', 'N', 'V', 'A', 'L', 'S', '_', 'V', '6'};
+const char kEof[8] = {'E', 'O', 'F', '_', 'M', 'A', 'R', 'K'};
+constexpr long kHeader = 18, kTrailer = 17;
+
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return JNE_ERR_IO; }
+
+// Cursor over a whole file held in memory-sized chunks: files are read through a large stdio buffer.
+struct Reader {
+  FILE* f = nullptr;
+  std::vector<char> buf;
+  ~Reader() { if (f) fclose(f); }
+  bool open(const char* path) {
+    f = fopen(path, "rb");
+    if (!f) return false;
+    buf.resize(4u << 20);
+    setvbuf(f, buf.data(), _IOFBF, buf.size());
+    return true;
+  }
+};
+
+struct Header { uint8_t model, dim; uint32_t steps; };
+
+// 0 ok, 1 file too short for a header, -1 magic mismatch
+int read_header(FILE* f, Header* h) {
+  unsigned char b[kHeader];
+  if (fread(b, 1, kHeader, f) != (size_t)kHeader) return 1;
+  if (memcmp(b, kMagic, 12) != 0) return -1;
+  h->model = b[12]; h->dim = b[13];
+  h->steps = (uint32_t)b[14] | ((uint32_t)b[15] << 8) | ((uint32_t)b[16] << 16) | ((uint32_t)b[17] << 24);
+  return 0;
+}
+
+bool read_trailer(FILE* f, long file_len, uint64_t* count, uint32_t* per_run) {
+  if (file_len < kHeader + kTrailer) return false;
+  if (fseek(f, file_len - kTrailer, SEEK_SET) != 0) return false;
+  unsigned char b[kTrailer];
+  if (fread(b, 1, kTrailer, f) != (size_t)kTrailer) return false;
+  if (memcmp(b, kEof, 8) != 0) return false;
+  uint64_t c = 0;
+  for (int i = 0; i < 8; ++i) c |= (uint64_t)b[8 + i] << (8 * i);
+  *count = c; *per_run = b[16];
+  return true;
+}
+
+// Reads one ULEB128 u32 from a stream: >0 bytes consumed, 0 clean EOF before the first byte, <0 error.
+int read_uleb(FILE* f, uint32_t* v) {
+  uint32_t result = 0; int shift = 0, n = 0;
+  for (;;) {
+    int c = fgetc(f);
+    if (c == EOF) return n == 0 ? 0 : -1;
+    ++n;
+    if (n > 5) return -2;
+    const uint32_t bits = (uint32_t)c & 0x7F;
+    if (shift == 28 && bits > 0x0F) return -3;
+    result |= bits << shift;
+    shift += 7;
+    if (!(c & 0x80)) { *v = result; return n; }
+  }
+}
+
+// Walks the records from the current position (just behind the header).  on_record(seed, count, payload offset)
+// is called per COMPLETE record; returns the offset just behind the last complete record.
+// limit: stop after this many records (trailer-known fast path) or UINT64_MAX (scan path, reader.rs:157-216).
+template <class F>
+long walk(FILE* f, long file_len, uint64_t limit, bool scan, F&& on_record, uint64_t* n_out, std::string* err) {
+  long good_end = kHeader;
+  uint64_t n = 0;
+  fseek(f, kHeader, SEEK_SET);
+  while (n < limit) {
+    uint32_t seed;
+    const int used = read_uleb(f, &seed);
+    if (used <= 0) { if (!scan && err) *err = "Incomplete ULEB128 encoding"; break; }
+    const int cnt = fgetc(f);
+    if (cnt == EOF) break;
+    const long payload = ftell(f);
+    if (cnt == 0) {
+      if (scan) {   // a zero count followed by the EOF marker ends the data (reader.rs:178-190)
+        char e[8];
+        if (fread(e, 1, 8, f) == 8 && memcmp(e, kEof, 8) == 0) break;
+        fseek(f, payload, SEEK_SET);
+      } else { if (err) *err = "Invalid eigenvalue count: cannot be zero"; break; }
+    }
+    if (payload + 8L * cnt > file_len) break;        // torn record: dropped (reader.rs:199-210)
+    if (!on_record(seed, (uint32_t)cnt, payload)) break;
+    fseek(f, payload + 8L * cnt, SEEK_SET);
+    good_end = payload + 8L * cnt;
+    ++n;
+  }
+  *n_out = n;
+  return good_end;
+}
+
+long file_length(FILE* f) {
+  fseek(f, 0, SEEK_END);
+  return ftell(f);
+}
+
+}  // namespace
+
+struct jne_dat_writer {
+  FILE* f = nullptr;
+  std::vector<unsigned char> buf;
+  uint64_t written = 0;
+  uint32_t per_run = 0;   // 0 = not yet known
+  uint8_t model = 0, dim = 0;
+  uint32_t steps = 0;
+};
+
+extern "C" {
+
+const char* jne_dat_last_error(void) { return g_err.c_str(); }
+
+int jne_uleb128_encode(uint32_t value, uint8_t out[5]) {
+  int n = 0;
+  do {
+    uint8_t byte = value & 0x7F;
+    value >>= 7;
+    if (value) byte |= 0x80;
+    out[n++] = byte;
+  } while (value);
+  return n;
+}
+
+int jne_uleb128_encoded_size(uint32_t v) { return v < (1u << 7) ? 1 : v < (1u << 14) ? 2 : v < (1u << 21) ? 3 : v < (1u << 28) ? 4 : 5; }
+
+int jne_uleb128_decode(const uint8_t* bytes, size_t len, uint32_t* value) {
+  uint32_t result = 0; int shift = 0;
+  for (size_t i = 0; i < len; ++i) {
+    if (i + 1 > 5) return -2;                                   // EncodingTooLong
+    const uint32_t bits = bytes[i] & 0x7F;
+    if (shift == 28 && bits > 0x0F) return -3;                  // ValueTooLarge
+    result |= bits << shift;
+    shift += 7;
+    if (!(bytes[i] & 0x80)) { if (value) *value = result; return (int)i + 1; }
+  }
+  return -1;                                                    // IncompleteEncoding
+}
+
+uint64_t jne_dat_expected_file_size(uint64_t num_runs, uint32_t per_run) {
+  // total ULEB128 bytes of seeds 1..=num_runs by size class (file_format.rs:29-86)
+  auto upto = [](uint64_t n) {   // sum of encoded sizes of 1..n
+    const uint64_t lim[5] = {127, 16383, 2097151, 268435455, 4294967295ull};
+    uint64_t total = 0, lo = 0;
+    for (int k = 0; k < 5 && n > lo; ++k) { const uint64_t hi = n < lim[k] ? n : lim[k]; total += (hi - lo) * (k + 1); lo = lim[k]; }
+    return total;
+  };
+  const uint64_t seeds = num_runs == 0 ? 1 : upto(num_runs);
+  return kHeader + seeds + num_runs + 8ull * per_run * num_runs + kTrailer;
+}
+
+int jne_dat_info(const char* path, uint8_t* model, uint8_t* dim, uint32_t* steps, uint64_t* n_records,
+                 uint32_t* per_run, int* has_trailer) {
+  Reader r;
+  if (!r.open(path)) return fail(std::string("cannot open ") + path + ": " + strerror(errno));
+  const long len = file_length(r.f);
+  fseek(r.f, 0, SEEK_SET);
+  Header h{};
+  const int hr = read_header(r.f, &h);
+  if (hr < 0) return fail("File format error: magic header mismatch");
+  if (hr > 0) return fail("file too short for a header");
+  uint64_t count = 0; uint32_t pr = 0;
+  const bool trailer = read_trailer(r.f, len, &count, &pr);
+  if (!trailer) {
+    uint32_t first = 0;
+    walk(r.f, len, UINT64_MAX, true, [&](uint32_t, uint32_t c, long) { if (!first) first = c; return true; }, &count, nullptr);
+    pr = first;
+  }
+  if (model) *model = h.model;
+  if (dim) *dim = h.dim;
+  if (steps) *steps = h.steps;
+  if (n_records) *n_records = count;
+  if (per_run) *per_run = pr;
+  if (has_trailer) *has_trailer = trailer ? 1 : 0;
+  return JNE_OK;
+}
+
+int jne_dat_read(const char* path, uint32_t* seeds, double* eigs, uint64_t capacity, uint32_t p, uint64_t* n_read) {
+  Reader r;
+  if (!r.open(path)) return fail(std::string("cannot open ") + path + ": " + strerror(errno));
+  const long len = file_length(r.f);
+  fseek(r.f, 0, SEEK_SET);
+  Header h{};
+  const int hr = read_header(r.f, &h);
+  if (hr < 0) return fail("File format error: magic header mismatch");
+  if (hr > 0) return fail("file too short for a header");
+  uint64_t count = 0; uint32_t pr = 0;
+  const bool trailer = read_trailer(r.f, len, &count, &pr);
+  std::string err;
+  bool mismatch = false;
+  uint64_t n = 0;
+  const uint64_t limit = trailer ? (count < capacity ? count : capacity) : capacity;
+  walk(r.f, trailer ? len - kTrailer : len, limit, !trailer,
+       [&](uint32_t seed, uint32_t c, long payload) {
+         if (c != p) { mismatch = true; err = "Eigenvalue count mismatch: expected " + std::to_string(p) + ", actual " + std::to_string(c); return false; }
+         seeds[n] = seed;
+         fseek(r.f, payload, SEEK_SET);
+         if (fread(eigs + n * p, 8, p, r.f) != p) return false;   // little-endian host assumed (x86-64 / aarch64)
+         ++n;
+         return true;
+       }, &count, &err);
+  if (mismatch) return fail(err);
+  if (n_read) *n_read = n;
+  return JNE_OK;
+}
+
+int jne_dat_open(const char* path, uint8_t model, uint8_t dim, uint32_t steps, uint64_t* existing, jne_dat_writer** out) {
+  if (!path || !out) return fail("path/out is NULL");
+  *out = nullptr;
+  uint64_t have = 0; uint32_t per_run = 0;
+  bool fresh = access(path, F_OK) != 0;
+  if (!fresh) {
+    Reader r;
+    if (!r.open(path)) return fail(std::string("cannot open ") + path + ": " + strerror(errno));
+    const long len = file_length(r.f);
+    fseek(r.f, 0, SEEK_SET);
+    Header h{};
+    const int hr = read_header(r.f, &h);
+    if (hr < 0) {
+      fresh = true;                                  // foreign magic: recreate (writer.rs:116-150)
+    } else if (hr > 0) {
+      fresh = true;                                  // shorter than a header: nothing to keep
+    } else {
+      if (h.model != model) return fail("Model mismatch: file has model " + std::to_string(h.model) + ", expected " + std::to_string(model));
+      if (h.dim != dim) return fail("Dimension mismatch: file has dim " + std::to_string(h.dim) + ", expected " + std::to_string(dim));
+      if (h.steps != steps) return fail("Steps mismatch: file has steps " + std::to_string(h.steps) + ", expected " + std::to_string(steps));
+      uint64_t count = 0; uint32_t pr = 0;
+      const bool trailer = read_trailer(r.f, len, &count, &pr);
+      uint32_t first = 0;
+      const long good_end = walk(r.f, trailer ? len - kTrailer : len, trailer ? count : UINT64_MAX, !trailer,
+                                 [&](uint32_t, uint32_t c, long) { if (!first) first = c; return true; }, &have, nullptr);
+      per_run = first;
+      fclose(r.f); r.f = nullptr;
+      // drop the trailer (writer.rs:181-203) and any torn tail so that appended records stay parseable
+      if (truncate(path, good_end) != 0) return fail(std::string("truncate failed: ") + strerror(errno));
+    }
+  }
+  jne_dat_writer* w = new jne_dat_writer();
+  w->model = model; w->dim = dim; w->steps = steps; w->written = have; w->per_run = per_run;
+  w->f = fopen(path, fresh ? "wb" : "ab");
+  if (!w->f) { delete w; return fail(std::string("cannot open ") + path + " for writing: " + strerror(errno)); }
+  setvbuf(w->f, nullptr, _IONBF, 0);                 // batches are written whole: no second buffer
+  if (fresh) {
+    unsigned char h[kHeader];
+    memcpy(h, kMagic, 12); h[12] = model; h[13] = dim;
+    for (int i = 0; i < 4; ++i) h[14 + i] = (steps >> (8 * i)) & 0xFF;
+    if (fwrite(h, 1, kHeader, w->f) != (size_t)kHeader) { fclose(w->f); delete w; return fail("header write failed"); }
+  }
+  if (existing) *existing = have;
+  *out = w;
+  return JNE_OK;
+}
+
+int jne_dat_append_batch(jne_dat_writer* w, const uint32_t* seeds, const double* eigs, uint64_t n, uint32_t p) {
+  if (!w || !w->f) return fail("writer is closed");
+  if (p > 255) return fail("Too many eigenvalues: " + std::to_string(p) + " exceeds maximum of 255");
+  if (n == 0) return JNE_OK;
+  if (w->per_run == 0) w->per_run = p;
+  if (p != w->per_run)
+    return fail("Eigenvalue count mismatch: expected " + std::to_string(w->per_run) + ", actual " + std::to_string(p) +
+                " (model " + std::to_string(w->model) + ", dim " + std::to_string(w->dim) + ", steps " + std::to_string(w->steps) + ")");
+  const size_t rec_max = 5 + 1 + 8 * (size_t)p;
+  const uint64_t chunk = 1u << 16;
+  for (uint64_t a = 0; a < n; a += chunk) {
+    const uint64_t m = n - a < chunk ? n - a : chunk;
+    w->buf.resize(m * rec_max);
+    unsigned char* q = w->buf.data();
+    for (uint64_t i = 0; i < m; ++i) {
+      q += jne_uleb128_encode(seeds[a + i], q);
+      *q++ = (unsigned char)p;
+      memcpy(q, eigs + (a + i) * p, 8 * (size_t)p);   // f64 little-endian == host representation
+      q += 8 * (size_t)p;
+    }
+    const size_t bytes = q - w->buf.data();
+    if (fwrite(w->buf.data(), 1, bytes, w->f) != bytes) return fail(std::string("write failed: ") + strerror(errno));
+  }
+  w->written += n;
+  return JNE_OK;
+}
+
+int jne_dat_flush(jne_dat_writer* w) {
+  if (!w || !w->f) return fail("writer is closed");
+  return fflush(w->f) == 0 ? JNE_OK : fail(std::string("flush failed: ") + strerror(errno));
+}
+
+int jne_dat_finish(jne_dat_writer* w) {
+  if (!w || !w->f) return fail("writer is closed");
+  unsigned char t[kTrailer];
+  memcpy(t, kEof, 8);
+  for (int i = 0; i < 8; ++i) t[8 + i] = (w->written >> (8 * i)) & 0xFF;
+  t[16] = (unsigned char)w->per_run;
+  const bool ok = fwrite(t, 1, kTrailer, w->f) == (size_t)kTrailer && fflush(w->f) == 0;
+  fclose(w->f);
+  delete w;
+  return ok ? JNE_OK : fail("trailer write failed");
+}
+
+void jne_dat_abandon(jne_dat_writer* w) {
+  if (!w) return;
+  if (w->f) fclose(w->f);
+  delete w;
+}
+
+int jne_dat_completed_bitmap(const char* path, uint8_t model, uint8_t dim, uint32_t steps, uint64_t num_runs,
+                             uint8_t* bitmap, uint64_t* completed) {
+  if (!bitmap) return fail("bitmap is NULL");
+  memset(bitmap, 0, (num_runs + 7) / 8);
+  if (completed) *completed = 0;
+  if (access(path, F_OK) != 0) return JNE_OK;        // progress.rs:17-19
+  Reader r;
+  if (!r.open(path)) return JNE_OK;                  // unreadable: start over (progress.rs:51)
+  const long len = file_length(r.f);
+  fseek(r.f, 0, SEEK_SET);
+  Header h{};
+  if (read_header(r.f, &h) != 0) return JNE_OK;      // damaged: start over
+  if (h.model != model) return fail("Model mismatch: file has model " + std::to_string(h.model) + ", expected " + std::to_string(model));
+  if (h.dim != dim) return fail("Dimension mismatch: file has dim " + std::to_string(h.dim) + ", expected " + std::to_string(dim));
+  if (h.steps != steps) return fail("Steps mismatch: file has steps " + std::to_string(h.steps) + ", expected " + std::to_string(steps));
+  uint64_t count = 0; uint32_t pr = 0;
+  const bool trailer = read_trailer(r.f, len, &count, &pr);
+  uint64_t n = 0;
+  walk(r.f, trailer ? len - kTrailer : len, trailer ? count : UINT64_MAX, !trailer,
+       [&](uint32_t seed, uint32_t, long) {
+         if (seed >= 1 && seed <= num_runs) bitmap[(seed - 1) >> 3] |= (uint8_t)(1u << ((seed - 1) & 7));
+         return true;
+       }, &n, nullptr);
+  if (completed) *completed = n;
+  return JNE_OK;
+}
+
+uint64_t jne_dat_remaining_seeds(const uint8_t* bitmap, uint64_t num_runs, uint32_t* out, uint64_t capacity) {
+  uint64_t k = 0;
+  for (uint64_t s = 1; s <= num_runs; ++s) {
+    if (!(bitmap[(s - 1) >> 3] & (1u << ((s - 1) & 7)))) {
+      if (out && k < capacity) out[k] = (uint32_t)s;
+      ++k;
+    }
+  }
+  return k;
+}
+
+}  // extern "C"

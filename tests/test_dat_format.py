@@ -1,0 +1,163 @@
+"""CPU tests of the batched EIGENVALS_V6 writer / reader / resume scan
+against the byte vectors of the reference's DATA_FORMAT.md and its own storage tests.  (-m "not gpu")"""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from johansen_null_eigenspectra_b200 import JneError, dat
+
+
+# src/tests/data_storage/uleb128_unit_test.rs:4-30, uleb128_test.rs
+def test_uleb128_vectors():
+    enc = {0: [0x00], 1: [0x01], 127: [0x7F], 128: [0x80, 0x01], 255: [0xFF, 0x01], 256: [0x80, 0x02],
+           300: [0xAC, 0x02], 16383: [0xFF, 0x7F], 16384: [0x80, 0x80, 0x01]}
+    for v, b in enc.items():
+        assert dat.uleb128_encode(v) == bytes(b)
+        assert dat.uleb128_decode(bytes(b)) == (v, len(b))
+    sizes = {0: 1, 127: 1, 128: 2, 16383: 2, 16384: 3, 2097151: 3, 2097152: 4, 268435455: 4, 268435456: 5, 2**32 - 1: 5}
+    for v, n in sizes.items():
+        assert dat.uleb128_encoded_size(v) == n == len(dat.uleb128_encode(v))
+        assert dat.uleb128_decode(dat.uleb128_encode(v)) == (v, n)
+
+
+def test_uleb128_errors():   # uleb128_unit_test.rs:67-100
+    with pytest.raises(ValueError, match="Incomplete"):
+        dat.uleb128_decode(bytes([0x80]))
+    with pytest.raises(ValueError, match="Incomplete"):
+        dat.uleb128_decode(b"")
+    assert dat.uleb128_decode(bytes([0xFF, 0xFF, 0xFF, 0xFF, 0x0F])) == (2**32 - 1, 5)
+    with pytest.raises(ValueError, match="too large"):
+        dat.uleb128_decode(bytes([0xFF, 0xFF, 0xFF, 0xFF, 0x1F]))
+    with pytest.raises(ValueError, match="too long"):
+        dat.uleb128_decode(bytes([0x80, 0x80, 0x80, 0x80, 0x80, 0x01]))
+
+
+def test_bytes_match_data_format_md(tmp_path):
+    """DATA_FORMAT.md:98-150: header, two records, trailer, byte for byte."""
+    path = tmp_path / "eigenvalues_model0_dim1_steps10.dat"
+    w = dat.AppendOnlyWriter(path, 0, 1, 10)
+    w.append_eigenvalues(1, [1.0])
+    w.append_eigenvalues(300, [2.0])
+    w.finish()
+    raw = path.read_bytes()
+    header = bytes.fromhex("45 49 47 45 4E 56 41 4C 53 5F 56 36 00 01 0A 00 00 00")
+    rec1 = bytes.fromhex("01 01 3F F0 00 00 00 00 00 00")[:2] + struct.pack("<d", 1.0)
+    rec2 = bytes.fromhex("AC 02 01") + struct.pack("<d", 2.0)
+    trailer = b"EOF_MARK" + struct.pack("<Q", 2) + bytes([1])
+    assert raw == header + rec1 + rec2 + trailer
+    assert len(raw) == 18 + 10 + 11 + 17
+
+
+def test_expected_file_size_matches_written_file(tmp_path):
+    n, p = 20000, 3
+    path = tmp_path / "f.dat"
+    w = dat.AppendOnlyWriter(path, 2, 3, 77)
+    w.append_batch(np.arange(1, n + 1), np.random.default_rng(0).random((n, p)))
+    w.finish()
+    assert os.path.getsize(path) == dat.expected_file_size(n, p)     # file_format.rs:14-27
+    # DATA_FORMAT.md:83-96 example (dim 1, 10M records, seeds 0..9 999 999): its 47 886 371 bytes count header,
+    # seed, count byte and trailer but leave out the 8-byte eigenvalue of every record (doc drift); with the
+    # payload, and seeds 1..=10M as the code numbers them (progress.rs:58), the size differs by 3 bytes
+    assert abs(dat.expected_file_size(10_000_000, 1) - (47_886_371 + 80_000_000)) <= 3
+
+
+def test_round_trip_and_info(tmp_path):   # append_writer_test.rs round-trip / 1000 records
+    rng = np.random.default_rng(1)
+    seeds = rng.permutation(np.arange(1, 1001)).astype(np.uint32)
+    eigs = rng.random((1000, 13))
+    path = tmp_path / "rt.dat"
+    w = dat.AppendOnlyWriter(path, 3, 12, 10000)
+    assert w.existing_records == 0
+    w.append_batch(seeds[:400], eigs[:400])
+    w.append_batch(seeds[400:], eigs[400:])
+    w.finish()
+    info = dat.file_info(path)
+    assert info == {"model": 3, "dim": 12, "steps": 10000, "records": 1000, "eigenvalues_per_run": 13, "has_trailer": True}
+    s, e, m, d, t = dat.read_append_file(path)
+    assert (m, d, t) == (3, 12, 10000) and np.array_equal(s, seeds) and np.array_equal(e, eigs)
+
+
+def test_unfinished_file_is_scan_read_and_torn_record_dropped(tmp_path):   # append_writer_test.rs:66-89, reader.rs:199-210
+    path = tmp_path / "unfinished.dat"
+    w = dat.AppendOnlyWriter(path, 0, 2, 103)
+    w.append_batch([1, 2, 3], np.arange(6.0).reshape(3, 2))
+    w.abandon()                                   # no trailer
+    info = dat.file_info(path)
+    assert info["records"] == 3 and not info["has_trailer"] and info["eigenvalues_per_run"] == 2
+    with open(path, "ab") as f:                   # a torn 4th record: seed + count + half an eigenvalue
+        f.write(bytes([4, 2]) + b"\x00\x00\x00\x00")
+    s, e, *_ = dat.read_append_file(path)
+    assert list(s) == [1, 2, 3] and np.array_equal(e, np.arange(6.0).reshape(3, 2))
+    # re-opening truncates the torn tail and appends cleanly
+    w = dat.AppendOnlyWriter(path, 0, 2, 103)
+    assert w.existing_records == 3
+    w.append_batch([4], [[7.0, 8.0]])
+    w.finish()
+    s, e, *_ = dat.read_append_file(path)
+    assert list(s) == [1, 2, 3, 4] and list(e[3]) == [7.0, 8.0] and dat.file_info(path)["has_trailer"]
+
+
+def test_resume_removes_trailer_and_counts(tmp_path):   # writer.rs:79-115,181-203
+    path = tmp_path / "resume.dat"
+    w = dat.AppendOnlyWriter(path, 1, 2, 50)
+    w.append_batch([1, 2], np.ones((2, 3)))
+    w.finish()
+    w = dat.AppendOnlyWriter(path, 1, 2, 50)
+    assert w.existing_records == 2
+    w.append_batch([5], np.full((1, 3), 2.0))
+    w.finish()
+    info = dat.file_info(path)
+    assert info["records"] == 3 and info["has_trailer"]
+    assert os.path.getsize(path) == 18 + 3 * (1 + 1 + 24) + 17
+
+
+def test_header_mismatch_and_count_errors(tmp_path):   # append_writer_test.rs:143-227
+    path = tmp_path / "mm.dat"
+    w = dat.AppendOnlyWriter(path, 0, 2, 50)
+    w.append_batch([1], [[1.0, 2.0]])
+    with pytest.raises(JneError, match="Eigenvalue count mismatch: expected 2, actual 3"):
+        w.append_batch([2], [[1.0, 2.0, 3.0]])
+    with pytest.raises(JneError, match="Too many eigenvalues: 256 exceeds maximum of 255"):
+        w.append_batch([3], np.zeros((1, 256)))
+    w.finish()
+    with pytest.raises(JneError, match="Model mismatch: file has model 0, expected 1"):
+        dat.AppendOnlyWriter(path, 1, 2, 50)
+    with pytest.raises(JneError, match="Dimension mismatch: file has dim 2, expected 3"):
+        dat.AppendOnlyWriter(path, 0, 3, 50)
+    with pytest.raises(JneError, match="Steps mismatch: file has steps 50, expected 51"):
+        dat.AppendOnlyWriter(path, 0, 2, 51)
+    bad = tmp_path / "bad.dat"
+    bad.write_bytes(b"NOT_A_DAT_FILE_AT_ALL" * 3)
+    with pytest.raises(JneError, match="magic header mismatch"):
+        dat.file_info(bad)
+    w = dat.AppendOnlyWriter(bad, 0, 2, 50)          # foreign magic: recreated (writer.rs:116-150)
+    assert w.existing_records == 0
+    w.finish()
+    assert dat.file_info(bad)["records"] == 0
+
+
+def test_resume_scan_bitmap(tmp_path):   # progress.rs:11-61, integration/helpers.rs:25-68 (file rewritten without some seeds)
+    path = tmp_path / "p.dat"
+    assert dat.check_append_progress(path, 0, 2, 103, 5)[0] == 0             # missing file
+    assert list(dat.check_append_progress(path, 0, 2, 103, 5)[1]) == [1, 2, 3, 4, 5]
+    w = dat.AppendOnlyWriter(path, 0, 2, 103)
+    w.append_batch([1, 3, 5, 9], np.zeros((4, 2)))                           # 9 > num_runs: counted, not mapped
+    w.finish()
+    done, rem = dat.check_append_progress(path, 0, 2, 103, 5)
+    assert done == 4 and list(rem) == [2, 4]
+    with pytest.raises(JneError, match="Steps mismatch"):
+        dat.check_append_progress(path, 0, 2, 104, 5)
+    n = 100_000
+    big = tmp_path / "big.dat"
+    w = dat.AppendOnlyWriter(big, 4, 1, 10)
+    keep = np.setdiff1d(np.arange(1, n + 1), np.arange(7, n + 1, 1000))
+    w.append_batch(keep, np.zeros((keep.size, 1)))
+    w.abandon()
+    done, rem = dat.check_append_progress(big, 4, 1, 10, n)
+    assert done == keep.size and np.array_equal(rem, np.arange(7, n + 1, 1000))
+
+
+def test_filename():   # simulation_test.rs:68
+    assert dat.get_filename(0, 5, 999) == "data/eigenvalues_model0_dim5_steps999.dat"

@@ -1,0 +1,52 @@
+"""End-to-end orchestration on the GPU: run_model_simulation (C++ csrc/jne_host.cpp) -> batched EIGENVALS_V6 file,
+mirroring the reference's integration tests.  (-m gpu)"""
+import numpy as np
+import pytest
+
+from johansen_null_eigenspectra_b200 import dat
+
+pytestmark = pytest.mark.gpu
+
+
+def test_resumable_simulation(tmp_path, engine):
+    """src/tests/data_storage/integration/resumable.rs:4-76: model 0, dim 2, T 103, 5 runs; drop seeds 2 and 4 from
+    the file; re-run; every seed 1..5 present and each record identical (the reference asks 1e-10 on the sum)."""
+    path = tmp_path / "eigenvalues_model0_dim2_steps103.dat"
+    st = dat.run_model_simulation(0, 2, 103, 5, str(path), devices=[0])
+    assert st == {"completed_before": 0, "computed": 5, "total_in_file": 5}
+    seeds, eigs, m, d, t = dat.read_append_file(path)
+    assert (m, d, t) == (0, 2, 103) and sorted(seeds) == [1, 2, 3, 4, 5] and eigs.shape == (5, 2)   # basic_api.rs:35
+    first = {int(s): e.copy() for s, e in zip(seeds, eigs)}
+    # integration/helpers.rs:25-68: rewrite the file without seeds 2 and 4
+    keep = np.isin(seeds, [1, 3, 5])
+    path.unlink()
+    w = dat.AppendOnlyWriter(path, 0, 2, 103)
+    w.append_batch(seeds[keep], eigs[keep])
+    w.finish()
+    st = dat.run_model_simulation(0, 2, 103, 5, str(path), devices=[0])
+    assert st == {"completed_before": 3, "computed": 2, "total_in_file": 5}
+    seeds2, eigs2, *_ = dat.read_append_file(path)
+    assert sorted(seeds2) == [1, 2, 3, 4, 5]
+    for s, e in zip(seeds2, eigs2):
+        assert np.array_equal(e, first[int(s)])                 # bit-identical, stronger than 1e-10
+        assert np.array_equal(e, engine.eigs_batch(0, 2, 103, [int(s)])[0])
+    # a third run has nothing to do (parallel_compute.rs:182-198)
+    assert dat.run_model_simulation(0, 2, 103, 5, str(path), devices=[0])["computed"] == 0
+
+
+def test_all_models_files_and_mismatch_restart(tmp_path, engine):
+    """integration/multiple_models.rs:4-45 (all five models, finite values, seeds in 1..=num_runs) and the
+    delete-and-restart policy on a parameter mismatch (parallel_compute.rs:159-175)."""
+    for model in range(5):
+        path = tmp_path / f"eigenvalues_model{model}_dim2_steps211.dat"
+        st = dat.run_model_simulation(model, 2, 211, 300, str(path), devices=[0])
+        assert st["total_in_file"] == 300
+        seeds, eigs, m, d, t = dat.read_append_file(path)
+        assert m == model and np.all(np.isfinite(eigs)) and eigs.shape[1] == (3 if model in (1, 3) else 2)
+        assert sorted(seeds) == list(range(1, 301))
+        assert np.array_equal(eigs[np.argsort(seeds)], engine.eigs_batch(model, 2, 211, np.arange(1, 301)))
+    # same file name, different steps -> incompatible header -> removed and recomputed
+    path = tmp_path / "eigenvalues_model0_dim2_steps211.dat"
+    st = dat.run_model_simulation(0, 2, 212, 10, str(path), devices=[0])
+    assert st == {"completed_before": 0, "computed": 10, "total_in_file": 10}
+    assert dat.file_info(path)["steps"] == 212
