@@ -136,7 +136,7 @@ JneRunParams make_params(uint8_t model, uint32_t dim, uint32_t steps, bool from_
 template <int DP, bool MULTI> constexpr size_t cta_smem() {
   return (size_t)JNE_WARPS_PER_CTA * (MULTI ? JneGeo<DP>::WARP_SMEM_MULTI : JneGeo<DP>::WARP_SMEM) * sizeof(double);
 }
-constexpr size_t pencil_smem() { return (size_t)JNE_WARPS_PER_CTA * (2 * 16 * JNE_LD + 64) * sizeof(double); }
+constexpr size_t pencil_smem() { return (size_t)JNE_WARPS_PER_CTA * (2 * 16 * JNE_LD + 96) * sizeof(double); }
 
 template <int DP, int DET, bool RNG, bool MULTI>
 cudaError_t launch_one(const uint32_t* d_seeds, const double* d_dB, uint64_t n, const JneRunParams& prm,

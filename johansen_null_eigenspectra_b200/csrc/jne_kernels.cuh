@@ -52,7 +52,7 @@ template <int DP> struct JneGeo {
   static constexpr int VV_SZ = 8 * NRT * VV_LD;
   static constexpr int VEC_SZ = 6 * 4 * 16;
   static constexpr int MAT_SZ = 16 * JNE_LD;
-  static constexpr int MISC_SZ = 64;
+  static constexpr int MISC_SZ = 96;    // invd[16] cs[16] ev[16] pq[8 as int2] schedule[240 bytes]
   static constexpr int TOT_SZ = 7 * 16;
   static constexpr int RAW_SZ = VV_SZ + VEC_SZ + TOT_SZ;          // raw segment moments ...
   static constexpr int WORK_SZ = 2 * MAT_SZ + MISC_SZ;            // ... aliased by the solver workspace
@@ -92,19 +92,32 @@ __device__ __forceinline__ double jne_rsqrt(double x) {
   return y;
 }
 
+// Round-robin (circle method) pairing of ne players: slot 0 pairs player ne-1 with `step`, slot l pairs
+// (step + l) with (step - l) modulo ne-1.  Filled once per run into shared memory as bytes [step][slot][2].
+__device__ __forceinline__ void jne_build_schedule(unsigned char* sched, int ne) {
+  const int lane = threadIdx.x & 31, np = ne >> 1, m = ne - 1;
+  for (int e = lane; e < m * np; e += 32) {
+    const int step = e / np, l = e - step * np;
+    const int a = (l == 0) ? m : (step + l) % m;
+    const int b = (step + m - l) % m;
+    sched[2 * e] = (unsigned char)min(a, b);
+    sched[2 * e + 1] = (unsigned char)max(a, b);
+  }
+}
+
 __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, double* __restrict__ R,
                                                    double* __restrict__ misc, int p, int d, double factor,
-                                                   double* __restrict__ out) {
+                                                   double* __restrict__ out, bool build_schedule) {
   const int lane = threadIdx.x & 31;
-  double* invd = misc;        // [16]
-  double* cs = misc + 16;     // [8][2]
-  double* ev = misc + 32;     // [16] eigenvalues, [16..24) packed pair indices
+  double* invd = misc;                                            // [16]
+  double* cs = misc + 16;                                         // [8] x (c, s)
+  double* ev = misc + 32;                                         // [16]
+  int* pq = reinterpret_cast<int*>(misc + 48);                    // [8] x (p, q)
+  unsigned char* sched = reinterpret_cast<unsigned char*>(misc + 56);   // [15][8][2] bytes
 
-  // --- Cholesky, right-looking, lower triangle in place ---
+  // --- Cholesky S2 = L L', right-looking, lower triangle in place; only 1/l_jj is ever needed ---
   for (int j = 0; j < p; ++j) {
-    const double djj = S2[j * JNE_LD + j];
-    const double ljj = sqrt(djj);
-    const double inv = 1.0 / ljj;
+    const double inv = jne_rsqrt(S2[j * JNE_LD + j]);             // NaN for a non-positive pivot -> flagged below
     __syncwarp();
     if (lane == 0) invd[j] = inv;
     for (int i = j + 1 + lane; i < p; i += 32) S2[i * JNE_LD + j] *= inv;
@@ -126,20 +139,23 @@ __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, doub
       R[i * JNE_LD + lane] = w * invd[i];
     }
   }
-  __syncwarp();
-  // --- A = W W' into the S2 storage (L is dead now), zero-padded to ne x ne; two rows per pass ---
-  const int ne = (p + 1) & ~1;          // even number of players; for odd p index p is an all-zero row/col
+  // the pair schedule depends on d only: multi-model launches build it for the first model
+  const int ne = (d + 1) & ~1;          // even number of players; for odd d index d is an all-zero row/col
   const int npairs = ne >> 1;
+  if (build_schedule) jne_build_schedule(sched, ne);
+  __syncwarp();
+  // --- G = W'W (d x d; same non-zero spectrum as W W' and as the pencil) into the S2 storage (L is dead),
+  //     zero-padded to ne x ne; two rows per pass.  Models 1 and 3 (p = d+1) have rank d: their extra
+  //     eigenvalue is exactly 0 here (the reference's dggev returns O(1e-14) noise for it). ---
   double tr = 0.0;
   for (int i0 = 0; i0 < ne; i0 += 2) {
     const int i = i0 + (lane >> 4), j = lane & 15;
     if (j <= i) {
       double a = 0.0;
-      if (i < p)
-        for (int c = 0; c < d; ++c) a = fma(R[i * JNE_LD + c], R[j * JNE_LD + c], a);
+      if (i < d)
+        for (int r = 0; r < p; ++r) a = fma(R[r * JNE_LD + i], R[r * JNE_LD + j], a);
       if (i == j) tr += a;
-      // this phase only reads R and only writes S2, so the store needs no staging
-      S2[i * JNE_LD + j] = a;
+      S2[i * JNE_LD + j] = a;      // this phase only reads R and only writes S2: no staging needed
       S2[j * JNE_LD + i] = a;
     }
   }
@@ -147,11 +163,11 @@ __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, doub
   for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
   // --- block ownership: lane -> (P1 <= P2) pair slots; a second block only when npairs == 8 ---
   const int nblk = npairs * (npairs + 1) / 2;
-  int b1p = 0, b1q = 0, b2p = -1, b2q = 0;
+  int b1p = -1, b1q = 0, b2p = -1, b2q = 0;
   {
     int r = 0, k = lane;
     while (r < npairs && k >= npairs - r) { k -= npairs - r; ++r; }
-    if (r < npairs) { b1p = r; b1q = r + k; } else { b1p = -1; }
+    if (r < npairs) { b1p = r; b1q = r + k; }
     if (lane + 32 < nblk) {
       r = 0; k = lane + 32;
       while (k >= npairs - r) { k -= npairs - r; ++r; }
@@ -163,38 +179,36 @@ __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, doub
   // every quantity fed to the FP32-seeded reciprocals inside the float range
   {
     const double inv_tr = 1.0 / tr;
-    for (int e = lane; e < ne * ne; e += 32) {
-      const int i = e / ne, j = e - i * ne;
-      S2[i * JNE_LD + j] *= inv_tr;
+    for (int e = lane; e < ne * 16; e += 32) {
+      const int i = e >> 4, j = e & 15;
+      if (j < ne) S2[i * JNE_LD + j] *= inv_tr;
     }
     factor *= tr;
   }
   __syncwarp();
-  const double tol = 1.3877787807814457e-17;   // 2^-56 (x trace = 1)
-  int* pq = reinterpret_cast<int*>(ev + 16);               // [8][2]
-  for (int sweep = 0; sweep < 24; ++sweep) {
+  // Off-diagonals below 2^-50 (x trace = 1) are left alone: they move an eigenvalue by at most that much
+  // (second order unless degenerate), i.e. <= 1e-11 relative on the smallest eigenvalues seen here.
+  const double tol = 8.8817841970012523e-16;
+  for (int sweep = 0; sweep < 30; ++sweep) {
     int rotated = 0;
     for (int step = 0; step < ne - 1; ++step) {
-      // rotation of pair slot `lane` (circle method: player ne-1 fixed, the others rotate)
+      // rotation of pair slot `lane`.  tan(theta) from FP32 arithmetic (it only steers convergence);
+      // (c, s) normalised in FP64 so that every J is orthogonal to rounding.
       if (lane < npairs) {
-        const int a = (lane == 0) ? ne - 1 : (step + lane) % (ne - 1);
-        const int b = (step + (ne - 1) - lane) % (ne - 1);
-        const int pp = min(a, b), qq = max(a, b);
+        const int pp = sched[2 * (step * npairs + lane)], qq = sched[2 * (step * npairs + lane) + 1];
         double c = 1.0, s = 0.0;
         const double apq = S2[pp * JNE_LD + qq];
         if (fabs(apq) > tol) {
-          const double app = S2[pp * JNE_LD + pp], aqq = S2[qq * JNE_LD + qq];
-          const double theta = 0.5 * (aqq - app) * jne_rcp(apq);
-          const double h = fma(theta, theta, 1.0);
-          const double t = copysign(jne_rcp(fabs(theta) + h * jne_rsqrt(h)), theta);
+          const float diff = (float)(S2[qq * JNE_LD + qq] - S2[pp * JNE_LD + pp]);
+          const float th = __fdividef(diff, 2.0f * (float)apq);
+          const float tf = copysignf(__frcp_rn(fabsf(th) + sqrtf(fmaf(th, th, 1.0f))), th);
+          const double t = (double)tf;
           c = jne_rsqrt(fma(t, t, 1.0));
           s = t * c;
           rotated = 1;
         }
-        cs[2 * lane] = c;
-        cs[2 * lane + 1] = s;
-        pq[2 * lane] = pp;
-        pq[2 * lane + 1] = qq;
+        *reinterpret_cast<double2*>(cs + 2 * lane) = make_double2(c, s);
+        *reinterpret_cast<int2*>(pq + 2 * lane) = make_int2(pp, qq);
       }
       __syncwarp();
       // block pass: B <- J1' B J2 for the 2x2 block (rows of slot P1) x (cols of slot P2)
@@ -202,16 +216,20 @@ __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, doub
       for (int pass = 0; pass < 2; ++pass) {
         const int P1 = pass ? b2p : b1p, P2 = pass ? b2q : b1q;
         if (P1 >= 0) {
-          const double c1 = cs[2 * P1], s1 = cs[2 * P1 + 1], c2 = cs[2 * P2], s2 = cs[2 * P2 + 1];
+          const double2 r1 = *reinterpret_cast<const double2*>(cs + 2 * P1);
+          const double2 r2 = *reinterpret_cast<const double2*>(cs + 2 * P2);
+          const double c1 = r1.x, s1 = r1.y, c2 = r2.x, s2 = r2.y;
           if (s1 != 0.0 || s2 != 0.0) {
-            const int p1 = pq[2 * P1], q1 = pq[2 * P1 + 1], p2 = pq[2 * P2], q2 = pq[2 * P2 + 1];
+            const int2 i1 = *reinterpret_cast<const int2*>(pq + 2 * P1);
+            const int2 i2 = *reinterpret_cast<const int2*>(pq + 2 * P2);
+            const int p1 = i1.x, q1 = i1.y, p2 = i2.x, q2 = i2.y;
             const double x00 = S2[p1 * JNE_LD + p2], x01 = S2[p1 * JNE_LD + q2];
             const double x10 = S2[q1 * JNE_LD + p2], x11 = S2[q1 * JNE_LD + q2];
             const double r00 = fma(c1, x00, -s1 * x10), r01 = fma(c1, x01, -s1 * x11);   // J1' B
             const double r10 = fma(s1, x00, c1 * x10), r11 = fma(s1, x01, c1 * x11);
-            double y00 = fma(c2, r00, -s2 * r01), y01 = fma(s2, r00, c2 * r01);          // (.) J2
-            double y10 = fma(c2, r10, -s2 * r11), y11 = fma(s2, r10, c2 * r11);
-            if (P1 == P2) { y01 = 0.0; y10 = 0.0; }        // the annihilated element, exactly
+            const double y00 = fma(c2, r00, -s2 * r01), y11 = fma(s2, r10, c2 * r11);    // (.) J2
+            double y01 = fma(s2, r00, c2 * r01), y10 = fma(c2, r10, -s2 * r11);
+            if (P1 == P2) { y01 = 0.5 * (y01 + y10); y10 = y01; }   // the (nearly) annihilated element, kept symmetric
             S2[p1 * JNE_LD + p2] = y00; S2[p1 * JNE_LD + q2] = y01;
             S2[q1 * JNE_LD + p2] = y10; S2[q1 * JNE_LD + q2] = y11;
             if (P1 != P2) {                                 // mirror: the matrix is kept in full storage
@@ -225,10 +243,10 @@ __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, doub
     }
     if (!__any_sync(0xffffffffu, rotated)) break;
   }
-  // --- eigenvalues = factor * |diag|, sorted descending by rank counting ---
+  // --- eigenvalues = factor * |diag| (d of them, the other p - d are 0), sorted descending by rank counting ---
   double v = 0.0;
   if (lane < p) {
-    v = fabs(S2[lane * JNE_LD + lane]) * factor;
+    v = (lane < d) ? fabs(S2[lane * JNE_LD + lane]) * factor : 0.0 * factor;   // 0 * NaN keeps a failure visible
     ev[lane] = v;
   }
   __syncwarp();
@@ -561,7 +579,7 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
       }
       __syncwarp();
     }
-    ok &= jne_warp_pencil_solve(S2, R, misc, p, d, prm.factor, out + run * prm.out_stride + off);
+    ok &= jne_warp_pencil_solve(S2, R, misc, p, d, prm.factor, out + run * prm.out_stride + off, off == 0);
     off += p;
     if (!MULTI) break;
     __syncwarp();
@@ -582,13 +600,13 @@ jne_pencil_kernel(const double* __restrict__ S1, const double* __restrict__ S2in
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t run = (uint64_t)blockIdx.x * JNE_WARPS_PER_CTA + warp;
   if (run >= n) return;
-  double* S2 = smem + (size_t)warp * (2 * 16 * JNE_LD + 64);
+  double* S2 = smem + (size_t)warp * (2 * 16 * JNE_LD + 96);
   double* R = S2 + 16 * JNE_LD;
   double* misc = R + 16 * JNE_LD;
   for (int e = lane; e < p * p; e += 32) S2[(e / p) * JNE_LD + (e % p)] = S2in[run * p * p + e];
   for (int e = lane; e < p * d; e += 32) R[(e / d) * JNE_LD + (e % d)] = S1[run * p * d + e];
   __syncwarp();
-  const bool ok = jne_warp_pencil_solve(S2, R, misc, p, d, factor, out + run * p);
+  const bool ok = jne_warp_pencil_solve(S2, R, misc, p, d, factor, out + run * p, true);
   if (!ok && lane == 0) atomicAdd(err_count, 1u);
 }
 
