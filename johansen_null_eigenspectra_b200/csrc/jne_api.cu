@@ -114,15 +114,15 @@ JneRunParams make_params_mask(uint32_t mask, uint32_t dim, uint32_t steps, bool 
   p.model = 0;
   for (int m = 0; m < 5; ++m) if ((mask >> m) & 1u) p.model = m;   // highest selected model
   p.p = p.out_stride;   // doubles per run (== eigenvalues per run for a single model)
-  p.seg_len = 4u * ((steps + 15u) / 16u);
+  p.seg_len = 8u * ((steps + 31u) / 32u);
   p.T = (double)steps;
   p.factor = from_increments ? (double)steps : 1.0;
-  uint64_t full = p.seg_len / 4;
+  uint64_t full = p.seg_len / 8;
   for (int k = 0; k < 4; ++k) {
     const uint64_t a = std::min<uint64_t>((uint64_t)k * p.seg_len, steps);
     const uint64_t b = std::min<uint64_t>(a + p.seg_len, steps);
     p.seg_n[k] = (double)(b - a);
-    full = std::min<uint64_t>(full, (b - a) / 4);
+    full = std::min<uint64_t>(full, (b - a) / 8);
     segment_weights(a, b, steps, &p.seg_w1[k], &p.seg_w2[k]);
   }
   p.full_blocks = (uint32_t)full;

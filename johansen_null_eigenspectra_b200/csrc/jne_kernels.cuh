@@ -29,10 +29,10 @@
 struct JneRunParams {
   uint32_t dim;        // d
   uint32_t steps;      // T
-  uint32_t seg_len;    // steps per segment, multiple of 4
+  uint32_t seg_len;    // steps per segment, multiple of 8
   uint32_t model;      // 0..4
   uint32_t p;          // eigenvalues per run
-  uint32_t full_blocks;  // leading 4-step blocks that are inside the segment for every lane
+  uint32_t full_blocks;  // leading 8-step blocks that are inside the segment for every lane
   uint32_t model_mask;   // bit m set: solve model m (multi-model launches; single-model launches set one bit)
   uint32_t out_stride;   // doubles per run in `out` (sum of p over the selected models)
   double T;            // (double)steps
@@ -375,29 +375,54 @@ __device__ __forceinline__ void jne_warp_assemble(const double* VV, const double
 }
 
 // ---------------------------------------------------------------------------------------------
-// The time loop works on blocks of 4 consecutive steps of the lane's segment, software-pipelined:
-// jne_gen4 produces the increments of block j+1 (Philox + Box-Muller, or global loads) while
-// jne_consume4 feeds block j to the MMAs.  The two are independent and branch-free, so ptxas
-// interleaves the RNG's IMAD.WIDE / MUFU chain with the DMMA stream of the same warp: both contend
-// for the shared FP64 pipe (profiles/r1_microbench_dmma_interference.txt), and a warp that only
-// alternates between the two phases leaves that pipe idle a quarter of the time.
+// The time loop works on blocks of 8 consecutive steps of the lane's segment.  jne_gen8 produces the
+// block's increments (Philox + Box-Muller, or global loads), jne_consume8 feeds them to the MMAs.  Both
+// are branch-free.
+//
+// RNG balance: a Philox call yields 4 steps of one row, and a lane owns DP/8 rows (0.5, 1, 1.5 or 2).  With
+// 1.5 rows (DP = 12) lanes g >= 4 would idle through the second row's call, so the calls are spread over
+// all lanes instead: per 8 steps every lane generates its row g twice (steps 0-3, 4-7) and ONE block of a
+// row 8 + (g & 3) -- lanes g < 4 for steps 0-3, lanes g >= 4 for steps 4-7 -- and the upper lanes hand
+// theirs to lane g - 4 with four FP32 shuffles: 3 calls per lane instead of 4.  DP = 4 likewise: 1 instead of 2.
+// The value of element (row, step) is unchanged: it depends on (seed, row, step) only.
 // ---------------------------------------------------------------------------------------------
 template <int DP, bool SRC_RNG> struct JneZ { using type = float; };
 template <int DP> struct JneZ<DP, false> { using type = double; };
 
 template <int DP, bool SRC_RNG>
-__device__ __forceinline__ void jne_gen4(uint32_t t, uint32_t t_end, uint32_t d, int g, const jne_keys& keys,
-                                         const float (&rowscale)[JneGeo<DP>::NRT], const double* __restrict__ dBrun,
-                                         typename JneZ<DP, SRC_RNG>::type (&z)[JneGeo<DP>::NRT][4]) {
+__device__ __forceinline__ void jne_gen8(uint32_t t, uint32_t t_end, uint32_t d, int g, const jne_keys& keys,
+                                         const float (&rowscale)[JneGeo<DP>::NRT], float xscale,
+                                         const double* __restrict__ dBrun,
+                                         typename JneZ<DP, SRC_RNG>::type (&z)[JneGeo<DP>::NRT][8]) {
   using G = JneGeo<DP>;
+  if constexpr (!SRC_RNG) {
 #pragma unroll
-  for (int j = 0; j < G::NRT; ++j) {
-    const uint32_t row = 8 * j + g;
-    if constexpr (SRC_RNG) {
-      jne_normals4_keyed(keys, row, t >> 2, z[j], rowscale[j]);
-    } else {
+    for (int j = 0; j < G::NRT; ++j) {
+      const uint32_t row = 8 * j + g;
 #pragma unroll
-      for (int s = 0; s < 4; ++s) z[j][s] = (row < d && t + s < t_end) ? dBrun[(uint64_t)(t + s) * d + row] : 0.0;
+      for (int s = 0; s < 8; ++s) z[j][s] = (row < d && t + s < t_end) ? dBrun[(uint64_t)(t + s) * d + row] : 0.0;
+    }
+  } else if constexpr (G::B == 0) {           // DP = 8, 16: every lane owns whole rows
+#pragma unroll
+    for (int j = 0; j < G::NRT; ++j) {
+      jne_normals4_keyed(keys, 8 * j + g, t >> 2, &z[j][0], rowscale[j]);
+      jne_normals4_keyed(keys, 8 * j + g, (t >> 2) + 1, &z[j][4], rowscale[j]);
+    }
+  } else {                                    // DP = 4, 12: the last row slot is shared by lanes g and g ^ 4
+    constexpr int L = G::NRT - 1;             // the shared slot
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      jne_normals4_keyed(keys, 8 * j + g, t >> 2, &z[j][0], rowscale[j]);
+      jne_normals4_keyed(keys, 8 * j + g, (t >> 2) + 1, &z[j][4], rowscale[j]);
+    }
+    float x[4];
+    jne_normals4_keyed(keys, 8 * L + (g & 3), (t >> 2) + (g >> 2), x, xscale);
+    const bool low = g < 4;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const float other = __shfl_xor_sync(0xffffffffu, x[s], 16);    // lane g ^ 4, same segment
+      z[L][s] = low ? x[s] : 0.0f;
+      z[L][4 + s] = low ? other : 0.0f;
     }
   }
 }
@@ -405,15 +430,14 @@ __device__ __forceinline__ void jne_gen4(uint32_t t, uint32_t t_end, uint32_t d,
 // MASKED blocks (only the ragged tail of the last segment, or tiny T) zero the contributions of
 // steps at or beyond t_end.
 template <int DP, int DET, bool SRC_RNG, bool MASKED>
-__device__ __forceinline__ void jne_consume4(uint32_t t, uint32_t t_end, int g, int src_lane,
-                                             const typename JneZ<DP, SRC_RNG>::type (&z)[JneGeo<DP>::NRT][4],
+__device__ __forceinline__ void jne_consume8(uint32_t t, uint32_t t_end, int g, int src_lane,
+                                             const typename JneZ<DP, SRC_RNG>::type (&z)[JneGeo<DP>::NRT][8],
                                              double (&c)[JneGeo<DP>::NRT], double (&s0)[JneGeo<DP>::NRT],
                                              double (&s1)[JneGeo<DP>::NRT], double (&s2)[JneGeo<DP>::NRT],
-                                             double (&u1)[JneGeo<DP>::NRT], double (&u2)[JneGeo<DP>::NRT],
                                              double (&acc)[JneGeo<DP>::NT][2], double& w1, double w2c) {
   using G = JneGeo<DP>;
 #pragma unroll
-  for (int s = 0; s < 4; ++s) {
+  for (int s = 0; s < 8; ++s) {
     const bool active = !MASKED || (t + s) < t_end;
     double f[G::NRT], dz[G::NRT], cn[G::NRT];
 #pragma unroll
@@ -452,17 +476,18 @@ __device__ __forceinline__ void jne_consume4(uint32_t t, uint32_t t_end, int g, 
 #endif
         ++ti;
       }
-    // deterministic cross moments and the running path
+    // deterministic cross moments of the path (those of the increments follow by summation by parts in
+    // the epilogue: sum w z = w_last c_end - sum (w_t - w_{t-1}) c_t) and the running path
     double w2 = 0.0;
     if (DET >= 2) w2 = fma(3.0 * w1, w1, w2c);
 #pragma unroll
     for (int j = 0; j < G::NRT; ++j) {
       s0[j] += f[j];
-      if (DET >= 1) { s1[j] = fma(w1, f[j], s1[j]); u1[j] = fma(w1, dz[j], u1[j]); }
-      if (DET >= 2) { s2[j] = fma(w2, f[j], s2[j]); u2[j] = fma(w2, dz[j], u2[j]); }
+      if (DET >= 1) s1[j] = fma(w1, f[j], s1[j]);
+      if (DET >= 2) s2[j] = fma(w2, f[j], s2[j]);
       c[j] = cn[j];
     }
-    w1 += 2.0;
+    if (DET >= 1) w1 += 2.0;
   }
 }
 
@@ -502,38 +527,47 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   float rowscale[G::NRT];
 #pragma unroll
   for (int j = 0; j < G::NRT; ++j) rowscale[j] = (8u * j + g < d) ? 1.0f : 0.0f;
+  const float xscale = (8u * (G::NRT - 1) + (g & 3) < d) ? 1.0f : 0.0f;   // the shared row slot (DP = 4, 12)
 
-  double c[G::NRT], s0[G::NRT], s1[G::NRT], s2[G::NRT], u1[G::NRT], u2[G::NRT];
+  double c[G::NRT], s0[G::NRT], s1[G::NRT], s2[G::NRT];
 #pragma unroll
-  for (int j = 0; j < G::NRT; ++j) { c[j] = s0[j] = s1[j] = s2[j] = u1[j] = u2[j] = 0.0; }
+  for (int j = 0; j < G::NRT; ++j) { c[j] = s0[j] = s1[j] = s2[j] = 0.0; }
   double acc[G::NT][2];
 #pragma unroll
   for (int i = 0; i < G::NT; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
 
-  double w1 = 2.0 * (double)t_begin + 1.0 - prm.T;
+  const double w1_first = 2.0 * (double)t_begin + 1.0 - prm.T;
+  double w1 = w1_first;
   const double w2c = -(prm.T * prm.T - 1.0);
   const int src_lane = (((g - G::B) & 7) << 2) | k;
 
-  // blocks in which every lane's four steps are inside its segment need no masking
-  ZT zc[G::NRT][4], zn[G::NRT][4];
+  // blocks in which every lane's eight steps are inside its segment need no masking
+  ZT z[G::NRT][8];
   uint32_t t = t_begin;
-  const uint32_t t_full = t_begin + 4u * prm.full_blocks, t_stop = t_begin + prm.seg_len;
-  jne_gen4<DP, SRC_RNG>(t, t_end, d, g, keys, rowscale, dBrun, zn);
-  for (; t < t_full; t += 4) {
-#pragma unroll
-    for (int j = 0; j < G::NRT; ++j)
-#pragma unroll
-      for (int s = 0; s < 4; ++s) zc[j][s] = zn[j][s];
-    jne_gen4<DP, SRC_RNG>(t + 4, t_end, d, g, keys, rowscale, dBrun, zn);
-    jne_consume4<DP, DET, SRC_RNG, false>(t, t_end, g, src_lane, zc, c, s0, s1, s2, u1, u2, acc, w1, w2c);
+  const uint32_t t_full = t_begin + 8u * prm.full_blocks, t_stop = t_begin + prm.seg_len;
+  for (; t < t_full; t += 8) {
+    jne_gen8<DP, SRC_RNG>(t, t_end, d, g, keys, rowscale, xscale, dBrun, z);
+    jne_consume8<DP, DET, SRC_RNG, false>(t, t_end, g, src_lane, z, c, s0, s1, s2, acc, w1, w2c);
   }
-  for (; t < t_stop; t += 4) {
+  for (; t < t_stop; t += 8) {
+    jne_gen8<DP, SRC_RNG>(t, t_end, d, g, keys, rowscale, xscale, dBrun, z);
+    jne_consume8<DP, DET, SRC_RNG, true>(t, t_end, g, src_lane, z, c, s0, s1, s2, acc, w1, w2c);
+  }
+
+  // sum w1 z and sum w2 z over the lane's segment by summation by parts (z_t = c_{t+1} - c_t, c_0 = 0,
+  // w1_t - w1_{t-1} = 2, w2_t - w2_{t-1} = 12 w1_t - 12):
+  //   u1 = w1_last c_end - 2 sum c,      u2 = w2_last c_end - 12 sum w1 c + 12 sum c
+  double u1[G::NRT], u2[G::NRT];
+  {
+    const double nseg = (double)(t_end - t_begin);
+    const double w1_last = w1_first + 2.0 * (nseg - 1.0);
+    const double w2_last = fma(3.0 * w1_last, w1_last, w2c);
 #pragma unroll
-    for (int j = 0; j < G::NRT; ++j)
-#pragma unroll
-      for (int s = 0; s < 4; ++s) zc[j][s] = zn[j][s];
-    jne_gen4<DP, SRC_RNG>(t + 4, t_end, d, g, keys, rowscale, dBrun, zn);
-    jne_consume4<DP, DET, SRC_RNG, true>(t, t_end, g, src_lane, zc, c, s0, s1, s2, u1, u2, acc, w1, w2c);
+    for (int j = 0; j < G::NRT; ++j) {
+      const bool any = t_end > t_begin;
+      u1[j] = any ? fma(w1_last, c[j], -2.0 * s0[j]) : 0.0;
+      u2[j] = any ? fma(w2_last, c[j], 12.0 * (s0[j] - s1[j])) : 0.0;
+    }
   }
 
   // ---- dump raw moments to the warp's shared memory ----

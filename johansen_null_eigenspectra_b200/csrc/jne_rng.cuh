@@ -93,7 +93,7 @@ __device__ __forceinline__ void jne_normals4(uint32_t seed, uint32_t row, uint32
   jne_box_muller(w.x, w.y, z[0], z[1]);
   jne_box_muller(w.z, w.w, z[2], z[3]);
 }
-__device__ __forceinline__ void jne_normals4_keyed(const jne_keys& ks, uint32_t row, uint32_t tb, float z[4],
+__device__ __forceinline__ void jne_normals4_keyed(const jne_keys& ks, uint32_t row, uint32_t tb, float* z,
                                                    float scale = 1.0f) {
 #ifdef JNE_EXP_NORNG   // experiment only: no Philox / Box-Muller (NOT a valid stream)
   z[0] = scale * 0.5f; z[1] = -scale * (float)(row + 1) * 0.25f; z[2] = scale * 0.125f * (tb & 3); z[3] = -scale;
