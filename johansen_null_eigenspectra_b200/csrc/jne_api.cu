@@ -41,6 +41,7 @@ struct Device {
   Slot slot[2];
   unsigned int* d_err = nullptr;
   unsigned int* h_err = nullptr;  // pinned
+  unsigned char* d_sched = nullptr;   // 8 Jacobi pairing tables (ne = 2, 4, .., 16), 256 bytes each
   double* d_scratch = nullptr;    // increments / pencil inputs, grown on demand
   size_t scratch_bytes = 0;
 };
@@ -105,6 +106,24 @@ uint32_t mask_width(uint32_t mask, uint32_t dim) {
     if ((mask >> m) & 1u) w += (m == 1 || m == 3) ? dim + 1 : dim;
   return w;
 }
+
+// Round-robin (circle method) pairing of ne players: slot 0 pairs player ne-1 with `step`, slot l pairs
+// (step + l) with (step - l) modulo ne-1.  Bytes [step][slot][2], 256 per table, tables for ne = 2, 4, .., 16.
+void make_schedules(unsigned char* tables /* 8 x 256 */) {
+  std::memset(tables, 0, 8 * 256);
+  for (int ne = 2; ne <= 16; ne += 2) {
+    unsigned char* t = tables + (ne / 2 - 1) * 256;
+    const int np = ne / 2, m = ne - 1;
+    for (int step = 0; step < m; ++step)
+      for (int l = 0; l < np; ++l) {
+        const int a = (l == 0) ? m : (step + l) % m, b = (step + m - l) % m;
+        t[2 * (step * np + l)] = (unsigned char)std::min(a, b);
+        t[2 * (step * np + l) + 1] = (unsigned char)std::max(a, b);
+      }
+  }
+}
+
+const unsigned char* sched_for(const Device& dv, uint32_t d) { return dv.d_sched + (((d + 1) / 2) - 1) * 256; }
 
 JneRunParams make_params_mask(uint32_t mask, uint32_t dim, uint32_t steps, bool from_increments) {
   JneRunParams p{};
@@ -189,10 +208,12 @@ int drain(jne_ctx* ctx, Slot& s, uint32_t p, double* out) {
 }
 
 // One device's share of a host-buffer batch (called on its own host thread).
-int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm, const uint32_t* seeds, uint64_t n, double* out,
+int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32_t* seeds, uint64_t n, double* out,
               std::string* err_out) {
   auto body = [&]() -> int {
     JNE_CUDA(ctx, cudaSetDevice(dv.id));
+    JneRunParams prm = prm_in;
+    prm.sched = sched_for(dv, prm.dim);
     *dv.h_err = 0;
     JNE_CUDA(ctx, cudaMemsetAsync(dv.d_err, 0, sizeof(unsigned int), dv.stream));
     uint64_t done = 0;
@@ -329,6 +350,7 @@ void jne_shutdown(jne_ctx* ctx) {
       if (s.done) cudaEventDestroy(s.done);
     }
     if (dv.d_err) cudaFree(dv.d_err);
+    if (dv.d_sched) cudaFree(dv.d_sched);
     if (dv.h_err) cudaFreeHost(dv.h_err);
     if (dv.d_scratch) cudaFree(dv.d_scratch);
     if (dv.stream) cudaStreamDestroy(dv.stream);
@@ -373,6 +395,10 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
         JNE_CUDA(nullptr, cudaMallocHost(&s.h_out, kChunkRuns * kMaxWidth * sizeof(double)));
         JNE_CUDA(nullptr, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
       }
+      unsigned char tables[8 * 256];
+      make_schedules(tables);
+      JNE_CUDA(nullptr, cudaMalloc(&dv.d_sched, sizeof tables));
+      JNE_CUDA(nullptr, cudaMemcpy(dv.d_sched, tables, sizeof tables, cudaMemcpyHostToDevice));
       JNE_CUDA(nullptr, cudaMalloc(&dv.d_err, sizeof(unsigned int)));
       JNE_CUDA(nullptr, cudaMemset(dv.d_err, 0, sizeof(unsigned int)));
       JNE_CUDA(nullptr, cudaMallocHost(&dv.h_err, sizeof(unsigned int)));
@@ -422,7 +448,8 @@ int jne_eigs_batch_multi_device(jne_ctx* ctx, uint32_t model_mask, uint32_t dim,
   if (!d_seeds || !d_out) return fail(ctx, JNE_ERR_INVALID_ARG, "d_seeds/d_out is NULL");
   Device& dv = ctx->devs[0];
   JNE_CUDA(ctx, cudaSetDevice(dv.id));
-  const JneRunParams prm = make_params_mask(model_mask, dim, steps, false);
+  JneRunParams prm = make_params_mask(model_mask, dim, steps, false);
+  prm.sched = sched_for(dv, dim);
   const uint64_t max_runs = (uint64_t)0x7fffffffu * JNE_WARPS_PER_CTA;
   for (uint64_t off = 0; off < n; off += max_runs) {
     const uint64_t m = std::min(max_runs, n - off);
@@ -466,7 +493,8 @@ int jne_eigs_batch_device(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t st
   if (!d_seeds || !d_out) return fail(ctx, JNE_ERR_INVALID_ARG, "d_seeds/d_out is NULL");
   Device& dv = ctx->devs[0];
   JNE_CUDA(ctx, cudaSetDevice(dv.id));
-  const JneRunParams prm = make_params(model, dim, steps, false);
+  JneRunParams prm = make_params(model, dim, steps, false);
+  prm.sched = sched_for(dv, dim);
   // grid.x is 32-bit: split very large batches
   const uint64_t max_runs = (uint64_t)0x7fffffffu * JNE_WARPS_PER_CTA;
   for (uint64_t off = 0; off < n; off += max_runs) {
@@ -494,10 +522,12 @@ int jne_check_async(jne_ctx* ctx) {
   return JNE_OK;
 }
 
-static int single_device_run(jne_ctx* ctx, const JneRunParams& prm, const uint32_t* seeds, const double* dB,
+static int single_device_run(jne_ctx* ctx, const JneRunParams& prm_in, const uint32_t* seeds, const double* dB,
                              uint64_t n, double* out, double* mats) {
   Device& dv = ctx->devs[0];
   JNE_CUDA(ctx, cudaSetDevice(dv.id));
+  JneRunParams prm = prm_in;
+  prm.sched = sched_for(dv, prm.dim);
   const bool rng = dB == nullptr;
   const uint64_t per_run_in = rng ? 0 : (uint64_t)prm.dim * prm.steps;
   // bound the scratch: <= 1 GiB of increments, <= 2^18 runs per launch
@@ -620,7 +650,7 @@ int jne_pencil_eigs_batch(jne_ctx* ctx, uint32_t p, uint32_t d, const double* S1
     JNE_CUDA(ctx, cudaMemcpyAsync(d1, S1 + off * p * d, m * p * d * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
     JNE_CUDA(ctx, cudaMemcpyAsync(d2, S2 + off * p * p, m * p * p * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
     jne_pencil_kernel<<<(unsigned)((m + JNE_WARPS_PER_CTA - 1) / JNE_WARPS_PER_CTA), 32 * JNE_WARPS_PER_CTA, pencil_smem(), dv.stream>>>(
-        d1, d2, m, (int)p, (int)d, 1.0, dout, dv.d_err);
+        d1, d2, m, (int)p, (int)d, 1.0, dout, dv.d_err, sched_for(dv, d));
     JNE_CUDA(ctx, cudaGetLastError());
     ctx->launches.fetch_add(1);
     JNE_CUDA(ctx, cudaMemcpyAsync(out + off * p, dout, m * p * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));

@@ -35,6 +35,7 @@ struct JneRunParams {
   uint32_t full_blocks;  // leading 8-step blocks that are inside the segment for every lane
   uint32_t model_mask;   // bit m set: solve model m (multi-model launches; single-model launches set one bit)
   uint32_t out_stride;   // doubles per run in `out` (sum of p over the selected models)
+  const unsigned char* sched;   // device pointer: round-robin Jacobi pairing for ne = even(dim), [step][slot][2] bytes
   double T;            // (double)steps
   double factor;       // s^2 * T: 1 for the RNG path (s^2 = dt), T for caller-supplied increments
   double seg_n[4];     // steps in segment k
@@ -54,10 +55,16 @@ template <int DP> struct JneGeo {
   static constexpr int MAT_SZ = 16 * JNE_LD;
   static constexpr int MISC_SZ = 96;    // invd[16] cs[16] ev[16] pq[8 as int2] schedule[240 bytes]
   static constexpr int TOT_SZ = 7 * 16;
-  static constexpr int RAW_SZ = VV_SZ + VEC_SZ + TOT_SZ;          // raw segment moments ...
-  static constexpr int WORK_SZ = 2 * MAT_SZ + MISC_SZ;            // ... aliased by the solver workspace
-  static constexpr int WARP_SMEM = RAW_SZ > WORK_SZ ? RAW_SZ : WORK_SZ;
-  static constexpr int WARP_SMEM_MULTI = RAW_SZ + WORK_SZ;        // multi-model: raw moments stay live
+  // per-warp layout (doubles):  [0, TOT) totals | raw: VV, vec  -- after stitching the raw area is dead and
+  // [TOT, TOT + STITCH) holds the model-independent stitched moments M_BB, M_Bz (16 x 16 each)
+  static constexpr int RAW_SZ = TOT_SZ + VV_SZ + VEC_SZ;
+  static constexpr int STITCH_SZ = 2 * 256;
+  static constexpr int WORK_SZ = 2 * MAT_SZ + MISC_SZ;            // solver workspace
+  // single-model launches: the workspace aliases the stitched moments (entries pass through registers)
+  static constexpr int WARP_SMEM = RAW_SZ > TOT_SZ + WORK_SZ ? RAW_SZ : TOT_SZ + WORK_SZ;
+  // multi-model launches: the stitched moments stay live for the next model, the workspace sits behind them
+  static constexpr int WARP_SMEM_MULTI =
+      RAW_SZ > TOT_SZ + STITCH_SZ + WORK_SZ ? RAW_SZ : TOT_SZ + STITCH_SZ + WORK_SZ;
 };
 
 __device__ __forceinline__ void jne_dmma(double& c0, double& c1, double a, double b) {
@@ -94,20 +101,17 @@ __device__ __forceinline__ double jne_rsqrt(double x) {
 
 // Round-robin (circle method) pairing of ne players: slot 0 pairs player ne-1 with `step`, slot l pairs
 // (step + l) with (step - l) modulo ne-1.  Filled once per run into shared memory as bytes [step][slot][2].
-__device__ __forceinline__ void jne_build_schedule(unsigned char* sched, int ne) {
-  const int lane = threadIdx.x & 31, np = ne >> 1, m = ne - 1;
-  for (int e = lane; e < m * np; e += 32) {
-    const int step = e / np, l = e - step * np;
-    const int a = (l == 0) ? m : (step + l) % m;
-    const int b = (step + m - l) % m;
-    sched[2 * e] = (unsigned char)min(a, b);
-    sched[2 * e + 1] = (unsigned char)max(a, b);
-  }
+// The host precomputes the table for the launch's dimension (jne_api.cu, make_schedule); the warp copies its
+// 240 bytes into shared memory.  src == nullptr: keep the table already there (next model of the same run).
+__device__ __forceinline__ void jne_load_schedule(unsigned char* sched, const unsigned char* __restrict__ src) {
+  const int lane = threadIdx.x & 31;
+  if (lane < 30) reinterpret_cast<uint2*>(sched)[lane] = reinterpret_cast<const uint2*>(src)[lane];
 }
 
 __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, double* __restrict__ R,
                                                    double* __restrict__ misc, int p, int d, double factor,
-                                                   double* __restrict__ out, bool build_schedule) {
+                                                   double* __restrict__ out,
+                                                   const unsigned char* __restrict__ sched_src) {
   const int lane = threadIdx.x & 31;
   double* invd = misc;                                            // [16]
   double* cs = misc + 16;                                         // [8] x (c, s)
@@ -142,7 +146,7 @@ __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, doub
   // the pair schedule depends on d only: multi-model launches build it for the first model
   const int ne = (d + 1) & ~1;          // even number of players; for odd d index d is an all-zero row/col
   const int npairs = ne >> 1;
-  if (build_schedule) jne_build_schedule(sched, ne);
+  if (sched_src != nullptr) jne_load_schedule(sched, sched_src);
   __syncwarp();
   // --- G = W'W (d x d; same non-zero spectrum as W W' and as the pencil) into the S2 storage (L is dead),
   //     zero-padded to ne x ne; two rows per pass.  Models 1 and 3 (p = d+1) have rank d: their extra
@@ -265,25 +269,23 @@ __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, doub
 }
 
 // ---------------------------------------------------------------------------------------------
-// Assembly: raw segment moments (shared memory) -> per-model S2 (p x p) and R = S1' (p x d).
+// Epilogue part 1, once per run: stitch the four segments (model-independent).
 //   VV  [8*NRT][VV_LD] : sum over segments and steps of V V', V = [c (DP rows) ; z (DP rows)]
 //   vec [6][4][16]     : per segment k and row r:  0 e = c_end, 1 s0 = sum c, 2 s1 = sum w1 c,
 //                        3 s2 = sum w2 c, 4 u1 = sum w1 z, 5 u2 = sum w2 z
-//   tot [7][16]        : whole-run totals (scratch)
-// S2 / R ALIAS the raw area: every entry is first computed into registers, then, after a warp
-// barrier, stored -- this halves the shared memory per warp and doubles the resident warps.
-// F per model follows src/johansen_statistics.rs:102-197.  Row scalings of
-// F leave the pencil's eigenvalues unchanged, so the trend row is carried as (w1+1)/T
-// (= 2 (tau - 1/2)) and the detrended tau^2 row as w2/T^2 (= 12 x its residual on [1, tau]).
+// out:
+//   tot [6][16]        : whole-run totals  0 S_B = sum B, 1 S_1B = sum w1 B, 2 S_2B = sum w2 B,
+//                        3 S_z = sum dB, 4 S_1z = sum w1 dB, 5 S_2z = sum w2 dB
+//   MBB, MBZ [16][16]  : sum B B' and sum B dB' with B = b0 + c:  sum (b0+c)(b0+c)' =
+//                        n b0 b0' + b0 (sum c)' + (sum c) b0' + sum c c'   
+// MBB / MBZ ALIAS the raw area: every entry is computed into registers, then, after a warp barrier, stored.
 // ---------------------------------------------------------------------------------------------
 template <int DP>
-__device__ __forceinline__ void jne_warp_assemble(const double* VV, const double* vec, double* tot,
-                                                  double* S2, double* R, const JneRunParams& prm, int model, int p) {
+__device__ __forceinline__ void jne_warp_stitch(const double* VV, const double* vec, double* tot,
+                                                double* MBB, double* MBZ, const JneRunParams& prm) {
   using G = JneGeo<DP>;
   const int lane = threadIdx.x & 31;
   const int d = prm.dim;
-  const double T = prm.T;
-  // tot[0]=S_B, [1]=S_1B, [2]=S_2B, [3]=S_z, [4]=S_1z, [5]=S_2z
   if (lane < 16) {
     const int r = lane;
     double b0 = 0.0, sB = 0.0, s1B = 0.0, s2B = 0.0, sz = 0.0, s1z = 0.0, s2z = 0.0;
@@ -301,12 +303,6 @@ __device__ __forceinline__ void jne_warp_assemble(const double* VV, const double
     tot[0 * 16 + r] = sB;  tot[1 * 16 + r] = s1B; tot[2 * 16 + r] = s2B;
     tot[3 * 16 + r] = sz;  tot[4 * 16 + r] = s1z; tot[5 * 16 + r] = s2z;
   }
-  __syncwarp();
-  const int nb = (model == 2 || model == 4) ? d - 1 : d;   // Brownian rows kept in F
-  const double invT = 1.0 / T;
-  const double nu = T * (T * T - 1.0) / 3.0;               // sum w1^2
-  const double inv_nu = 1.0 / nu;                          // inf at T = 1 (model 4 needs T >= 3)
-  // --- Brownian block: entry (i = 2q + half, j = lane & 15), kept in registers ---
   constexpr int NQ = (DP + 1) / 2;
   double r_bb[NQ], r_bz[NQ];
   const int j = lane & 15;
@@ -314,11 +310,10 @@ __device__ __forceinline__ void jne_warp_assemble(const double* VV, const double
   for (int q = 0; q < NQ; ++q) {
     const int i = 2 * q + (lane >> 4);
     double mbb = 0.0, mbz = 0.0;
-    if (i < nb) {
+    if (i < d && j < d) {
       double bi = 0.0, bj = 0.0;
-      const bool jb = j < nb, jz = j < d;
-      if (jb) mbb = (i <= j) ? VV[i * G::VV_LD + j] : VV[j * G::VV_LD + i];
-      if (jz) mbz = VV[i * G::VV_LD + DP + j];
+      mbb = (i <= j) ? VV[i * G::VV_LD + j] : VV[j * G::VV_LD + i];
+      mbz = VV[i * G::VV_LD + DP + j];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const double ei = vec[(0 * 4 + k) * 16 + i], ej = vec[(0 * 4 + k) * 16 + j];
@@ -327,6 +322,47 @@ __device__ __forceinline__ void jne_warp_assemble(const double* VV, const double
         mbz += bi * ej;
         bi += ei; bj += ej;
       }
+    }
+    r_bb[q] = mbb;
+    r_bz[q] = mbz;
+  }
+  __syncwarp();   // all reads of the raw area are done: the stitched moments may now overwrite it
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int i = 2 * q + (lane >> 4);
+    if (i < 16) { MBB[i * 16 + j] = r_bb[q]; MBZ[i * 16 + j] = r_bz[q]; }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue part 2, per model: S2 = sum F F' (p x p) and R = S1' = sum F dB' (p x d) from the stitched
+// moments, with demeaning / detrending as Schur complements.  F per model follows
+// src/johansen_statistics.rs:102-197.  Row scalings of F leave the pencil's
+// eigenvalues unchanged, so the trend row is carried as (w1+1)/T (= 2 (tau - 1/2)) and the detrended
+// tau^2 row as w2/T^2 (= 12 x its residual on [1, tau]).  ALIASED: S2 / R may overlap MBB / MBZ
+// (single-model launches); entries pass through registers and a warp barrier.
+// ---------------------------------------------------------------------------------------------
+template <int DP>
+__device__ __forceinline__ void jne_warp_assemble(const double* MBB, const double* MBZ, const double* tot,
+                                                  double* S2, double* R, const JneRunParams& prm, int model, int p) {
+  const int lane = threadIdx.x & 31;
+  const int d = prm.dim;
+  const double T = prm.T;
+  const int nb = (model == 2 || model == 4) ? d - 1 : d;   // Brownian rows kept in F
+  const double invT = 1.0 / T;
+  const double nu = T * (T * T - 1.0) / 3.0;               // sum w1^2
+  const double inv_nu = 1.0 / nu;                          // inf at T = 1 (model 4 needs T >= 3)
+  constexpr int NQ = (DP + 1) / 2;
+  double r_bb[NQ], r_bz[NQ];
+  const int j = lane & 15;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int i = 2 * q + (lane >> 4);
+    double mbb = 0.0, mbz = 0.0;
+    if (i < nb) {
+      mbb = MBB[i * 16 + j];
+      mbz = MBZ[i * 16 + j];
       const double SBi = tot[0 * 16 + i], S1Bi = tot[1 * 16 + i];
       if (model >= 2) {   // demean (models 2,3,4)  src/johansen_statistics.rs:120-125,145-150,186-194
         mbb -= SBi * tot[0 * 16 + j] * invT;
@@ -357,7 +393,7 @@ __device__ __forceinline__ void jne_warp_assemble(const double* VV, const double
       dg = 0.8 * T * (T * T - 1.0) * (T * T - 4.0) * invT * invT * invT * invT;   // sum w2^2 / T^4
     }
   }
-  __syncwarp();   // all reads of the raw area are done: S2 / R may now overwrite it
+  __syncwarp();   // all reads of the stitched moments are done: S2 / R may overwrite them (single-model)
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const int i = 2 * q + (lane >> 4);
@@ -498,7 +534,7 @@ __device__ __forceinline__ void jne_consume8(uint32_t t, uint32_t t_end, int g, 
 // DET: 0 = models 0,1 (sum c only), 1 = models 2,3 (+ w1 moments), 2 = model 4 (+ w2 moments).
 // ---------------------------------------------------------------------------------------------
 template <int DP, int DET, bool SRC_RNG, bool MULTI>
-__global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA)
+__global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA, (MULTI && SRC_RNG) ? 5 : 1)
 jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB, uint64_t n,
                JneRunParams prm, double* __restrict__ out, unsigned int* __restrict__ err_count,
                double* __restrict__ dbg /* optional: per run S2 (16x16) then R (16x16) */) {
@@ -509,12 +545,14 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   const uint64_t run = (uint64_t)blockIdx.x * JNE_WARPS_PER_CTA + warp;
   if (run >= n) return;
   double* wsm = smem + (size_t)warp * (MULTI ? G::WARP_SMEM_MULTI : G::WARP_SMEM);
-  double* VV = wsm;                 // raw view
+  double* tot = wsm;                // whole-run totals (live through the epilogue)
+  double* VV = tot + G::TOT_SZ;     // raw view
   double* vec = VV + G::VV_SZ;
-  double* tot = vec + G::VEC_SZ;
-  // work view: single-model launches alias it onto the raw view (see jne_warp_assemble); multi-model
-  // launches keep the raw moments live for the next model and place it behind them
-  double* S2 = MULTI ? wsm + G::RAW_SZ : wsm;
+  double* MBB = tot + G::TOT_SZ;    // stitched view (aliases the raw view, see jne_warp_stitch)
+  double* MBZ = MBB + 256;
+  // work view: single-model launches alias it onto the stitched view (see jne_warp_assemble); multi-model
+  // launches keep the stitched moments live for the next model and place it behind them
+  double* S2 = MULTI ? MBZ + 256 : MBB;
   double* R = S2 + G::MAT_SZ;
   double* misc = R + G::MAT_SZ;
 
@@ -523,6 +561,7 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   const uint32_t t_begin = min((uint32_t)k * prm.seg_len, T);
   const uint32_t t_end = min(T, t_begin + prm.seg_len);
   const jne_keys keys = jne_make_keys(SRC_RNG ? seeds[run] : 0u, reinterpret_cast<volatile uint32_t*>(wsm));
+  const unsigned char* sched_src = prm.sched;
   const double* dBrun = SRC_RNG ? nullptr : dB + run * (uint64_t)d * T;
   float rowscale[G::NRT];
 #pragma unroll
@@ -597,13 +636,14 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   // ---- per model: assemble (Schur complements for the deterministic terms) and solve ----
   // One Brownian path serves every selected model: the reference draws the path from (dim, steps, seed)
   // only (src/rng_matrix.rs:11) and its CLI loops the models over the same seeds (src/main.rs:109).
+  jne_warp_stitch<DP>(VV, vec, tot, MBB, MBZ, prm);
   bool ok = true;
   uint32_t off = 0;
 #pragma unroll 1
   for (int model = 0; model < 5; ++model) {
     if (!((prm.model_mask >> model) & 1u)) continue;
     const int p = (model == 1 || model == 3) ? (int)d + 1 : (int)d;
-    jne_warp_assemble<DP>(VV, vec, tot, S2, R, prm, model, p);
+    jne_warp_assemble<DP>(MBB, MBZ, tot, S2, R, prm, model, p);
     if (dbg != nullptr) {
       double* o = dbg + run * 512;
       for (int e = lane; e < 256; e += 32) {
@@ -613,7 +653,8 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
       }
       __syncwarp();
     }
-    ok &= jne_warp_pencil_solve(S2, R, misc, p, d, prm.factor, out + run * prm.out_stride + off, off == 0);
+    ok &= jne_warp_pencil_solve(S2, R, misc, p, d, prm.factor, out + run * prm.out_stride + off,
+                                off == 0 ? sched_src : nullptr);
     off += p;
     if (!MULTI) break;
     __syncwarp();
@@ -629,7 +670,8 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA)
 jne_pencil_kernel(const double* __restrict__ S1, const double* __restrict__ S2in, uint64_t n, int p, int d,
-                  double factor, double* __restrict__ out, unsigned int* __restrict__ err_count) {
+                  double factor, double* __restrict__ out, unsigned int* __restrict__ err_count,
+                  const unsigned char* __restrict__ sched) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t run = (uint64_t)blockIdx.x * JNE_WARPS_PER_CTA + warp;
@@ -640,7 +682,7 @@ jne_pencil_kernel(const double* __restrict__ S1, const double* __restrict__ S2in
   for (int e = lane; e < p * p; e += 32) S2[(e / p) * JNE_LD + (e % p)] = S2in[run * p * p + e];
   for (int e = lane; e < p * d; e += 32) R[(e / d) * JNE_LD + (e % d)] = S1[run * p * d + e];
   __syncwarp();
-  const bool ok = jne_warp_pencil_solve(S2, R, misc, p, d, factor, out + run * p, true);
+  const bool ok = jne_warp_pencil_solve(S2, R, misc, p, d, factor, out + run * p, sched);
   if (!ok && lane == 0) atomicAdd(err_count, 1u);
 }
 
