@@ -86,13 +86,17 @@ __device__ __forceinline__ void jne_dmma(double& c0, double& c1, double a, doubl
 // 1/x and 1/sqrt(x) to ~1 ulp from an FP32 seed + two Newton steps; x must be inside the float range
 // (true for every call site below).  Avoids the ~35-instruction IEEE division / sqrt sequences.
 __device__ __forceinline__ double jne_rcp(double x) {
-  double r = (double)__frcp_rn((float)x);
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"((float)x));
+  double r = (double)r0;
   r = fma(r, fma(-x, r, 1.0), r);
   r = fma(r, fma(-x, r, 1.0), r);
   return r;
 }
 __device__ __forceinline__ double jne_rsqrt(double x) {
-  double y = (double)rsqrtf((float)x);
+  float y0;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"((float)x));
+  double y = (double)y0;
   const double hx = 0.5 * x;
   y = fma(y, fma(-hx * y, y, 0.5), y);
   y = fma(y, fma(-hx * y, y, 0.5), y);
@@ -108,6 +112,19 @@ __device__ __forceinline__ void jne_load_schedule(unsigned char* sched, const un
   if (lane < 30) reinterpret_cast<uint2*>(sched)[lane] = reinterpret_cast<const uint2*>(src)[lane];
 }
 
+// 1/sqrt(x) for any positive finite double (the Cholesky pivots scale with the caller's increments squared,
+// so they may lie outside the float range): x = m 4^k, m in [1, 4).  Non-positive or NaN -> NaN.
+__device__ __forceinline__ double jne_rsqrt_wide(double x) {
+  if (!(x > 0.0) || !(x < 1.7e308)) return __longlong_as_double(0x7ff8000000000000ll);
+  double post = 1.0;
+  if (x < 0x1p-900) { x *= 0x1p200; post = 0x1p100; }         // denormals / tiny values: rsqrt(x 2^200) 2^100
+  const int hi = __double2hiint(x);
+  const int k2 = (((hi >> 20) & 0x7ff) - 1023) & ~1;          // even part of the exponent
+  const double m = __hiloint2double(hi - (k2 << 20), __double2loint(x));
+  const double y = jne_rsqrt(m);
+  return __hiloint2double(__double2hiint(y) - ((k2 >> 1) << 20), __double2loint(y)) * post;
+}
+
 __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, double* __restrict__ R,
                                                    double* __restrict__ misc, int p, int d, double factor,
                                                    double* __restrict__ out,
@@ -121,7 +138,7 @@ __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, doub
 
   // --- Cholesky S2 = L L', right-looking, lower triangle in place; only 1/l_jj is ever needed ---
   for (int j = 0; j < p; ++j) {
-    const double inv = jne_rsqrt(S2[j * JNE_LD + j]);             // NaN for a non-positive pivot -> flagged below
+    const double inv = jne_rsqrt_wide(S2[j * JNE_LD + j]);        // NaN for a non-positive pivot -> flagged below
     __syncwarp();
     if (lane == 0) invd[j] = inv;
     for (int i = j + 1 + lane; i < p; i += 32) S2[i * JNE_LD + j] *= inv;
@@ -202,11 +219,16 @@ __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, doub
         const int pp = sched[2 * (step * npairs + lane)], qq = sched[2 * (step * npairs + lane) + 1];
         double c = 1.0, s = 0.0;
         const double apq = S2[pp * JNE_LD + qq];
-        if (fabs(apq) > tol) {
-          const float diff = (float)(S2[qq * JNE_LD + qq] - S2[pp * JNE_LD + pp]);
-          const float th = __fdividef(diff, 2.0f * (float)apq);
-          const float tf = copysignf(__frcp_rn(fabsf(th) + sqrtf(fmaf(th, th, 1.0f))), th);
-          const double t = (double)tf;
+        const double app = S2[pp * JNE_LD + pp], aqq = S2[qq * JNE_LD + qq];
+        const double diff = aqq - app;
+        // Leaving a_pq in place moves the two eigenvalues by about a_pq^2 / |diff| (second order) and never by
+        // more than |a_pq|: skip the rotation when that is below 1e-14 of the smaller one, or below 2^-50 outright.
+        if (fabs(apq) > tol && apq * apq > 1e-14 * fabs(diff) * fmin(app, aqq)) {
+          float th, h, tf;
+          asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(th) : "f"((float)diff), "f"(2.0f * (float)apq));
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(fmaf(th, th, 1.0f)));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tf) : "f"(fabsf(th) + h));
+          const double t = (double)copysignf(tf, th);
           c = jne_rsqrt(fma(t, t, 1.0));
           s = t * c;
           rotated = 1;

@@ -280,3 +280,16 @@ def test_multi_model_full_size_vs_oracle(engine):
         z = engine.gen_normal_matrix(12, 10000, int(s))
         for m in range(5):
             assert_close(multi[m][i], orc.eigs_from_normals(z, m), f"model {m}")
+
+
+def test_increment_scale_covariance(engine):
+    """Scaling the caller's increments by c scales every eigenvalue by c^2 (S1'S1 ~ c^4, S2 ~ c^2).  Tiny and huge
+    scales must neither overflow the FP32-seeded reciprocals of the solver nor lose accuracy (the reference's own
+    S1'S1 would underflow at c = 1e-140; the whitened formulation here never forms c^4 terms)."""
+    rng = np.random.default_rng(12)
+    db = rng.standard_normal((3, 300, 5)) / np.sqrt(300)
+    for model in (0, 3, 4):
+        ref = orc.eigs_batch_from_increments(db, model)
+        for scale in (1e-140, 1e-30, 1.0, 1e30, 1e140):
+            got = engine.eigs_from_increments(model, db * scale)
+            assert_close(got / scale / scale, ref, f"model {model} scale {scale}")
