@@ -130,6 +130,20 @@ int jne_pencil_eigs_batch(jne_ctx* ctx, uint32_t p, uint32_t d, const double* S1
 int jne_eigs_batch_debug(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps,
                          const uint32_t* seeds, uint64_t n, double* out, double* mats);
 
+/* ---- streaming statistics ------------------------------------------- */
+
+/* Percentiles of the trace (sum of a record's eigenvalues) and of the max-eigenvalue over n records resident on
+ * device 0 (row i at d_eigs + i*stride, p values) -- calculate_trace_percentiles / calculate_maxeig_percentiles,
+ * src/simulation_analyzers.rs:42-81, which today re-read and sort the whole .dat file on the host.  qs: n_q
+ * fractions in [0,1]; value at rank q (n-1) with linear interpolation (:4-18).  qs / outputs are HOST arrays. */
+int jne_percentiles_device(jne_ctx* ctx, const void* d_eigs, uint64_t n, uint32_t p, uint32_t stride,
+                           const double* qs, uint32_t n_q, double* trace_out, double* maxeig_out, void* stream);
+
+/* Simulate seeds first_seed .. first_seed+n-1 on device 0 and return only those percentiles: eigenvalues never
+ * leave the GPU (seeds are generated on the device, records are reduced to (trace, max) as they are produced). */
+int jne_simulate_percentiles(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, uint32_t first_seed,
+                             uint64_t n, const double* qs, uint32_t n_q, double* trace_out, double* maxeig_out);
+
 /* ---- orchestration helper (C++ mirror in csrc/jne_host.hpp) -------------------------------------- */
 
 /* run_model_simulation (src/data_storage/parallel_compute.rs:150-232) for one (model, dim, steps, num_runs) job:

@@ -50,6 +50,9 @@ def _load() -> C.CDLL:
         "jne_brownian_motion_matrix": (C.c_int, [vp, u32, u32, dbl, u32, vp]),
         "jne_pencil_eigs_batch": (C.c_int, [vp, u32, u32, vp, vp, u64, vp]),
         "jne_eigs_batch_debug": (C.c_int, [vp, u8, u32, u32, vp, u64, vp, vp]),
+        "jne_percentiles_device": (C.c_int, [vp, vp, u64, u32, u32, vp, u32, vp, vp, vp]),
+        "jne_simulate_percentiles": (C.c_int, [vp, u8, u32, u32, u32, u64, vp, u32, vp, vp]),
+        "jne_run_model_simulation": (C.c_int, [vp, u8, u32, u32, u64, C.c_char_p, C.c_int, ip, C.c_int, C.POINTER(u64)]),
         "jne_fp64_peak_tflops": (C.c_int, [vp, C.c_int, dbl, C.POINTER(dbl)]),
         "jne_launch_count": (u64, [vp]),
         "jne_flops_per_run": (dbl, [u8, u32, u32]),
@@ -267,6 +270,23 @@ class Engine:
         out = np.empty((n, p), dtype=np.float64)
         self._check(lib.jne_pencil_eigs_batch(self._ctx, p, d, s1t.ctypes.data, S2.ctypes.data, n, out.ctypes.data))
         return out
+
+    # -- streaming statistics (src/simulation_analyzers.rs:42-81) ---------------------------------------
+    def simulate_percentiles(self, model, dim: int, steps: int, num_runs: int, percentiles, first_seed: int = 1):
+        """(trace percentiles, max-eig percentiles) of seeds first_seed..first_seed+num_runs-1; nothing but the
+        percentiles leaves the GPU."""
+        qs = np.ascontiguousarray(percentiles, dtype=np.float64)
+        tr = np.empty(qs.size); mx = np.empty(qs.size)
+        self._check(lib.jne_simulate_percentiles(self._ctx, _model_number(model), dim, steps, first_seed, num_runs,
+                                                 qs.ctypes.data, qs.size, tr.ctypes.data, mx.ctypes.data))
+        return tr, mx
+
+    def percentiles_device(self, d_eigs_ptr: int, n: int, p: int, stride: int, percentiles, stream_ptr: int = 0):
+        qs = np.ascontiguousarray(percentiles, dtype=np.float64)
+        tr = np.empty(qs.size); mx = np.empty(qs.size)
+        self._check(lib.jne_percentiles_device(self._ctx, C.c_void_p(d_eigs_ptr), n, p, stride, qs.ctypes.data,
+                                               qs.size, tr.ctypes.data, mx.ctypes.data, C.c_void_p(stream_ptr)))
+        return tr, mx
 
     def fp64_peak_tflops(self, mode: int = 0, ms_target: float = 200.0) -> float:
         v = C.c_double()

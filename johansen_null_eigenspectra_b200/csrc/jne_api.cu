@@ -12,6 +12,8 @@
 #include <thread>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "../../include/jne.h"
 #include "jne_kernels.cuh"
 
@@ -303,6 +305,39 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, 
 #pragma unroll
   for (int i = 0; i < 16; ++i) s += acc[i];
   if (s == 123.456) sink[0] = s;
+}
+
+// ---- streaming statistics ----
+// SumAggregator / MaxAggregator of src/simulation_analyzers.rs:25-40: the sum runs over the record in stored
+// (descending) order, the maximum folds from f64::MIN.
+__global__ void jne_aggregate_kernel(const double* __restrict__ eigs, uint64_t n, uint32_t p, uint32_t stride,
+                                     double* __restrict__ trace, double* __restrict__ maxeig) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* e = eigs + i * stride;
+  double sum = 0.0, mx = -1.7976931348623157e308;
+  for (uint32_t k = 0; k < p; ++k) { sum += e[k]; mx = fmax(mx, e[k]); }
+  trace[i] = sum;
+  maxeig[i] = mx;
+}
+
+// get_percentile_value of src/simulation_analyzers.rs:4-18: rank = q (n-1), linear interpolation.
+__global__ void jne_percentile_kernel(const double* __restrict__ sorted, uint64_t n, const double* __restrict__ qs,
+                                      uint32_t nq, double* __restrict__ out) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nq) return;
+  if (n == 0) { out[k] = __longlong_as_double(0x7ff8000000000000ll); return; }
+  const double rank = qs[k] * (double)(n - 1);
+  const uint64_t lo = (uint64_t)floor(rank), hi = (uint64_t)ceil(rank);
+  if (lo == hi) { out[k] = sorted[lo]; return; }
+  const double w = rank - (double)lo;
+  // two products and one sum, each rounded (no FMA contraction): bit-identical to the reference's expression
+  out[k] = __dadd_rn(__dmul_rn(sorted[lo], 1.0 - w), __dmul_rn(sorted[hi], w));
+}
+
+__global__ void jne_iota_kernel(uint32_t first, uint64_t n, uint32_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = first + (uint32_t)i;
 }
 
 }  // namespace
@@ -660,6 +695,92 @@ int jne_pencil_eigs_batch(jne_ctx* ctx, uint32_t p, uint32_t d, const double* S1
   JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
   if (*dv.h_err) return fail(ctx, JNE_ERR_NONFINITE, "non-finite eigenvalues (S2 not positive definite?)");
   return JNE_OK;
+}
+
+// Sort the two aggregate arrays and interpolate the requested percentiles; d_trace / d_max hold n doubles each and
+// are followed by n more doubles each of sort space.  Results land in the host arrays.
+static int percentiles_of(jne_ctx* ctx, Device& dv, double* d_trace, double* d_max, uint64_t n, const double* qs,
+                          uint32_t nq, double* trace_out, double* maxeig_out, cudaStream_t st) {
+  size_t tmp_bytes = 0;
+  JNE_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_trace, d_trace + n, (int64_t)n, 0, 64, st));
+  void* d_tmp = nullptr;
+  double* d_q = nullptr;
+  JNE_CUDA(ctx, cudaMalloc(&d_tmp, tmp_bytes + 64));
+  JNE_CUDA(ctx, cudaMalloc(&d_q, 3 * (size_t)nq * sizeof(double)));
+  auto body = [&]() -> int {
+    JNE_CUDA(ctx, cudaMemcpyAsync(d_q, qs, nq * sizeof(double), cudaMemcpyHostToDevice, st));
+    JNE_CUDA(ctx, cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_trace, d_trace + n, (int64_t)n, 0, 64, st));
+    jne_percentile_kernel<<<(nq + 63) / 64, 64, 0, st>>>(d_trace + n, n, d_q, nq, d_q + nq);
+    JNE_CUDA(ctx, cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_max, d_max + n, (int64_t)n, 0, 64, st));
+    jne_percentile_kernel<<<(nq + 63) / 64, 64, 0, st>>>(d_max + n, n, d_q, nq, d_q + 2 * nq);
+    JNE_CUDA(ctx, cudaGetLastError());
+    ctx->launches.fetch_add(2);
+    JNE_CUDA(ctx, cudaMemcpyAsync(trace_out, d_q + nq, nq * sizeof(double), cudaMemcpyDeviceToHost, st));
+    JNE_CUDA(ctx, cudaMemcpyAsync(maxeig_out, d_q + 2 * nq, nq * sizeof(double), cudaMemcpyDeviceToHost, st));
+    JNE_CUDA(ctx, cudaStreamSynchronize(st));
+    return JNE_OK;
+  };
+  const int rc = body();
+  cudaFree(d_tmp);
+  cudaFree(d_q);
+  return rc;
+}
+
+int jne_percentiles_device(jne_ctx* ctx, const void* d_eigs, uint64_t n, uint32_t p, uint32_t stride, const double* qs,
+                           uint32_t nq, double* trace_out, double* maxeig_out, void* stream) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  if (!d_eigs || !qs || !trace_out || !maxeig_out || p < 1 || stride < p || nq < 1)
+    return fail(ctx, JNE_ERR_INVALID_ARG, "jne_percentiles_device: bad arguments");
+  join_worker(ctx);
+  Device& dv = ctx->devs[0];
+  JNE_CUDA(ctx, cudaSetDevice(dv.id));
+  double* d_buf = nullptr;
+  JNE_CUDA(ctx, cudaMalloc(&d_buf, 4 * std::max<uint64_t>(n, 1) * sizeof(double)));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n) jne_aggregate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const double*)d_eigs, n, p, stride, d_buf, d_buf + 2 * n);
+  ctx->launches.fetch_add(1);
+  const int rc = percentiles_of(ctx, dv, d_buf, d_buf + 2 * n, n, qs, nq, trace_out, maxeig_out, st);
+  cudaFree(d_buf);
+  return rc;
+}
+
+int jne_simulate_percentiles(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, uint32_t first_seed, uint64_t n,
+                             const double* qs, uint32_t nq, double* trace_out, double* maxeig_out) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  join_worker(ctx);
+  int rc = validate(ctx, model, dim, steps);
+  if (rc) return rc;
+  if (!qs || !trace_out || !maxeig_out || nq < 1) return fail(ctx, JNE_ERR_INVALID_ARG, "jne_simulate_percentiles: bad arguments");
+  if ((uint64_t)first_seed + n > (1ull << 32)) return fail(ctx, JNE_ERR_INVALID_ARG, "seed range exceeds u32");
+  Device& dv = ctx->devs[0];
+  JNE_CUDA(ctx, cudaSetDevice(dv.id));
+  JneRunParams prm = make_params(model, dim, steps, false);
+  prm.sched = sched_for(dv, dim);
+  const uint64_t chunk = 1ull << 20;
+  double* d_agg = nullptr;     // trace[n] + sort space[n] + max[n] + sort space[n]
+  uint32_t* d_seeds = nullptr;
+  double* d_eigs = nullptr;
+  JNE_CUDA(ctx, cudaMalloc(&d_agg, 4 * std::max<uint64_t>(n, 1) * sizeof(double)));
+  JNE_CUDA(ctx, cudaMalloc(&d_seeds, chunk * sizeof(uint32_t)));
+  JNE_CUDA(ctx, cudaMalloc(&d_eigs, chunk * prm.p * sizeof(double)));
+  auto body = [&]() -> int {
+    JNE_CUDA(ctx, cudaMemsetAsync(dv.d_err, 0, sizeof(unsigned int), dv.stream));
+    for (uint64_t off = 0; off < n; off += chunk) {
+      const uint64_t m = std::min(chunk, n - off);
+      jne_iota_kernel<<<(unsigned)((m + 255) / 256), 256, 0, dv.stream>>>(first_seed + (uint32_t)off, m, d_seeds);
+      JNE_CUDA(ctx, launch_run<true>(d_seeds, nullptr, m, prm, d_eigs, dv.d_err, nullptr, dv.stream));
+      jne_aggregate_kernel<<<(unsigned)((m + 255) / 256), 256, 0, dv.stream>>>(d_eigs, m, prm.p, prm.p, d_agg + off, d_agg + 2 * n + off);
+      JNE_CUDA(ctx, cudaGetLastError());
+      ctx->launches.fetch_add(3);
+    }
+    JNE_CUDA(ctx, cudaMemcpyAsync(dv.h_err, dv.d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, dv.stream));
+    JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+    if (*dv.h_err) return fail(ctx, JNE_ERR_NONFINITE, "non-finite eigenvalues");
+    return percentiles_of(ctx, dv, d_agg, d_agg + 2 * n, n, qs, nq, trace_out, maxeig_out, dv.stream);
+  };
+  rc = body();
+  cudaFree(d_agg); cudaFree(d_seeds); cudaFree(d_eigs);
+  return rc;
 }
 
 int jne_fp64_peak_tflops(jne_ctx* ctx, int mode, double ms_target, double* tflops) {

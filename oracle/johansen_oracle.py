@@ -211,5 +211,6 @@ def percentiles(values, ps=(0.5, 0.75, 0.8, 0.85, 0.9, 0.95, 0.975, 0.99)) -> np
         idx = p * (n - 1)
         lo = int(np.floor(idx))
         hi = int(np.ceil(idx))
-        out.append(v[lo] if lo == hi else v[lo] + (idx - lo) * (v[hi] - v[lo]))
+        w = idx - lo
+        out.append(v[lo] if lo == hi else v[lo] * (1.0 - w) + v[hi] * w)   # simulation_analyzers.rs:12-17
     return np.array(out)

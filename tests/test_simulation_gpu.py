@@ -50,3 +50,30 @@ def test_all_models_files_and_mismatch_restart(tmp_path, engine):
     st = dat.run_model_simulation(0, 2, 212, 10, str(path), devices=[0])
     assert st == {"completed_before": 0, "computed": 10, "total_in_file": 10}
     assert dat.file_info(path)["steps"] == 212
+
+
+def test_streaming_percentiles(engine):
+    """Row f3: on-device trace / max-eig percentiles == the reference's analyser (src/simulation_analyzers.rs:4-65,
+    restated in oracle.percentiles) applied to the same records on the host."""
+    import torch
+    from oracle import johansen_oracle as orc
+    qs = [0.0, 0.5, 0.9, 0.95, 0.975, 0.99, 1.0]
+    for model, dim, T, n in [(0, 2, 103, 1), (1, 3, 200, 10001), (4, 12, 400, 30000)]:
+        ev = engine.eigs_batch(model, dim, T, np.arange(1, n + 1, dtype=np.uint32))
+        tr, mx = engine.simulate_percentiles(model, dim, T, n, qs)
+        trace = ev[:, 0].copy()
+        for k in range(1, ev.shape[1]):          # eigenvalues.iter().sum(): left to right in stored order
+            trace += ev[:, k]
+        ref_tr = orc.percentiles(trace, qs)
+        assert np.array_equal(tr, ref_tr), (tr - ref_tr)
+        assert np.array_equal(mx, orc.percentiles(ev[:, 0], qs))
+        d = torch.from_numpy(ev).cuda()
+        tr2, mx2 = engine.percentiles_device(d.data_ptr(), n, ev.shape[1], ev.shape[1], qs, torch.cuda.current_stream().cuda_stream)
+        assert np.array_equal(tr2, tr) and np.array_equal(mx2, mx)
+    # a different first seed selects a different sample (seeds 101..200 == the tail of 1..200)
+    ev = engine.eigs_batch(2, 4, 150, np.arange(101, 201, dtype=np.uint32))
+    tr, mx = engine.simulate_percentiles(2, 4, 150, 100, [0.5], first_seed=101)
+    trace = ev[:, 0].copy()
+    for k in range(1, ev.shape[1]):
+        trace += ev[:, k]
+    assert np.array_equal(tr, orc.percentiles(trace, [0.5]))
