@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -16,6 +17,7 @@
 
 #include "../../include/jne.h"
 #include "jne_kernels.cuh"
+#include "jne_kernels_v2.cuh"
 
 #define JNE_VERSION_STR "jne-b200 0.1.0 (sm_100a)"
 
@@ -44,6 +46,8 @@ struct Device {
   unsigned int* d_err = nullptr;
   unsigned int* h_err = nullptr;  // pinned
   unsigned char* d_sched = nullptr;   // 8 Jacobi pairing tables (ne = 2, 4, .., 16), 256 bytes each
+  double* d_mom = nullptr;            // v2 path: per-run moments between jne_moments12_kernel and jne_solve_kernel
+  uint64_t mom_runs = 0;              // capacity of d_mom in runs
   double* d_scratch = nullptr;    // increments / pencil inputs, grown on demand
   size_t scratch_bytes = 0;
 };
@@ -51,6 +55,7 @@ struct Device {
 }  // namespace
 
 struct jne_ctx {
+  int kernel_family = 1;   // 1: tensor path for every dim (default); 2: FMA-tiled path for 9 <= dim <= 12 (env JNE_KERNEL=v2)
   std::vector<Device> devs;
   std::string err;
   std::mutex err_mu;
@@ -182,9 +187,59 @@ cudaError_t launch_det(int det, const uint32_t* s, const double* b, uint64_t n, 
   }
 }
 
+constexpr uint64_t kMomChunk = 1ull << 18;   // runs per v2 moments/solve pair (1.27 GB of moments)
+
+template <int DET, bool RNG>
+cudaError_t launch_v2_det(const uint32_t* s, const double* b, uint64_t m, const JneRunParams& prm, double* mom, cudaStream_t st) {
+  constexpr unsigned runs_per_cta = 8 * JNE_V2_WARPS;
+  const unsigned grid = (unsigned)((m + runs_per_cta - 1) / runs_per_cta);
+  jne_moments12_kernel<DET, RNG><<<grid, 32 * JNE_V2_WARPS, 0, st>>>(s, b, m, prm, mom);
+  return cudaGetLastError();
+}
+
+// v2 (9 <= dim <= 12): moments kernel + solve kernel per chunk of runs, both on stream st
 template <bool RNG>
-cudaError_t launch_run(const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm, double* o,
-                       unsigned int* e, double* dbg, cudaStream_t st) {
+cudaError_t launch_v2(jne_ctx* ctx, Device& dv, const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm,
+                      double* o, unsigned int* e, double* dbg, cudaStream_t st) {
+  const uint64_t need = std::min<uint64_t>(n, kMomChunk);
+  if (dv.mom_runs < need) {
+    if (dv.d_mom) { cudaError_t f = cudaFree(dv.d_mom); dv.d_mom = nullptr; dv.mom_runs = 0; if (f != cudaSuccess) return f; }
+    cudaError_t a = cudaMalloc(&dv.d_mom, need * JNE_MOM_DOUBLES * sizeof(double));
+    if (a != cudaSuccess) return a;
+    dv.mom_runs = need;
+  }
+  const bool multi = (prm.model_mask & (prm.model_mask - 1u)) != 0;
+  const int det = multi ? 2 : ((prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2));
+  cudaError_t rc = cudaFuncSetAttribute(jne_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jne_solve_smem<true>());
+  if (rc != cudaSuccess) return rc;
+  rc = cudaFuncSetAttribute(jne_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jne_solve_smem<false>());
+  if (rc != cudaSuccess) return rc;
+  for (uint64_t off = 0; off < n; off += kMomChunk) {
+    const uint64_t m = std::min(kMomChunk, n - off);
+    const uint32_t* sp = s ? s + off : nullptr;
+    const double* bp = b ? b + off * (uint64_t)prm.dim * prm.steps : nullptr;
+    switch (det) {
+      case 0: rc = launch_v2_det<0, RNG>(sp, bp, m, prm, dv.d_mom, st); break;
+      case 1: rc = launch_v2_det<1, RNG>(sp, bp, m, prm, dv.d_mom, st); break;
+      default: rc = launch_v2_det<2, RNG>(sp, bp, m, prm, dv.d_mom, st); break;
+    }
+    if (rc != cudaSuccess) return rc;
+    const unsigned grid = (unsigned)((m + JNE_WARPS_PER_CTA - 1) / JNE_WARPS_PER_CTA);
+    double* op = o + off * prm.out_stride;
+    double* dp = dbg ? dbg + off * 512 : nullptr;
+    if (multi) jne_solve_kernel<true><<<grid, 32 * JNE_WARPS_PER_CTA, jne_solve_smem<true>(), st>>>(dv.d_mom, m, prm, op, e, dp);
+    else jne_solve_kernel<false><<<grid, 32 * JNE_WARPS_PER_CTA, jne_solve_smem<false>(), st>>>(dv.d_mom, m, prm, op, e, dp);
+    rc = cudaGetLastError();
+    if (rc != cudaSuccess) return rc;
+    ctx->launches.fetch_add(1);   // the solve kernel; the caller counts the moments kernel
+  }
+  return cudaSuccess;
+}
+
+template <bool RNG>
+cudaError_t launch_run(jne_ctx* ctx, Device& dv, const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm,
+                       double* o, unsigned int* e, double* dbg, cudaStream_t st) {
+  if (ctx->kernel_family == 2 && prm.dim >= 9 && prm.dim <= 12) return launch_v2<RNG>(ctx, dv, s, b, n, prm, o, e, dbg, st);
   const int det = (prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2);
   if (prm.dim <= 4) return launch_det<4, RNG>(det, s, b, n, prm, o, e, dbg, st);
   if (prm.dim <= 8) return launch_det<8, RNG>(det, s, b, n, prm, o, e, dbg, st);
@@ -227,7 +282,7 @@ int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32
       const uint64_t m = std::min<uint64_t>(kChunkRuns, n - done);
       std::memcpy(s.h_seeds, seeds + done, m * sizeof(uint32_t));
       JNE_CUDA(ctx, cudaMemcpyAsync(s.d_seeds, s.h_seeds, m * sizeof(uint32_t), cudaMemcpyHostToDevice, dv.stream));
-      JNE_CUDA(ctx, launch_run<true>(s.d_seeds, nullptr, m, prm, s.d_out, dv.d_err, nullptr, dv.stream));
+      JNE_CUDA(ctx, launch_run<true>(ctx, dv, s.d_seeds, nullptr, m, prm, s.d_out, dv.d_err, nullptr, dv.stream));
       ctx->launches.fetch_add(1);
       JNE_CUDA(ctx, cudaMemcpyAsync(s.h_out, s.d_out, m * prm.p * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
       JNE_CUDA(ctx, cudaEventRecord(s.done, dv.stream));
@@ -386,6 +441,7 @@ void jne_shutdown(jne_ctx* ctx) {
     }
     if (dv.d_err) cudaFree(dv.d_err);
     if (dv.d_sched) cudaFree(dv.d_sched);
+    if (dv.d_mom) cudaFree(dv.d_mom);
     if (dv.h_err) cudaFreeHost(dv.h_err);
     if (dv.d_scratch) cudaFree(dv.d_scratch);
     if (dv.stream) cudaStreamDestroy(dv.stream);
@@ -407,6 +463,7 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
   if (n_devices < 0) return fail(nullptr, JNE_ERR_INVALID_ARG, "n_devices < 0");
   if (n_devices == 0) n_devices = visible;
   jne_ctx* ctx = new jne_ctx();
+  if (const char* kf = std::getenv("JNE_KERNEL")) ctx->kernel_family = (std::strcmp(kf, "v2") == 0) ? 2 : 1;
   ctx->devs.resize(n_devices);
   for (int i = 0; i < n_devices; ++i) {
     Device& dv = ctx->devs[i];
@@ -488,7 +545,7 @@ int jne_eigs_batch_multi_device(jne_ctx* ctx, uint32_t model_mask, uint32_t dim,
   const uint64_t max_runs = (uint64_t)0x7fffffffu * JNE_WARPS_PER_CTA;
   for (uint64_t off = 0; off < n; off += max_runs) {
     const uint64_t m = std::min(max_runs, n - off);
-    JNE_CUDA(ctx, launch_run<true>((const uint32_t*)d_seeds + off, nullptr, m, prm, (double*)d_out + off * prm.out_stride,
+    JNE_CUDA(ctx, launch_run<true>(ctx, dv, (const uint32_t*)d_seeds + off, nullptr, m, prm, (double*)d_out + off * prm.out_stride,
                                    dv.d_err, nullptr, (cudaStream_t)stream));
     ctx->launches.fetch_add(1);
   }
@@ -534,7 +591,7 @@ int jne_eigs_batch_device(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t st
   const uint64_t max_runs = (uint64_t)0x7fffffffu * JNE_WARPS_PER_CTA;
   for (uint64_t off = 0; off < n; off += max_runs) {
     const uint64_t m = std::min(max_runs, n - off);
-    JNE_CUDA(ctx, launch_run<true>((const uint32_t*)d_seeds + off, nullptr, m, prm, (double*)d_out + off * prm.p,
+    JNE_CUDA(ctx, launch_run<true>(ctx, dv, (const uint32_t*)d_seeds + off, nullptr, m, prm, (double*)d_out + off * prm.p,
                                    dv.d_err, nullptr, (cudaStream_t)stream));
     ctx->launches.fetch_add(1);
   }
@@ -583,10 +640,10 @@ static int single_device_run(jne_ctx* ctx, const JneRunParams& prm_in, const uin
     const uint64_t m = std::min(chunk, n - off);
     if (rng) {
       JNE_CUDA(ctx, cudaMemcpyAsync(d_in, seeds + off, m * sizeof(uint32_t), cudaMemcpyHostToDevice, dv.stream));
-      JNE_CUDA(ctx, launch_run<true>((const uint32_t*)d_in, nullptr, m, prm, d_out, dv.d_err, d_dbg, dv.stream));
+      JNE_CUDA(ctx, launch_run<true>(ctx, dv, (const uint32_t*)d_in, nullptr, m, prm, d_out, dv.d_err, d_dbg, dv.stream));
     } else {
       JNE_CUDA(ctx, cudaMemcpyAsync(d_in, dB + off * per_run_in, m * per_run_in * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
-      JNE_CUDA(ctx, launch_run<false>(nullptr, (const double*)d_in, m, prm, d_out, dv.d_err, d_dbg, dv.stream));
+      JNE_CUDA(ctx, launch_run<false>(ctx, dv, nullptr, (const double*)d_in, m, prm, d_out, dv.d_err, d_dbg, dv.stream));
     }
     ctx->launches.fetch_add(1);
     JNE_CUDA(ctx, cudaMemcpyAsync(out + off * prm.p, d_out, m * prm.p * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
@@ -768,7 +825,7 @@ int jne_simulate_percentiles(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t
     for (uint64_t off = 0; off < n; off += chunk) {
       const uint64_t m = std::min(chunk, n - off);
       jne_iota_kernel<<<(unsigned)((m + 255) / 256), 256, 0, dv.stream>>>(first_seed + (uint32_t)off, m, d_seeds);
-      JNE_CUDA(ctx, launch_run<true>(d_seeds, nullptr, m, prm, d_eigs, dv.d_err, nullptr, dv.stream));
+      JNE_CUDA(ctx, launch_run<true>(ctx, dv, d_seeds, nullptr, m, prm, d_eigs, dv.d_err, nullptr, dv.stream));
       jne_aggregate_kernel<<<(unsigned)((m + 255) / 256), 256, 0, dv.stream>>>(d_eigs, m, prm.p, prm.p, d_agg + off, d_agg + 2 * n + off);
       JNE_CUDA(ctx, cudaGetLastError());
       ctx->launches.fetch_add(3);

@@ -293,3 +293,45 @@ def test_increment_scale_covariance(engine):
         for scale in (1e-140, 1e-30, 1.0, 1e30, 1e140):
             got = engine.eigs_from_increments(model, db * scale)
             assert_close(got / scale / scale, ref, f"model {model} scale {scale}")
+
+
+def test_fma_tiled_kernel_family():
+    """JNE_KERNEL=v2 selects the register-tiled FMA family (csrc/jne_kernels_v2.cuh) for 9 <= dim <= 12.  It consumes
+    the same random stream, so it must agree with the oracle fed the device normals (gate-1 tolerance), with the
+    increments entry, and -- to rounding, not bits: the summation order differs -- with the default tensor family."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import sys, numpy as np
+        sys.path.insert(0, ".")
+        import johansen_null_eigenspectra_b200 as jne
+        from oracle import johansen_oracle as orc
+        eng = jne.Engine([0])
+        seeds = np.array([1, 2, 77], dtype=np.uint32)
+        rng = np.random.default_rng(3)
+        worst = 0.0
+        for dim, T in [(9, 50), (10, 103), (11, 257), (12, 1001), (12, 10000)]:
+            multi = eng.eigs_batch_multi(range(5), dim, T, seeds)
+            db = rng.standard_normal((2, T, dim)) / np.sqrt(T)
+            for m in range(5):
+                got = eng.eigs_batch(m, dim, T, seeds)
+                assert np.array_equal(got, multi[m])
+                for i, s in enumerate(seeds):
+                    ref = orc.eigs_from_normals(eng.gen_normal_matrix(dim, T, int(s)), m)
+                    worst = max(worst, float(np.max(np.abs(got[i] - ref) / (1e-9 * np.abs(ref) + 1e-12 * ref.max()))))
+                ref = orc.eigs_batch_from_increments(db, m)
+                got = eng.eigs_from_increments(m, db)
+                worst = max(worst, float(np.max(np.abs(got - ref) / (1e-9 * np.abs(ref) + 1e-12 * ref.max(axis=1, keepdims=True)))))
+        np.save(sys.argv[1], eng.eigs_batch(3, 12, 400, np.arange(1, 501, dtype=np.uint32)))
+        print("WORST", worst)
+    ''')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for fam in ("v2", "v1"):
+        path = f"/tmp/jne_family_{fam}.npy"
+        env = dict(os.environ, JNE_KERNEL=fam)
+        r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        worst = float(r.stdout.split("WORST")[1])
+        assert worst <= 1.0, (fam, worst)
+        out[fam] = np.load(path)
+    assert np.allclose(out["v1"], out["v2"], rtol=1e-10, atol=1e-12 * out["v1"].max())
