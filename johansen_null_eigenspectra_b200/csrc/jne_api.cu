@@ -34,7 +34,8 @@ struct Slot {
   double* d_out = nullptr;
   uint32_t* h_seeds = nullptr;   // pinned
   double* h_out = nullptr;       // pinned
-  cudaEvent_t done = nullptr;
+  cudaEvent_t done = nullptr;      // D2H of this slot finished (copy stream)
+  cudaEvent_t computed = nullptr;  // kernel of this slot finished (compute stream)
   uint64_t n = 0, offset = 0;    // runs in flight and their position in the caller's arrays
   bool busy = false;
 };
@@ -42,6 +43,7 @@ struct Slot {
 struct Device {
   int id = -1;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // D2H of chunk i overlaps the kernel of chunk i+1
   Slot slot[2];
   unsigned int* d_err = nullptr;
   unsigned int* h_err = nullptr;  // pinned
@@ -284,8 +286,10 @@ int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32
       JNE_CUDA(ctx, cudaMemcpyAsync(s.d_seeds, s.h_seeds, m * sizeof(uint32_t), cudaMemcpyHostToDevice, dv.stream));
       JNE_CUDA(ctx, launch_run<true>(ctx, dv, s.d_seeds, nullptr, m, prm, s.d_out, dv.d_err, nullptr, dv.stream));
       ctx->launches.fetch_add(1);
-      JNE_CUDA(ctx, cudaMemcpyAsync(s.h_out, s.d_out, m * prm.p * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
-      JNE_CUDA(ctx, cudaEventRecord(s.done, dv.stream));
+      JNE_CUDA(ctx, cudaEventRecord(s.computed, dv.stream));
+      JNE_CUDA(ctx, cudaStreamWaitEvent(dv.copy_stream, s.computed, 0));
+      JNE_CUDA(ctx, cudaMemcpyAsync(s.h_out, s.d_out, m * prm.p * sizeof(double), cudaMemcpyDeviceToHost, dv.copy_stream));
+      JNE_CUDA(ctx, cudaEventRecord(s.done, dv.copy_stream));
       s.n = m; s.offset = done; s.busy = true;
       done += m;
       which ^= 1;
@@ -438,6 +442,7 @@ void jne_shutdown(jne_ctx* ctx) {
       if (s.h_seeds) cudaFreeHost(s.h_seeds);
       if (s.h_out) cudaFreeHost(s.h_out);
       if (s.done) cudaEventDestroy(s.done);
+      if (s.computed) cudaEventDestroy(s.computed);
     }
     if (dv.d_err) cudaFree(dv.d_err);
     if (dv.d_sched) cudaFree(dv.d_sched);
@@ -445,6 +450,7 @@ void jne_shutdown(jne_ctx* ctx) {
     if (dv.h_err) cudaFreeHost(dv.h_err);
     if (dv.d_scratch) cudaFree(dv.d_scratch);
     if (dv.stream) cudaStreamDestroy(dv.stream);
+    if (dv.copy_stream) cudaStreamDestroy(dv.copy_stream);
   }
   delete ctx;
 }
@@ -480,12 +486,14 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
       if (prop.major != 10)
         return fail(nullptr, JNE_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100 (B200); the kernels are built for sm_100a only");
       JNE_CUDA(nullptr, cudaStreamCreateWithFlags(&dv.stream, cudaStreamNonBlocking));
+      JNE_CUDA(nullptr, cudaStreamCreateWithFlags(&dv.copy_stream, cudaStreamNonBlocking));
       for (auto& s : dv.slot) {
         JNE_CUDA(nullptr, cudaMalloc(&s.d_seeds, kChunkRuns * sizeof(uint32_t)));
         JNE_CUDA(nullptr, cudaMalloc(&s.d_out, kChunkRuns * kMaxWidth * sizeof(double)));
         JNE_CUDA(nullptr, cudaMallocHost(&s.h_seeds, kChunkRuns * sizeof(uint32_t)));
         JNE_CUDA(nullptr, cudaMallocHost(&s.h_out, kChunkRuns * kMaxWidth * sizeof(double)));
         JNE_CUDA(nullptr, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        JNE_CUDA(nullptr, cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
       }
       unsigned char tables[8 * 256];
       make_schedules(tables);

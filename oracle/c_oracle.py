@@ -25,6 +25,10 @@ def load() -> C.CDLL:
     lib.jne_oracle_calculate_eigenvalues.argtypes = [C.c_int, C.c_size_t, C.c_uint32, C.c_int, C.c_size_t, C.c_void_p]
     lib.jne_oracle_eigs_batch.restype = C.c_int
     lib.jne_oracle_eigs_batch.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, C.c_void_p]
+    lib.jne_oracle_fast_from_increments.restype = C.c_int
+    lib.jne_oracle_fast_from_increments.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.jne_oracle_fast_batch.restype = C.c_int
+    lib.jne_oracle_fast_batch.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
     lib.jne_oracle_gen_normal_matrix.restype = None
     lib.jne_oracle_gen_normal_matrix.argtypes = [C.c_size_t, C.c_size_t, C.c_uint64, C.c_size_t, C.c_void_p]
     return lib
@@ -67,3 +71,23 @@ def gen_normal_matrix(lib, nrows: int, ncols: int, seed: int, ncpu: int = None) 
     buf = np.empty((ncols, nrows))
     lib.jne_oracle_gen_normal_matrix(nrows, ncols, seed, ncpu or physical_cores(), buf.ctypes.data)
     return buf.T
+
+
+def fast_from_increments(lib, db: np.ndarray, model: int) -> np.ndarray:
+    """The optimised-CPU variant on caller increments; db: (T, d) C-order."""
+    db = np.ascontiguousarray(db, dtype=np.float64)
+    T, d = db.shape
+    out = np.empty(num_eigs(model, d))
+    rc = lib.jne_oracle_fast_from_increments(model, d, T, db.ctypes.data, out.ctypes.data)
+    if rc:
+        raise FloatingPointError(f"oracle fast rc={rc}")
+    return out
+
+
+def fast_batch(lib, model: int, dim: int, steps: int, seeds, threads: int) -> np.ndarray:
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+    out = np.empty((seeds.size, num_eigs(model, dim)))
+    rc = lib.jne_oracle_fast_batch(model, dim, steps, seeds.ctypes.data, seeds.size, threads, out.ctypes.data)
+    if rc:
+        raise FloatingPointError(f"oracle fast rc={rc}")
+    return out

@@ -37,6 +37,8 @@
 extern void scipy_dggev_(const char* jobvl, const char* jobvr, const int* n, double* a, const int* lda, double* b,
                          const int* ldb, double* alphar, double* alphai, double* beta, double* vl, const int* ldvl,
                          double* vr, const int* ldvr, double* work, const int* lwork, int* info, size_t, size_t);
+extern void scipy_dsygv_(const int* itype, const char* jobz, const char* uplo, const int* n, double* a, const int* lda,
+                         double* b, const int* ldb, double* w, double* work, const int* lwork, int* info, size_t, size_t);
 extern void scipy_openblas_set_num_threads(int);
 
 /* ---------------- RNG: xoshiro256++ seeded by SplitMix64 ---------------- */
@@ -257,6 +259,106 @@ int jne_oracle_eigs_batch(int model, int d, size_t T, const uint32_t* seeds, siz
     jobs[t] = (job_t){d, model, nthreads, t, 0, T, n, n_physical_cpus, seeds, out};
     pthread_create(&th[t], NULL, worker, &jobs[t]);
   }
+  int rc = 0;
+  for (int t = 0; t < nthreads; ++t) { pthread_join(th[t], NULL); if (jobs[t].rc) rc = jobs[t].rc; }
+  free(th); free(jobs);
+  return rc;
+}
+
+
+/* ------------------------------------------------------------------------------------------------------------
+ * "Optimised CPU" variant: NOT the reference's algorithm, a fair best-effort CPU one, so
+ * that the GPU speed-up is not flattered by the reference's temporaries.  One pass over the path with raw moments
+ * (no d x T buffers), demeaning / detrending as Schur complements (same algebra as the GPU epilogue), LAPACK dsygv
+ * (symmetric-definite, eigenvalues only) instead of dggev('V','V').  Same xoshiro256++/ziggurat normals, one stream
+ * per run.  Checked against the faithful port through jne_oracle_fast_from_increments (tests/test_oracle.py).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct { double bb[16][16], bz[16][16], sb[16], s1b[16], s2b[16], sz[16], s1z[16], s2z[16]; } mom_t;
+
+static int fast_solve(const mom_t* m, int d, double T, int model, double factor, double* out) {
+  const int p = (model == 1 || model == 3) ? d + 1 : d, nb = (model == 2 || model == 4) ? d - 1 : d;
+  double S2[17 * 17], R[17][16], A[17 * 17], w[17], work[17 * 40];
+  memset(S2, 0, sizeof S2); memset(R, 0, sizeof R);
+  const double nu = T * (T * T - 1.0) / 3.0;
+  for (int i = 0; i < nb; ++i) {
+    for (int j = 0; j < nb; ++j) {
+      double v = i <= j ? m->bb[i][j] : m->bb[j][i];
+      if (model >= 2) v -= m->sb[i] * m->sb[j] / T;
+      if (model == 4) v -= m->s1b[i] * m->s1b[j] / nu;
+      S2[j * p + i] = v;
+    }
+    for (int j = 0; j < d; ++j) {
+      double v = m->bz[i][j];
+      if (model >= 2) v -= m->sb[i] * m->sz[j] / T;
+      if (model == 4) v -= m->s1b[i] * m->s1z[j] / nu;
+      R[i][j] = v;
+    }
+  }
+  if (p > nb) {
+    for (int j = 0; j < d; ++j) {
+      double s2v, rv;
+      if (model == 1) { s2v = m->sb[j]; rv = m->sz[j]; }
+      else if (model == 4) { s2v = m->s2b[j] / (T * T); rv = m->s2z[j] / (T * T); }
+      else { s2v = m->s1b[j] / T; rv = (m->s1z[j] + m->sz[j]) / T; }
+      if (j < nb) { S2[nb * p + j] = s2v; S2[j * p + nb] = s2v; }
+      R[nb][j] = rv;
+    }
+    S2[nb * p + nb] = model == 1 ? T : model == 4 ? 0.8 * T * (T * T - 1.0) * (T * T - 4.0) / (T * T * T * T) : (nu + T) / (T * T);
+  }
+  for (int i = 0; i < p; ++i) for (int j = 0; j < p; ++j) { double v = 0; for (int k = 0; k < d; ++k) v += R[i][k] * R[j][k]; A[j * p + i] = v; }
+  const int itype = 1, lwork = 17 * 40; int info = 0, pp = p;
+  scipy_dsygv_(&itype, "N", "U", &pp, A, &pp, S2, &pp, w, work, &lwork, &info, 1, 1);
+  for (int i = 0; i < p; ++i) out[i] = fabs(w[p - 1 - i]) * factor;
+  return info;
+}
+
+static void fast_accumulate(mom_t* m, int d, size_t T, const double* dB /* d x T col-major or NULL */, xo_t* rng) {
+  memset(m, 0, sizeof *m);
+  double B[16] = {0}, z[16];
+  const double TT = (double)T, w2c = -(TT * TT - 1.0);
+  for (size_t t = 0; t < T; ++t) {
+    const double w1 = 2.0 * (double)t + 1.0 - TT, w2 = 3.0 * w1 * w1 + w2c;
+    for (int i = 0; i < d; ++i) z[i] = dB ? dB[t * d + i] : standard_normal(rng);
+    for (int i = 0; i < d; ++i) {
+      const double b = B[i];
+      for (int j = i; j < d; ++j) m->bb[i][j] += b * B[j];
+      for (int j = 0; j < d; ++j) m->bz[i][j] += b * z[j];
+      m->sb[i] += b; m->s1b[i] += w1 * b; m->s2b[i] += w2 * b;
+      m->s1z[i] += w1 * z[i]; m->s2z[i] += w2 * z[i];
+    }
+    for (int i = 0; i < d; ++i) B[i] += z[i];
+  }
+  for (int i = 0; i < d; ++i) m->sz[i] = B[i];
+}
+
+int jne_oracle_fast_from_increments(int model, int d, size_t T, const double* dB, double* out) {
+  if (d > 16) return -1;
+  mom_t m;
+  fast_accumulate(&m, d, T, dB, NULL);
+  return fast_solve(&m, d, (double)T, model, (double)T, out);
+}
+
+typedef struct { int d, model, nthreads, tid, rc; size_t T, n; const uint32_t* seeds; double* out; } fjob_t;
+static void* fast_worker(void* arg) {
+  fjob_t* j = (fjob_t*)arg;
+  const int p = (j->model == 1 || j->model == 3) ? j->d + 1 : j->d;
+  for (size_t i = j->tid; i < j->n; i += j->nthreads) {
+    xo_t rng; xo_seed(&rng, (uint64_t)j->seeds[i]);
+    mom_t m;
+    fast_accumulate(&m, j->d, j->T, NULL, &rng);
+    const int rc = fast_solve(&m, j->d, (double)j->T, j->model, 1.0, j->out + i * p);
+    if (rc) j->rc = rc;
+  }
+  return NULL;
+}
+int jne_oracle_fast_batch(int model, int d, size_t T, const uint32_t* seeds, size_t n, int nthreads, double* out) {
+  if (d > 16) return -1;
+  pthread_once(&zig_once, zig_init);
+  scipy_openblas_set_num_threads(1);
+  if (nthreads < 1) nthreads = 1;
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+  fjob_t* jobs = (fjob_t*)malloc(sizeof(fjob_t) * nthreads);
+  for (int t = 0; t < nthreads; ++t) { jobs[t] = (fjob_t){d, model, nthreads, t, 0, T, n, seeds, out}; pthread_create(&th[t], NULL, fast_worker, &jobs[t]); }
   int rc = 0;
   for (int t = 0; t < nthreads; ++t) { pthread_join(th[t], NULL); if (jobs[t].rc) rc = jobs[t].rc; }
   free(th); free(jobs);

@@ -137,6 +137,21 @@ def test_c_oracle_matches_numpy_oracle():
         assert np.all(np.abs(c_oracle.eigs_from_increments(lib, db[i], 0) - c1[i]) <= eig_tol(c1[i]))
 
 
+def test_optimised_cpu_variant_matches_faithful_port():
+    """The "optimised CPU" baseline (one pass, raw moments + Schur complements, dsygv) is a different algorithm for
+    the same quantity: same increments => same eigenvalues as the faithful port, to gate-(1) tolerance."""
+    lib = c_oracle.load()
+    rng = np.random.default_rng(21)
+    for model in range(5):
+        for d, T in [(1, 30), (2, 103), (5, 400), (12, 1000), (15, 64)]:
+            db = rng.standard_normal((T, d)) / np.sqrt(T)
+            ref = orc.eigs_from_increments(db.T, model)
+            got = c_oracle.fast_from_increments(lib, db, model)
+            assert np.all(np.abs(got - ref) <= eig_tol(ref)), (model, d, T)
+    a = c_oracle.fast_batch(lib, 3, 4, 200, np.arange(1, 9), threads=2)
+    assert a.shape == (8, 5) and np.array_equal(a, c_oracle.fast_batch(lib, 3, 4, 200, np.arange(1, 9), threads=1))
+
+
 def test_c_oracle_rng_is_standard_normal_and_reproducible():
     """The reference's own RNG tests, applied to the port of its generator:
     src/tests/rng_matrix_test/gen_normal_matrix_test.rs:7-16 (CDF within 1e-2 at 99 quantiles),
