@@ -23,7 +23,7 @@
 
 namespace {
 
-constexpr uint64_t kChunkRuns = 1ull << 16;   // runs per launch on the host-buffer path (D2H of chunk i overlaps the kernel of chunk i+1)
+constexpr uint64_t kChunkRuns = 1ull << 15;   // runs per launch on the host-buffer path (D2H of chunk i overlaps the kernel of chunk i+1)
 constexpr uint64_t kMaxWidth = 5 * 16;        // doubles per run: all five models at dim 15
 
 std::mutex g_init_err_mu;
@@ -34,8 +34,8 @@ struct Slot {
   double* d_out = nullptr;
   uint32_t* h_seeds = nullptr;   // pinned
   double* h_out = nullptr;       // pinned
-  cudaEvent_t done = nullptr;      // D2H of this slot finished (copy stream)
-  cudaEvent_t computed = nullptr;  // kernel of this slot finished (compute stream)
+  cudaStream_t stream = nullptr;   // H2D -> kernel -> D2H of this slot; the two slots' streams overlap each other
+  cudaEvent_t done = nullptr;      // D2H of this slot finished
   uint64_t n = 0, offset = 0;    // runs in flight and their position in the caller's arrays
   bool busy = false;
 };
@@ -43,13 +43,12 @@ struct Slot {
 struct Device {
   int id = -1;
   cudaStream_t stream = nullptr;
-  cudaStream_t copy_stream = nullptr;   // D2H of chunk i overlaps the kernel of chunk i+1
   Slot slot[2];
   unsigned int* d_err = nullptr;
   unsigned int* h_err = nullptr;  // pinned
   unsigned char* d_sched = nullptr;   // 8 Jacobi pairing tables (ne = 2, 4, .., 16), 256 bytes each
-  double* d_mom = nullptr;            // v2 path: per-run moments between jne_moments12_kernel and jne_solve_kernel
-  uint64_t mom_runs = 0;              // capacity of d_mom in runs
+  double* d_mom[2] = {nullptr, nullptr};   // v2 path: per-run moments between jne_moments12_kernel and jne_solve_kernel,
+  uint64_t mom_runs[2] = {0, 0};           // one buffer per concurrently used stream (capacity in runs)
   double* d_scratch = nullptr;    // increments / pencil inputs, grown on demand
   size_t scratch_bytes = 0;
 };
@@ -202,14 +201,15 @@ cudaError_t launch_v2_det(const uint32_t* s, const double* b, uint64_t m, const 
 // v2 (9 <= dim <= 12): moments kernel + solve kernel per chunk of runs, both on stream st
 template <bool RNG>
 cudaError_t launch_v2(jne_ctx* ctx, Device& dv, const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm,
-                      double* o, unsigned int* e, double* dbg, cudaStream_t st) {
+                      double* o, unsigned int* e, double* dbg, cudaStream_t st, int ms) {
   const uint64_t need = std::min<uint64_t>(n, kMomChunk);
-  if (dv.mom_runs < need) {
-    if (dv.d_mom) { cudaError_t f = cudaFree(dv.d_mom); dv.d_mom = nullptr; dv.mom_runs = 0; if (f != cudaSuccess) return f; }
-    cudaError_t a = cudaMalloc(&dv.d_mom, need * JNE_MOM_DOUBLES * sizeof(double));
+  if (dv.mom_runs[ms] < need) {
+    if (dv.d_mom[ms]) { cudaError_t f = cudaFree(dv.d_mom[ms]); dv.d_mom[ms] = nullptr; dv.mom_runs[ms] = 0; if (f != cudaSuccess) return f; }
+    cudaError_t a = cudaMalloc(&dv.d_mom[ms], need * JNE_MOM_DOUBLES * sizeof(double));
     if (a != cudaSuccess) return a;
-    dv.mom_runs = need;
+    dv.mom_runs[ms] = need;
   }
+  double* d_mom = dv.d_mom[ms];
   const bool multi = (prm.model_mask & (prm.model_mask - 1u)) != 0;
   const int det = multi ? 2 : ((prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2));
   cudaError_t rc = cudaFuncSetAttribute(jne_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jne_solve_smem<true>());
@@ -221,16 +221,16 @@ cudaError_t launch_v2(jne_ctx* ctx, Device& dv, const uint32_t* s, const double*
     const uint32_t* sp = s ? s + off : nullptr;
     const double* bp = b ? b + off * (uint64_t)prm.dim * prm.steps : nullptr;
     switch (det) {
-      case 0: rc = launch_v2_det<0, RNG>(sp, bp, m, prm, dv.d_mom, st); break;
-      case 1: rc = launch_v2_det<1, RNG>(sp, bp, m, prm, dv.d_mom, st); break;
-      default: rc = launch_v2_det<2, RNG>(sp, bp, m, prm, dv.d_mom, st); break;
+      case 0: rc = launch_v2_det<0, RNG>(sp, bp, m, prm, d_mom, st); break;
+      case 1: rc = launch_v2_det<1, RNG>(sp, bp, m, prm, d_mom, st); break;
+      default: rc = launch_v2_det<2, RNG>(sp, bp, m, prm, d_mom, st); break;
     }
     if (rc != cudaSuccess) return rc;
     const unsigned grid = (unsigned)((m + JNE_WARPS_PER_CTA - 1) / JNE_WARPS_PER_CTA);
     double* op = o + off * prm.out_stride;
     double* dp = dbg ? dbg + off * 512 : nullptr;
-    if (multi) jne_solve_kernel<true><<<grid, 32 * JNE_WARPS_PER_CTA, jne_solve_smem<true>(), st>>>(dv.d_mom, m, prm, op, e, dp);
-    else jne_solve_kernel<false><<<grid, 32 * JNE_WARPS_PER_CTA, jne_solve_smem<false>(), st>>>(dv.d_mom, m, prm, op, e, dp);
+    if (multi) jne_solve_kernel<true><<<grid, 32 * JNE_WARPS_PER_CTA, jne_solve_smem<true>(), st>>>(d_mom, m, prm, op, e, dp);
+    else jne_solve_kernel<false><<<grid, 32 * JNE_WARPS_PER_CTA, jne_solve_smem<false>(), st>>>(d_mom, m, prm, op, e, dp);
     rc = cudaGetLastError();
     if (rc != cudaSuccess) return rc;
     ctx->launches.fetch_add(1);   // the solve kernel; the caller counts the moments kernel
@@ -240,8 +240,8 @@ cudaError_t launch_v2(jne_ctx* ctx, Device& dv, const uint32_t* s, const double*
 
 template <bool RNG>
 cudaError_t launch_run(jne_ctx* ctx, Device& dv, const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm,
-                       double* o, unsigned int* e, double* dbg, cudaStream_t st) {
-  if (ctx->kernel_family == 2 && prm.dim >= 9 && prm.dim <= 12) return launch_v2<RNG>(ctx, dv, s, b, n, prm, o, e, dbg, st);
+                       double* o, unsigned int* e, double* dbg, cudaStream_t st, int mom_slot = 0) {
+  if (ctx->kernel_family == 2 && prm.dim >= 9 && prm.dim <= 12) return launch_v2<RNG>(ctx, dv, s, b, n, prm, o, e, dbg, st, mom_slot);
   const int det = (prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2);
   if (prm.dim <= 4) return launch_det<4, RNG>(det, s, b, n, prm, o, e, dbg, st);
   if (prm.dim <= 8) return launch_det<8, RNG>(det, s, b, n, prm, o, e, dbg, st);
@@ -275,6 +275,7 @@ int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32
     prm.sched = sched_for(dv, prm.dim);
     *dv.h_err = 0;
     JNE_CUDA(ctx, cudaMemsetAsync(dv.d_err, 0, sizeof(unsigned int), dv.stream));
+    JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
     uint64_t done = 0;
     int which = 0;
     while (done < n) {
@@ -283,13 +284,13 @@ int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32
       if (rc) return rc;
       const uint64_t m = std::min<uint64_t>(kChunkRuns, n - done);
       std::memcpy(s.h_seeds, seeds + done, m * sizeof(uint32_t));
-      JNE_CUDA(ctx, cudaMemcpyAsync(s.d_seeds, s.h_seeds, m * sizeof(uint32_t), cudaMemcpyHostToDevice, dv.stream));
-      JNE_CUDA(ctx, launch_run<true>(ctx, dv, s.d_seeds, nullptr, m, prm, s.d_out, dv.d_err, nullptr, dv.stream));
+      // each slot has its own stream: the copies of one chunk and the tail wave of its kernel overlap the
+      // kernel of the other slot's chunk
+      JNE_CUDA(ctx, cudaMemcpyAsync(s.d_seeds, s.h_seeds, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+      JNE_CUDA(ctx, launch_run<true>(ctx, dv, s.d_seeds, nullptr, m, prm, s.d_out, dv.d_err, nullptr, s.stream, which));
       ctx->launches.fetch_add(1);
-      JNE_CUDA(ctx, cudaEventRecord(s.computed, dv.stream));
-      JNE_CUDA(ctx, cudaStreamWaitEvent(dv.copy_stream, s.computed, 0));
-      JNE_CUDA(ctx, cudaMemcpyAsync(s.h_out, s.d_out, m * prm.p * sizeof(double), cudaMemcpyDeviceToHost, dv.copy_stream));
-      JNE_CUDA(ctx, cudaEventRecord(s.done, dv.copy_stream));
+      JNE_CUDA(ctx, cudaMemcpyAsync(s.h_out, s.d_out, m * prm.p * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+      JNE_CUDA(ctx, cudaEventRecord(s.done, s.stream));
       s.n = m; s.offset = done; s.busy = true;
       done += m;
       which ^= 1;
@@ -442,15 +443,14 @@ void jne_shutdown(jne_ctx* ctx) {
       if (s.h_seeds) cudaFreeHost(s.h_seeds);
       if (s.h_out) cudaFreeHost(s.h_out);
       if (s.done) cudaEventDestroy(s.done);
-      if (s.computed) cudaEventDestroy(s.computed);
+      if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (dv.d_err) cudaFree(dv.d_err);
     if (dv.d_sched) cudaFree(dv.d_sched);
-    if (dv.d_mom) cudaFree(dv.d_mom);
+    for (double* m : dv.d_mom) if (m) cudaFree(m);
     if (dv.h_err) cudaFreeHost(dv.h_err);
     if (dv.d_scratch) cudaFree(dv.d_scratch);
     if (dv.stream) cudaStreamDestroy(dv.stream);
-    if (dv.copy_stream) cudaStreamDestroy(dv.copy_stream);
   }
   delete ctx;
 }
@@ -486,14 +486,13 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
       if (prop.major != 10)
         return fail(nullptr, JNE_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100 (B200); the kernels are built for sm_100a only");
       JNE_CUDA(nullptr, cudaStreamCreateWithFlags(&dv.stream, cudaStreamNonBlocking));
-      JNE_CUDA(nullptr, cudaStreamCreateWithFlags(&dv.copy_stream, cudaStreamNonBlocking));
       for (auto& s : dv.slot) {
         JNE_CUDA(nullptr, cudaMalloc(&s.d_seeds, kChunkRuns * sizeof(uint32_t)));
         JNE_CUDA(nullptr, cudaMalloc(&s.d_out, kChunkRuns * kMaxWidth * sizeof(double)));
         JNE_CUDA(nullptr, cudaMallocHost(&s.h_seeds, kChunkRuns * sizeof(uint32_t)));
         JNE_CUDA(nullptr, cudaMallocHost(&s.h_out, kChunkRuns * kMaxWidth * sizeof(double)));
         JNE_CUDA(nullptr, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-        JNE_CUDA(nullptr, cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
+        JNE_CUDA(nullptr, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
       }
       unsigned char tables[8 * 256];
       make_schedules(tables);
