@@ -298,7 +298,7 @@ def main():
         tfile = ROOT / "profiles" / "traffic_bytes_per_launch.json"
         if tfile.exists():
             try:
-                traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
+                traffic = json.loads(tfile.read_text()).get("dram_bytes_per_run") * R   # per launch of R seeds
             except Exception:
                 traffic = None
         line = {
@@ -312,7 +312,9 @@ def main():
                 "parallelism": f"seed-sharded x{world}, no collective",
             },
             "roofline": {
-                "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                # the FP64 tensor pipe (DMMA.8x8x4; scalar DFMA shares the same datapath and the same cap)
+                "bound": "tensor", "precision": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak,
                 "traffic": traffic,
                 "peak_source": "measured in this run: register-resident DFMA / DMMA m8n8k4 chains (jne_fp64_peak_tflops); "
                                "MEASURED_PEAKS.json holds no FP64 figure",
