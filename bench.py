@@ -51,7 +51,8 @@ def parse_args():
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--dim", type=int, default=12)
     ap.add_argument("--T", type=int, default=10000, help="time steps per run (the reference's --steps)")
-    ap.add_argument("--runs", type=int, default=1 << 17, help="runs per model per step per GPU")
+    # 133 200 = 45 full waves of 148 SMs x 5 resident CTAs x 4 runs per CTA (the fused kernel's geometry)
+    ap.add_argument("--runs", type=int, default=133200, help="runs per model per step per GPU")
     ap.add_argument("--cpu-runs", type=int, default=0, help="CPU sample: runs per model (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

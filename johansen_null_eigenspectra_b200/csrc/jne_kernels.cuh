@@ -494,6 +494,13 @@ __device__ __forceinline__ void jne_consume8(uint32_t t, uint32_t t_end, int g, 
                                              double (&s1)[JneGeo<DP>::NRT], double (&s2)[JneGeo<DP>::NRT],
                                              double (&acc)[JneGeo<DP>::NT][2], double& w1, double w2c) {
   using G = JneGeo<DP>;
+  // Trend moments per 8-step block.  With w1_s = w1 + 2s and w2_s = 3 w1_s^2 + w2c = w2 + 12 w1 s + 12 s^2:
+  //   sum_s w1_s f_s = w1 A + 2 B,   sum_s w2_s f_s = w2 A + 12 w1 B + 12 Q,   A = sum f_s, B = sum s f_s, Q = sum s^2 f_s
+  // so the per-step work is one add and one or two FMAs with small exact multipliers, and the weights are
+  // touched once per block instead of three FP64 operations per lane and step.
+  double bA[G::NRT], bB[G::NRT], bQ[G::NRT];
+#pragma unroll
+  for (int j = 0; j < G::NRT; ++j) { bA[j] = 0.0; bB[j] = 0.0; bQ[j] = 0.0; }
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
     const bool active = !MASKED || (t + s) < t_end;
@@ -536,16 +543,31 @@ __device__ __forceinline__ void jne_consume8(uint32_t t, uint32_t t_end, int g, 
       }
     // deterministic cross moments of the path (those of the increments follow by summation by parts in
     // the epilogue: sum w z = w_last c_end - sum (w_t - w_{t-1}) c_t) and the running path
-    double w2 = 0.0;
-    if (DET >= 2) w2 = fma(3.0 * w1, w1, w2c);
 #pragma unroll
     for (int j = 0; j < G::NRT; ++j) {
-      s0[j] += f[j];
-      if (DET >= 1) s1[j] = fma(w1, f[j], s1[j]);
-      if (DET >= 2) s2[j] = fma(w2, f[j], s2[j]);
+      bA[j] += f[j];     // every DET sums sum c the same way: records stay bit-identical across kernels
+      if (DET >= 1 && s > 0) bB[j] = fma((double)s, f[j], bB[j]);
+      if (DET >= 2 && s > 0) bQ[j] = fma((double)(s * s), f[j], bQ[j]);
       c[j] = cn[j];
     }
-    if (DET >= 1) w1 += 2.0;
+  }
+  if (DET == 0) {
+#pragma unroll
+    for (int j = 0; j < G::NRT; ++j) s0[j] += bA[j];
+  } else {
+    const double w2 = fma(3.0 * w1, w1, w2c), w1x12 = 12.0 * w1;
+#pragma unroll
+    for (int j = 0; j < G::NRT; ++j) {
+      s0[j] += bA[j];
+      s1[j] = fma(w1, bA[j], s1[j]);
+      s1[j] = fma(2.0, bB[j], s1[j]);
+      if (DET >= 2) {
+        s2[j] = fma(w2, bA[j], s2[j]);
+        s2[j] = fma(w1x12, bB[j], s2[j]);
+        s2[j] = fma(12.0, bQ[j], s2[j]);
+      }
+    }
+    w1 += 16.0;
   }
 }
 
@@ -556,7 +578,7 @@ __device__ __forceinline__ void jne_consume8(uint32_t t, uint32_t t_end, int g, 
 // DET: 0 = models 0,1 (sum c only), 1 = models 2,3 (+ w1 moments), 2 = model 4 (+ w2 moments).
 // ---------------------------------------------------------------------------------------------
 template <int DP, int DET, bool SRC_RNG, bool MULTI>
-__global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA, (MULTI && SRC_RNG) ? 5 : 1)
+__global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA, SRC_RNG ? ((DET == 0 && !MULTI) ? 6 : 5) : 1)
 jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB, uint64_t n,
                JneRunParams prm, double* __restrict__ out, unsigned int* __restrict__ err_count,
                double* __restrict__ dbg /* optional: per run S2 (16x16) then R (16x16) */) {
