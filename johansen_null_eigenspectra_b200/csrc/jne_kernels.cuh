@@ -58,7 +58,8 @@ template <int DP> struct JneGeo {
   // per-warp layout (doubles):  [0, TOT) totals | raw: VV, vec  -- after stitching the raw area is dead and
   // [TOT, TOT + STITCH) holds the model-independent stitched moments M_BB, M_Bz (16 x 16 each)
   static constexpr int RAW_SZ = TOT_SZ + VV_SZ + VEC_SZ;
-  static constexpr int STITCH_SZ = 2 * 256;
+  static constexpr int STITCH_HALF = DP * 16;                    // M_BB (and M_Bz): DP rows x 16 columns
+  static constexpr int STITCH_SZ = 2 * STITCH_HALF;
   static constexpr int WORK_SZ = 2 * MAT_SZ + MISC_SZ;            // solver workspace
   // single-model launches: the workspace aliases the stitched moments (entries pass through registers)
   static constexpr int WARP_SMEM = RAW_SZ > TOT_SZ + WORK_SZ ? RAW_SZ : TOT_SZ + WORK_SZ;
@@ -352,7 +353,7 @@ __device__ __forceinline__ void jne_warp_stitch(const double* VV, const double* 
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const int i = 2 * q + (lane >> 4);
-    if (i < 16) { MBB[i * 16 + j] = r_bb[q]; MBZ[i * 16 + j] = r_bz[q]; }
+    if (i < DP) { MBB[i * 16 + j] = r_bb[q]; MBZ[i * 16 + j] = r_bz[q]; }
   }
   __syncwarp();
 }
@@ -577,8 +578,11 @@ __device__ __forceinline__ void jne_consume8(uint32_t t, uint32_t t_end, int g, 
 // src/rng_matrix.rs:36) and the path is rebuilt exactly as src/johansen_statistics.rs:80-82 does.
 // DET: 0 = models 0,1 (sum c only), 1 = models 2,3 (+ w1 moments), 2 = model 4 (+ w2 moments).
 // ---------------------------------------------------------------------------------------------
+#ifndef JNE_MULTI_MINB
+#define JNE_MULTI_MINB 5
+#endif
 template <int DP, int DET, bool SRC_RNG, bool MULTI>
-__global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA, SRC_RNG ? ((DET == 0 && !MULTI) ? 6 : 5) : 1)
+__global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA, SRC_RNG ? (MULTI ? JNE_MULTI_MINB : (DET == 0 ? 6 : 5)) : 1)
 jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB, uint64_t n,
                JneRunParams prm, double* __restrict__ out, unsigned int* __restrict__ err_count,
                double* __restrict__ dbg /* optional: per run S2 (16x16) then R (16x16) */) {
@@ -593,10 +597,10 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   double* VV = tot + G::TOT_SZ;     // raw view
   double* vec = VV + G::VV_SZ;
   double* MBB = tot + G::TOT_SZ;    // stitched view (aliases the raw view, see jne_warp_stitch)
-  double* MBZ = MBB + 256;
+  double* MBZ = MBB + G::STITCH_HALF;
   // work view: single-model launches alias it onto the stitched view (see jne_warp_assemble); multi-model
   // launches keep the stitched moments live for the next model and place it behind them
-  double* S2 = MULTI ? MBZ + 256 : MBB;
+  double* S2 = MULTI ? MBZ + G::STITCH_HALF : MBB;
   double* R = S2 + G::MAT_SZ;
   double* misc = R + G::MAT_SZ;
 

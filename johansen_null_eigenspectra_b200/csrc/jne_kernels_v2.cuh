@@ -233,15 +233,16 @@ jne_solve_kernel(const double* __restrict__ mom, uint64_t n, JneRunParams prm, d
   double* wsm = smem + (size_t)warp * WS;
   double* tot = wsm;
   double* MBB = tot + G::TOT_SZ;
-  double* MBZ = MBB + 256;
-  double* S2 = MULTI ? MBZ + 256 : MBB;
+  double* MBZ = MBB + G::STITCH_HALF;
+  double* S2 = MULTI ? MBZ + G::STITCH_HALF : MBB;
   double* R = S2 + G::MAT_SZ;
   double* misc = R + G::MAT_SZ;
   const int d = prm.dim;
   const double* M = mom + run * (uint64_t)JNE_MOM_DOUBLES;
-  for (int e = lane; e < 512; e += 32) {
-    const int i = (e >> 4) & 15, j = e & 15;
-    MBB[e] = (i < d && j < d) ? M[e] : 0.0;       // covers MBB (e < 256) and MBZ (e >= 256) alike
+  for (int e = lane; e < G::STITCH_HALF; e += 32) {   // 12 rows x 16 columns of each 16 x 16 global array
+    const int i = e >> 4, j = e & 15;
+    MBB[e] = (i < d && j < d) ? M[e] : 0.0;
+    MBZ[e] = (i < d && j < d) ? M[256 + e] : 0.0;
   }
   for (int e = lane; e < 96; e += 32) tot[e] = ((e & 15) < d) ? M[512 + e] : 0.0;
   __syncwarp();
