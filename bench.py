@@ -175,6 +175,9 @@ def main():
 
     import torch
     import torch.distributed as dist
+    if not (ROOT / "johansen_null_eigenspectra_b200" / "libjne.so").exists() and local_rank == 0:
+        import __graft_entry__          # built artefacts are git-ignored: build on a fresh checkout
+        __graft_entry__.build()
     import johansen_null_eigenspectra_b200 as jne
     from johansen_null_eigenspectra_b200.sharding import weak_scaling_seeds
 

@@ -8,8 +8,22 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 
+def _ensure_built():
+    """A fresh checkout has no libjne.so (built artefacts are git-ignored): build it, and the C oracle, before any
+    test imports the package.  build.py is loaded by path so that the package itself is not imported first."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("jne_build", ROOT / "johansen_null_eigenspectra_b200" / "build.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if mod.is_stale():
+        mod.build_library()
+    from oracle import c_oracle
+    c_oracle.build()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    _ensure_built()
 
 
 @pytest.fixture(scope="session")
