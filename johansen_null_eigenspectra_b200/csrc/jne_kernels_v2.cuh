@@ -24,8 +24,12 @@
 #define JNE_V2_MINB 2         // min resident CTAs per SM (register cap = 65536 / (32 * WARPS * MINB))
 #endif
 
+#ifndef JNE_V2_SMEM
+#define JNE_V2_SMEM 1         // 1: operands travel through shared memory (4 stores + 10 loads); 0: 30 shuffles
+#endif
+
 template <int DET, bool SRC_RNG, bool MASKED>
-__device__ __forceinline__ void jne_v2_step(const double (&zs)[3], bool active, int src1, int src2, double (&c)[3],
+__device__ __forceinline__ void jne_v2_step(const double (&zs)[3], bool active, int src1, int src2, double* xch, double (&c)[3],
                                             double (&s0)[3], double (&s1)[3], double (&s2)[3], double (&azd)[3][4][3],
                                             double (&aown)[6], double (&an1)[3][3], double (&an2)[6], double& w1,
                                             double w2c) {
@@ -40,6 +44,32 @@ __device__ __forceinline__ void jne_v2_step(const double (&zs)[3], bool active, 
   }
   // increments of the other three lanes of the group (rows 3(l^x) + b) and path values of the next two lanes
   double r[3][3], fn1[3], fn2[3];
+#if JNE_V2_SMEM
+  {
+    // xch: the WARP's exchange area, lane-major so that every access is bank-conflict free:
+    //   double2 A[32] = (dz0, dz1), double B[32] = dz2, double2 C[32] = (f0, f1), double D[32] = f2.
+    // All traffic stays inside the warp, whose shared-memory operations execute in program order.
+    const int lane = threadIdx.x & 31;
+    double2* A = reinterpret_cast<double2*>(xch);
+    double* B = xch + 64;
+    double2* C = reinterpret_cast<double2*>(xch + 96);
+    double* D = xch + 160;
+    A[lane] = make_double2(dz[0], dz[1]);
+    B[lane] = dz[2];
+    C[lane] = make_double2(f[0], f[1]);
+    D[lane] = f[2];
+    __syncwarp();
+#pragma unroll
+    for (int x = 1; x <= 3; ++x) {
+      const double2 a = A[lane ^ x];
+      r[x - 1][0] = a.x; r[x - 1][1] = a.y; r[x - 1][2] = B[lane ^ x];
+    }
+    const double2 a1 = C[src1], a2 = C[src2];
+    fn1[0] = a1.x; fn1[1] = a1.y; fn1[2] = D[src1];
+    fn2[0] = a2.x; fn2[1] = a2.y; fn2[2] = D[src2];
+    __syncwarp();   // the next step's stores must not overtake lagging lanes' loads of this step
+  }
+#else
 #pragma unroll
   for (int b = 0; b < 3; ++b) {
     r[0][b] = __shfl_xor_sync(0xffffffffu, dz[b], 1);
@@ -48,6 +78,7 @@ __device__ __forceinline__ void jne_v2_step(const double (&zs)[3], bool active, 
     fn1[b] = __shfl_sync(0xffffffffu, f[b], src1);
     fn2[b] = __shfl_sync(0xffffffffu, f[b], src2);
   }
+#endif
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
 #pragma unroll
@@ -80,6 +111,7 @@ __global__ void __launch_bounds__(32 * JNE_V2_WARPS, JNE_V2_MINB)
 jne_moments12_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB, uint64_t n, JneRunParams prm,
                      double* __restrict__ mom) {
   __shared__ uint32_t key_stage[JNE_V2_WARPS][32][10];
+  __shared__ __align__(16) double xch_all[JNE_V2_WARPS][192];   // per warp: A[32] double2, B[32], C[32] double2, D[32]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int l = lane & 3;
   const uint64_t run_raw = ((uint64_t)blockIdx.x * JNE_V2_WARPS + warp) * 8 + (lane >> 2);
@@ -103,6 +135,7 @@ jne_moments12_kernel(const uint32_t* __restrict__ seeds, const double* __restric
 #pragma unroll
   for (int a = 0; a < 3; ++a) scale[a] = (3u * l + a < d) ? 1.0f : 0.0f;
   const int src1 = (lane & ~3) | ((l + 1) & 3), src2 = (lane & ~3) | ((l + 2) & 3);
+  double* xch = &xch_all[warp][0];
 
   double c[3] = {0, 0, 0}, s0[3] = {0, 0, 0}, s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
   double azd[3][4][3], aown[6], an1[3][3], an2[6];
@@ -135,7 +168,7 @@ jne_moments12_kernel(const uint32_t* __restrict__ seeds, const double* __restric
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const double zs[3] = {z[0][s], z[1][s], z[2][s]};
-      jne_v2_step<DET, SRC_RNG, false>(zs, true, src1, src2, c, s0, s1, s2, azd, aown, an1, an2, w1, w2c);
+      jne_v2_step<DET, SRC_RNG, false>(zs, true, src1, src2, xch, c, s0, s1, s2, azd, aown, an1, an2, w1, w2c);
     }
   }
   if ((T & 3u) != 0u) {   // ragged tail: steps at or beyond T contribute nothing
@@ -156,7 +189,7 @@ jne_moments12_kernel(const uint32_t* __restrict__ seeds, const double* __restric
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const double zs[3] = {z[0][s], z[1][s], z[2][s]};
-      jne_v2_step<DET, SRC_RNG, true>(zs, 4 * tb + s < T, src1, src2, c, s0, s1, s2, azd, aown, an1, an2, w1, w2c);
+      jne_v2_step<DET, SRC_RNG, true>(zs, 4 * tb + s < T, src1, src2, xch, c, s0, s1, s2, azd, aown, an1, an2, w1, w2c);
     }
   }
   if (!live) return;
