@@ -46,7 +46,7 @@ struct Device {
   Slot slot[2];
   unsigned int* d_err = nullptr;
   unsigned int* h_err = nullptr;  // pinned
-  unsigned char* d_sched = nullptr;   // 8 Jacobi pairing tables (ne = 2, 4, .., 16), 256 bytes each
+  uint32_t* d_jtab = nullptr;   // 8 Jacobi step tables (ne = 2, 4, .., 16), kTabWords words each
   double* d_mom[2] = {nullptr, nullptr};   // v2 path: per-run moments between jne_moments12_kernel and jne_solve_kernel,
   uint64_t mom_runs[2] = {0, 0};           // one buffer per concurrently used stream (capacity in runs)
   double* d_scratch = nullptr;    // increments / pencil inputs, grown on demand
@@ -115,23 +115,39 @@ uint32_t mask_width(uint32_t mask, uint32_t dim) {
   return w;
 }
 
-// Round-robin (circle method) pairing of ne players: slot 0 pairs player ne-1 with `step`, slot l pairs
-// (step + l) with (step - l) modulo ne-1.  Bytes [step][slot][2], 256 per table, tables for ne = 2, 4, .., 16.
-void make_schedules(unsigned char* tables /* 8 x 256 */) {
-  std::memset(tables, 0, 8 * 256);
+// Jacobi step tables (jne_warp_jacobi).  Round-robin (circle method) pairing of ne players: in step `step`
+// slot 0 pairs player ne-1 with `step`, slot l pairs (step + l) with (step - l) modulo ne-1; each pair is (min, max).
+// Per step: npairs rotation words o(p,p) | o(q,q) << 8 | o(p,q) << 16, then one word per 2x2 block (P1 <= P2) of
+// pair slots, o(p1,p2) | o(p1,q2) << 8 | o(q1,p2) << 16 | o(q1,q2) << 24, where o(i,j) is the offset of the
+// element in the packed upper triangle of the ne x ne matrix.  One table per ne = 2, 4, .., 16.
+constexpr int kTabWords = 15 * (8 + 36);
+void make_jacobi_tables(uint32_t* tables /* 8 x kTabWords */) {
+  std::memset(tables, 0, 8 * kTabWords * sizeof(uint32_t));
   for (int ne = 2; ne <= 16; ne += 2) {
-    unsigned char* t = tables + (ne / 2 - 1) * 256;
-    const int np = ne / 2, m = ne - 1;
-    for (int step = 0; step < m; ++step)
+    uint32_t* t = tables + (ne / 2 - 1) * kTabWords;
+    const int np = ne / 2, m = ne - 1, nblk = np * (np + 1) / 2;
+    auto tri = [ne](int i, int j) -> uint32_t {
+      if (i > j) std::swap(i, j);
+      return (uint32_t)(i * ne - i * (i - 1) / 2 + (j - i));
+    };
+    for (int step = 0; step < m; ++step) {
+      int pp[8], qq[8];
       for (int l = 0; l < np; ++l) {
         const int a = (l == 0) ? m : (step + l) % m, b = (step + m - l) % m;
-        t[2 * (step * np + l)] = (unsigned char)std::min(a, b);
-        t[2 * (step * np + l) + 1] = (unsigned char)std::max(a, b);
+        pp[l] = std::min(a, b);
+        qq[l] = std::max(a, b);
       }
+      uint32_t* row = t + step * (np + nblk);
+      for (int l = 0; l < np; ++l) row[l] = tri(pp[l], pp[l]) | tri(qq[l], qq[l]) << 8 | tri(pp[l], qq[l]) << 16;
+      int blk = 0;
+      for (int P1 = 0; P1 < np; ++P1)
+        for (int P2 = P1; P2 < np; ++P2)
+          row[np + blk++] = tri(pp[P1], pp[P2]) | tri(pp[P1], qq[P2]) << 8 | tri(qq[P1], pp[P2]) << 16 | tri(qq[P1], qq[P2]) << 24;
+    }
   }
 }
 
-const unsigned char* sched_for(const Device& dv, uint32_t d) { return dv.d_sched + (((d + 1) / 2) - 1) * 256; }
+const uint32_t* jtab_for(const Device& dv, uint32_t d) { return dv.d_jtab + (((d + 1) / 2) - 1) * kTabWords; }
 
 JneRunParams make_params_mask(uint32_t mask, uint32_t dim, uint32_t steps, bool from_increments) {
   JneRunParams p{};
@@ -161,9 +177,9 @@ JneRunParams make_params(uint8_t model, uint32_t dim, uint32_t steps, bool from_
 }
 
 template <int DP, bool MULTI> constexpr size_t cta_smem() {
-  return (size_t)JNE_WARPS_PER_CTA * (MULTI ? JneGeo<DP>::WARP_SMEM_MULTI : JneGeo<DP>::WARP_SMEM) * sizeof(double);
+  return (size_t)JNE_WARPS_PER_CTA * JneEpi<DP, MULTI ? 5 : 1>::WARP_SMEM * sizeof(double);
 }
-constexpr size_t pencil_smem() { return (size_t)JNE_WARPS_PER_CTA * (2 * 16 * JNE_LD + 96) * sizeof(double); }
+constexpr size_t pencil_smem() { return (size_t)JNE_WARPS_PER_CTA * JneEpi<16, 1>::END * sizeof(double); }
 
 template <int DP, int DET, bool RNG, bool MULTI>
 cudaError_t launch_one(const uint32_t* d_seeds, const double* d_dB, uint64_t n, const JneRunParams& prm,
@@ -272,7 +288,7 @@ int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32
   auto body = [&]() -> int {
     JNE_CUDA(ctx, cudaSetDevice(dv.id));
     JneRunParams prm = prm_in;
-    prm.sched = sched_for(dv, prm.dim);
+    prm.jtab = jtab_for(dv, prm.dim);
     *dv.h_err = 0;
     JNE_CUDA(ctx, cudaMemsetAsync(dv.d_err, 0, sizeof(unsigned int), dv.stream));
     JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
@@ -446,7 +462,7 @@ void jne_shutdown(jne_ctx* ctx) {
       if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (dv.d_err) cudaFree(dv.d_err);
-    if (dv.d_sched) cudaFree(dv.d_sched);
+    if (dv.d_jtab) cudaFree(dv.d_jtab);
     for (double* m : dv.d_mom) if (m) cudaFree(m);
     if (dv.h_err) cudaFreeHost(dv.h_err);
     if (dv.d_scratch) cudaFree(dv.d_scratch);
@@ -494,10 +510,10 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
         JNE_CUDA(nullptr, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         JNE_CUDA(nullptr, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
       }
-      unsigned char tables[8 * 256];
-      make_schedules(tables);
-      JNE_CUDA(nullptr, cudaMalloc(&dv.d_sched, sizeof tables));
-      JNE_CUDA(nullptr, cudaMemcpy(dv.d_sched, tables, sizeof tables, cudaMemcpyHostToDevice));
+      std::vector<uint32_t> tables(8 * kTabWords);
+      make_jacobi_tables(tables.data());
+      JNE_CUDA(nullptr, cudaMalloc(&dv.d_jtab, tables.size() * sizeof(uint32_t)));
+      JNE_CUDA(nullptr, cudaMemcpy(dv.d_jtab, tables.data(), tables.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
       JNE_CUDA(nullptr, cudaMalloc(&dv.d_err, sizeof(unsigned int)));
       JNE_CUDA(nullptr, cudaMemset(dv.d_err, 0, sizeof(unsigned int)));
       JNE_CUDA(nullptr, cudaMallocHost(&dv.h_err, sizeof(unsigned int)));
@@ -548,7 +564,7 @@ int jne_eigs_batch_multi_device(jne_ctx* ctx, uint32_t model_mask, uint32_t dim,
   Device& dv = ctx->devs[0];
   JNE_CUDA(ctx, cudaSetDevice(dv.id));
   JneRunParams prm = make_params_mask(model_mask, dim, steps, false);
-  prm.sched = sched_for(dv, dim);
+  prm.jtab = jtab_for(dv, dim);
   const uint64_t max_runs = (uint64_t)0x7fffffffu * JNE_WARPS_PER_CTA;
   for (uint64_t off = 0; off < n; off += max_runs) {
     const uint64_t m = std::min(max_runs, n - off);
@@ -593,7 +609,7 @@ int jne_eigs_batch_device(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t st
   Device& dv = ctx->devs[0];
   JNE_CUDA(ctx, cudaSetDevice(dv.id));
   JneRunParams prm = make_params(model, dim, steps, false);
-  prm.sched = sched_for(dv, dim);
+  prm.jtab = jtab_for(dv, dim);
   // grid.x is 32-bit: split very large batches
   const uint64_t max_runs = (uint64_t)0x7fffffffu * JNE_WARPS_PER_CTA;
   for (uint64_t off = 0; off < n; off += max_runs) {
@@ -626,7 +642,7 @@ static int single_device_run(jne_ctx* ctx, const JneRunParams& prm_in, const uin
   Device& dv = ctx->devs[0];
   JNE_CUDA(ctx, cudaSetDevice(dv.id));
   JneRunParams prm = prm_in;
-  prm.sched = sched_for(dv, prm.dim);
+  prm.jtab = jtab_for(dv, prm.dim);
   const bool rng = dB == nullptr;
   const uint64_t per_run_in = rng ? 0 : (uint64_t)prm.dim * prm.steps;
   // bound the scratch: <= 1 GiB of increments, <= 2^18 runs per launch
@@ -749,7 +765,7 @@ int jne_pencil_eigs_batch(jne_ctx* ctx, uint32_t p, uint32_t d, const double* S1
     JNE_CUDA(ctx, cudaMemcpyAsync(d1, S1 + off * p * d, m * p * d * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
     JNE_CUDA(ctx, cudaMemcpyAsync(d2, S2 + off * p * p, m * p * p * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
     jne_pencil_kernel<<<(unsigned)((m + JNE_WARPS_PER_CTA - 1) / JNE_WARPS_PER_CTA), 32 * JNE_WARPS_PER_CTA, pencil_smem(), dv.stream>>>(
-        d1, d2, m, (int)p, (int)d, 1.0, dout, dv.d_err, sched_for(dv, d));
+        d1, d2, m, (int)p, (int)d, 1.0, dout, dv.d_err, jtab_for(dv, d));
     JNE_CUDA(ctx, cudaGetLastError());
     ctx->launches.fetch_add(1);
     JNE_CUDA(ctx, cudaMemcpyAsync(out + off * p, dout, m * p * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
@@ -819,7 +835,7 @@ int jne_simulate_percentiles(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t
   Device& dv = ctx->devs[0];
   JNE_CUDA(ctx, cudaSetDevice(dv.id));
   JneRunParams prm = make_params(model, dim, steps, false);
-  prm.sched = sched_for(dv, dim);
+  prm.jtab = jtab_for(dv, dim);
   const uint64_t chunk = 1ull << 20;
   double* d_agg = nullptr;     // trace[n] + sort space[n] + max[n] + sort space[n]
   uint32_t* d_seeds = nullptr;

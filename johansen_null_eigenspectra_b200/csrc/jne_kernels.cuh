@@ -22,9 +22,8 @@
 #include <cuda_runtime.h>
 #include "jne_rng.cuh"
 
-#define JNE_MAX_DIM 15           // p = dim+1 <= 16 fits one half-warp column per Jacobi pair slot
+#define JNE_MAX_DIM 15           // p = dim+1 <= 16: one half-warp covers a row / column of the work matrices
 #define JNE_WARPS_PER_CTA 4
-#define JNE_LD 17                // leading dimension of the 16x16 work matrices (bank-conflict padding)
 
 struct JneRunParams {
   uint32_t dim;        // d
@@ -35,7 +34,7 @@ struct JneRunParams {
   uint32_t full_blocks;  // leading 8-step blocks that are inside the segment for every lane
   uint32_t model_mask;   // bit m set: solve model m (multi-model launches; single-model launches set one bit)
   uint32_t out_stride;   // doubles per run in `out` (sum of p over the selected models)
-  const unsigned char* sched;   // device pointer: round-robin Jacobi pairing for ne = even(dim), [step][slot][2] bytes
+  const uint32_t* jtab;  // device pointer: Jacobi step table for ne = even(dim) (jne_api.cu, make_jacobi_tables)
   double T;            // (double)steps
   double factor;       // s^2 * T: 1 for the RNG path (s^2 = dt), T for caller-supplied increments
   double seg_n[4];     // steps in segment k
@@ -52,20 +51,38 @@ template <int DP> struct JneGeo {
   // per-warp shared memory, in doubles
   static constexpr int VV_SZ = 8 * NRT * VV_LD;
   static constexpr int VEC_SZ = 6 * 4 * 16;
-  static constexpr int MAT_SZ = 16 * JNE_LD;
-  static constexpr int MISC_SZ = 96;    // invd[16] cs[16] ev[16] pq[8 as int2] schedule[240 bytes]
   static constexpr int TOT_SZ = 7 * 16;
-  // per-warp layout (doubles):  [0, TOT) totals | raw: VV, vec  -- after stitching the raw area is dead and
-  // [TOT, TOT + STITCH) holds the model-independent stitched moments M_BB, M_Bz (16 x 16 each)
   static constexpr int RAW_SZ = TOT_SZ + VV_SZ + VEC_SZ;
   static constexpr int STITCH_HALF = DP * 16;                    // M_BB (and M_Bz): DP rows x 16 columns
   static constexpr int STITCH_SZ = 2 * STITCH_HALF;
-  static constexpr int WORK_SZ = 2 * MAT_SZ + MISC_SZ;            // solver workspace
-  // single-model launches: the workspace aliases the stitched moments (entries pass through registers)
-  static constexpr int WARP_SMEM = RAW_SZ > TOT_SZ + WORK_SZ ? RAW_SZ : TOT_SZ + WORK_SZ;
-  // multi-model launches: the stitched moments stay live for the next model, the workspace sits behind them
-  static constexpr int WARP_SMEM_MULTI =
-      RAW_SZ > TOT_SZ + STITCH_SZ + WORK_SZ ? RAW_SZ : TOT_SZ + STITCH_SZ + WORK_SZ;
+  // pencil matrices S2 (p x p) and R = S1' (p x d), p <= min(DP + 1, 16): odd leading dimension (bank spread)
+  static constexpr int LDW = DP + 1;
+  static constexpr int WROWS = DP < 16 ? DP + 1 : 16;
+  static constexpr int MAT_SZ = WROWS * LDW + (WROWS * LDW & 1);
+  // Jacobi: ne = even(d) <= DP players, NPAIR pair slots, NBLK 2x2 blocks (P1 <= P2), packed upper triangle
+  static constexpr int NPAIR = DP / 2;
+  static constexpr int NBLK = NPAIR * (NPAIR + 1) / 2;
+  static constexpr int G_SZ = DP * (DP + 1) / 2;
+};
+
+// Per-warp shared-memory layout of the epilogue for up to NM models per run (1 or 5), in doubles:
+//   [0, TOT)  totals | stitched M_BB, M_Bz | S2, R | G[NM] packed | cs[NM][NPAIR] (c, s) | ev[16] | fac[8]
+// The raw moment dump of the time loop (VV, vec) aliases everything behind the totals.  NM == 1: S2 / R alias the
+// stitched moments (jne_warp_assemble passes the entries through registers).
+template <int DP, int NM> struct JneEpi {
+  using G = JneGeo<DP>;
+  static constexpr int OFF_S2 = NM > 1 ? G::TOT_SZ + G::STITCH_SZ : G::TOT_SZ;
+  static constexpr int OFF_R = OFF_S2 + G::MAT_SZ;
+  static constexpr int OFF_G = NM > 1 ? OFF_R + G::MAT_SZ
+                                      : G::TOT_SZ + (G::STITCH_SZ > 2 * G::MAT_SZ ? G::STITCH_SZ : 2 * G::MAT_SZ);
+  static constexpr int OFF_CS = OFF_G + NM * G::G_SZ;
+  static constexpr int OFF_EV = OFF_CS + 2 * NM * G::NPAIR;
+  static constexpr int OFF_FAC = OFF_EV + 16;
+  static constexpr int END = OFF_FAC + 8;
+  static constexpr int WARP_SMEM = G::RAW_SZ > END ? G::RAW_SZ : END;
+  static constexpr int NPASS_B = (NM * G::NBLK + 31) / 32;    // block passes per Jacobi step
+  static constexpr int NPASS_R = (NM * G::NPAIR + 31) / 32;   // rotation passes per Jacobi step
+  static_assert(OFF_CS % 2 == 0 && WARP_SMEM % 2 == 0 && END % 2 == 0, "double2 alignment of cs");
 };
 
 __device__ __forceinline__ void jne_dmma(double& c0, double& c1, double a, double b) {
@@ -74,15 +91,15 @@ __device__ __forceinline__ void jne_dmma(double& c0, double& c1, double a, doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: eigenvalues of the pencil (S1'S1, S2) for one run, one warp.
-//   S2 : p x p symmetric positive definite, full storage, ld JNE_LD   (destroyed)
-//   R  : p x d  = S1' (row j = sum_t F_j dB_t'), ld JNE_LD               (destroyed)
-// Cholesky S2 = L L', W = L^-1 R, A = W W' (same eigenvalues as the pencil), then cyclic two-sided
-// Jacobi in a round-robin parallel ordering: the ne/2 disjoint pairs of a step rotate concurrently,
-// and the update A <- J'AJ is applied per 2x2 BLOCK (pair slot P1 x pair slot P2), one lane per
-// block, so a step costs one rotation pass + one block pass.  lambda_i = factor * |a_ii| sorted
-// descending (src/johansen_statistics.rs:40-45).  Returns false when a value is not finite (the
-// reference panics at :45).
+// K3: eigenvalues of the pencil (S1'S1, S2), one warp per run, up to five models of the run at once.
+//   jne_warp_gram    per model: S2 = L L' (Cholesky), W = L^-1 R, G = W'W in ONE right-looking elimination
+//                    (the d x d Gram matrix has the pencil's non-zero spectrum), unit trace, packed triangle
+//   jne_warp_jacobi  cyclic two-sided Jacobi on all the run's G matrices together: the ne/2 disjoint pairs of
+//                    a round-robin step rotate concurrently and G <- J'GJ is applied per 2x2 BLOCK (pair slot
+//                    P1 x pair slot P2), one lane per block; rotation and block roles of every model share the
+//                    warp's 32 lanes, element addresses come from a host-built step table
+//   jne_warp_emit    lambda_i = factor * |g_ii| sorted descending (src/johansen_statistics.rs:40-45)
+// Replaces GeneralizedEigen::new (LAPACK dggev) + |alpha|/beta + sort, src/johansen_statistics.rs:35-46.
 // ---------------------------------------------------------------------------------------------
 // 1/x and 1/sqrt(x) to ~1 ulp from an FP32 seed + two Newton steps; x must be inside the float range
 // (true for every call site below).  Avoids the ~35-instruction IEEE division / sqrt sequences.
@@ -104,15 +121,6 @@ __device__ __forceinline__ double jne_rsqrt(double x) {
   return y;
 }
 
-// Round-robin (circle method) pairing of ne players: slot 0 pairs player ne-1 with `step`, slot l pairs
-// (step + l) with (step - l) modulo ne-1.  Filled once per run into shared memory as bytes [step][slot][2].
-// The host precomputes the table for the launch's dimension (jne_api.cu, make_schedule); the warp copies its
-// 240 bytes into shared memory.  src == nullptr: keep the table already there (next model of the same run).
-__device__ __forceinline__ void jne_load_schedule(unsigned char* sched, const unsigned char* __restrict__ src) {
-  const int lane = threadIdx.x & 31;
-  if (lane < 30) reinterpret_cast<uint2*>(sched)[lane] = reinterpret_cast<const uint2*>(src)[lane];
-}
-
 // 1/sqrt(x) for any positive finite double (the Cholesky pivots scale with the caller's increments squared,
 // so they may lie outside the float range): x = m 4^k, m in [1, 4).  Non-positive or NaN -> NaN.
 __device__ __forceinline__ double jne_rsqrt_wide(double x) {
@@ -126,143 +134,149 @@ __device__ __forceinline__ double jne_rsqrt_wide(double x) {
   return __hiloint2double(__double2hiint(y) - ((k2 >> 1) << 20), __double2loint(y)) * post;
 }
 
-__device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, double* __restrict__ R,
-                                                   double* __restrict__ misc, int p, int d, double factor,
-                                                   double* __restrict__ out,
-                                                   const unsigned char* __restrict__ sched_src) {
-  const int lane = threadIdx.x & 31;
-  double* invd = misc;                                            // [16]
-  double* cs = misc + 16;                                         // [8] x (c, s)
-  double* ev = misc + 32;                                         // [16]
-  int* pq = reinterpret_cast<int*>(misc + 48);                    // [8] x (p, q)
-  unsigned char* sched = reinterpret_cast<unsigned char*>(misc + 56);   // [15][8][2] bytes
+// offset of element (i <= j) in the packed upper triangle of an ne x ne symmetric matrix (row i holds ne - i entries)
+__device__ __forceinline__ int jne_tri(int i, int j, int ne) { return i * ne - ((i * (i - 1)) >> 1) + (j - i); }
 
-  // --- Cholesky S2 = L L', right-looking, lower triangle in place; only 1/l_jj is ever needed ---
+// G = R' S2^-1 R for one model.
+//   S2 : p x p symmetric positive definite, lower triangle used, ld LDW   (destroyed)
+//   R  : p x d = S1' (row j = sum_t F_j dB_t'), ld LDW                     (destroyed)
+// Right-looking elimination, one pivot j per step: lanes 0..15 scale column j of L (row x = lane), lanes
+// 16..31 scale row j of W = L^-1 R (column x = lane - 16); both travel by shuffle, are never stored, and
+// feed (a) the trailing update of S2, (b) the forward substitution of the remaining rows of R and (c) the
+// Gram accumulation G += w_j w_j' held in registers (lane (h, x) owns G[2q + h][x], x <= 2q + h).
+// Models 1 and 3 (p = d + 1) have rank d: their extra eigenvalue is exactly 0 here (dggev returns O(1e-14)
+// noise for it).  G is zero-padded to ne x ne (ne even), scaled to unit trace (makes the solve invariant to
+// the scale of the caller's increments and keeps the FP32-seeded reciprocals of the Jacobi in range) and
+// written as a packed upper triangle; the trace is returned on every lane.
+template <int DP>
+__device__ __forceinline__ double jne_warp_gram(double* __restrict__ S2, double* __restrict__ R, int p, int d, int ne,
+                                                double* __restrict__ Gm) {
+  constexpr int LDW = JneGeo<DP>::LDW, NQ = (DP + 1) / 2;
+  const int lane = threadIdx.x & 31, x = lane & 15, h = lane >> 4;
+  const bool row_s = x < p, col_r = x < d;
+  double acc[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
   for (int j = 0; j < p; ++j) {
-    const double inv = jne_rsqrt_wide(S2[j * JNE_LD + j]);        // NaN for a non-positive pivot -> flagged below
-    __syncwarp();
-    if (lane == 0) invd[j] = inv;
-    for (int i = j + 1 + lane; i < p; i += 32) S2[i * JNE_LD + j] *= inv;
-    __syncwarp();
-    // trailing update of the lower triangle: rows i in (j, p), cols k in (j, i]
-    const int i = j + 1 + (lane & 15);
-    if (i < p) {
-      const double lij = S2[i * JNE_LD + j];
-      for (int kk = j + 1 + (lane >> 4); kk <= i; kk += 2)
-        S2[i * JNE_LD + kk] = fma(-lij, S2[kk * JNE_LD + j], S2[i * JNE_LD + kk]);
+    const double inv = jne_rsqrt_wide(S2[j * LDW + j]);       // NaN for a non-positive pivot -> flagged at emit
+    double v = 0.0;
+    if (h == 0) { if (x > j && row_s) v = S2[x * LDW + j] * inv; }     // L[x][j]
+    else if (col_r) v = R[j * LDW + x] * inv;                            // W[j][x]
+    const double lxj = __shfl_sync(0xffffffffu, v, x);
+    const double wjx = __shfl_sync(0xffffffffu, v, 16 + x);
+    for (int k0 = j + 1; k0 < p; k0 += 2) {                   // two trailing columns / rows per pass
+      const int kk = k0 + h;
+      const double lkj = __shfl_sync(0xffffffffu, v, kk & 15);
+      if (kk < p) {
+        if (x >= kk && row_s) S2[x * LDW + kk] = fma(-lxj, lkj, S2[x * LDW + kk]);
+        if (col_r) R[kk * LDW + x] = fma(-lkj, wjx, R[kk * LDW + x]);
+      }
     }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+      if (2 * q < d) acc[q] = fma(__shfl_sync(0xffffffffu, v, 16 + ((2 * q + h) & 15)), wjx, acc[q]);
     __syncwarp();
   }
-  // --- W = L^-1 R : lane c solves column c by forward substitution ---
-  if (lane < d) {
-    for (int i = 0; i < p; ++i) {
-      double w = R[i * JNE_LD + lane];
-      for (int kk = 0; kk < i; ++kk) w = fma(-S2[i * JNE_LD + kk], R[kk * JNE_LD + lane], w);
-      R[i * JNE_LD + lane] = w * invd[i];
-    }
-  }
-  // the pair schedule depends on d only: multi-model launches build it for the first model
-  const int ne = (d + 1) & ~1;          // even number of players; for odd d index d is an all-zero row/col
-  const int npairs = ne >> 1;
-  if (sched_src != nullptr) jne_load_schedule(sched, sched_src);
-  __syncwarp();
-  // --- G = W'W (d x d; same non-zero spectrum as W W' and as the pencil) into the S2 storage (L is dead),
-  //     zero-padded to ne x ne; two rows per pass.  Models 1 and 3 (p = d+1) have rank d: their extra
-  //     eigenvalue is exactly 0 here (the reference's dggev returns O(1e-14) noise for it). ---
   double tr = 0.0;
-  for (int i0 = 0; i0 < ne; i0 += 2) {
-    const int i = i0 + (lane >> 4), j = lane & 15;
-    if (j <= i) {
-      double a = 0.0;
-      if (i < d)
-        for (int r = 0; r < p; ++r) a = fma(R[r * JNE_LD + i], R[r * JNE_LD + j], a);
-      if (i == j) tr += a;
-      S2[i * JNE_LD + j] = a;      // this phase only reads R and only writes S2: no staging needed
-      S2[j * JNE_LD + i] = a;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+    if (2 * q + h == x) tr += acc[q];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
+  const double inv_tr = 1.0 / tr;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int i = 2 * q + h;
+    if (i < ne && x <= i) Gm[jne_tri(x, i, ne)] = acc[q] * inv_tr;
+  }
+  return tr;
+}
+
+// Cyclic Jacobi on nm packed matrices Gs[m * gsz ..] at once.  Step table (per step: npairs rotation words, then
+// nblk block words; bytes are packed-triangle offsets):
+//   rotation word of pair slot l = (p, q):      o(p,p) | o(q,q) << 8 | o(p,q) << 16
+//   block word of (P1 <= P2) = (p1,q1),(p2,q2): o(p1,p2) | o(p1,q2) << 8 | o(q1,p2) << 16 | o(q1,q2) << 24
+// tan(theta) comes from FP32 arithmetic (it only steers convergence); (c, s) is normalised in FP64 so that every
+// J is orthogonal to rounding.  Leaving a_pq in place moves the two eigenvalues by about a_pq^2 / |a_qq - a_pp|
+// (second order) and never by more than |a_pq|: a rotation is skipped when that is below 1e-14 of the smaller
+// one, or when |a_pq| <= 2^-50 outright (trace = 1).  A model whose sweep rotates nothing stays untouched while
+// the others finish, so every matrix sees exactly the rotations it would see alone.
+template <int NPB, int NPR>
+__device__ __forceinline__ void jne_warp_jacobi(double* __restrict__ Gs, double2* __restrict__ cs,
+                                                const uint32_t* __restrict__ tab, int nm, int ne, int gsz) {
+  const int lane = threadIdx.x & 31;
+  const int npairs = ne >> 1, nblk = npairs * (npairs + 1) / 2, stride = npairs + nblk;
+  constexpr uint32_t NONE = 0xffffffffu;
+  // roles: rotation role r = m * npairs + slot; block role b = m * nblk + blk, blk -> (P1 <= P2)
+  uint32_t rrole[NPR], brole[NPB];
+#pragma unroll
+  for (int q = 0; q < NPR; ++q) {
+    const int r = lane + 32 * q;
+    rrole[q] = NONE;
+    if (r < nm * npairs) {
+      const int m = r / npairs;
+      rrole[q] = (uint32_t)(m * gsz) | ((uint32_t)r << 10) | ((uint32_t)(r - m * npairs) << 16);
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
-  // --- block ownership: lane -> (P1 <= P2) pair slots; a second block only when npairs == 8 ---
-  const int nblk = npairs * (npairs + 1) / 2;
-  int b1p = -1, b1q = 0, b2p = -1, b2q = 0;
-  {
-    int r = 0, k = lane;
-    while (r < npairs && k >= npairs - r) { k -= npairs - r; ++r; }
-    if (r < npairs) { b1p = r; b1q = r + k; }
-    if (lane + 32 < nblk) {
-      r = 0; k = lane + 32;
-      while (k >= npairs - r) { k -= npairs - r; ++r; }
-      b2p = r; b2q = r + k;
+  for (int q = 0; q < NPB; ++q) {
+    const int b = lane + 32 * q;
+    brole[q] = NONE;
+    if (b < nm * nblk) {
+      const int m = b / nblk, blk = b - m * nblk;
+      int r = 0, k = blk;
+      while (k >= npairs - r) { k -= npairs - r; ++r; }     // block (P1 = r, P2 = r + k)
+      brole[q] = (uint32_t)(m * gsz) | ((uint32_t)(m * npairs + r) << 10) | ((uint32_t)(m * npairs + r + k) << 16) |
+                 ((uint32_t)blk << 22) | (k == 0 ? (1u << 28) : 0u);
     }
   }
-  __syncwarp();
-  // normalise to unit trace: makes the solve invariant to the scale of the caller's increments and keeps
-  // every quantity fed to the FP32-seeded reciprocals inside the float range
-  {
-    const double inv_tr = 1.0 / tr;
-    for (int e = lane; e < ne * 16; e += 32) {
-      const int i = e >> 4, j = e & 15;
-      if (j < ne) S2[i * JNE_LD + j] *= inv_tr;
-    }
-    factor *= tr;
-  }
-  __syncwarp();
-  // Off-diagonals below 2^-50 (x trace = 1) are left alone: they move an eigenvalue by at most that much
-  // (second order unless degenerate), i.e. <= 1e-11 relative on the smallest eigenvalues seen here.
   const double tol = 8.8817841970012523e-16;
   for (int sweep = 0; sweep < 30; ++sweep) {
     int rotated = 0;
-    for (int step = 0; step < ne - 1; ++step) {
-      // rotation of pair slot `lane`.  tan(theta) from FP32 arithmetic (it only steers convergence);
-      // (c, s) normalised in FP64 so that every J is orthogonal to rounding.
-      if (lane < npairs) {
-        const int pp = sched[2 * (step * npairs + lane)], qq = sched[2 * (step * npairs + lane) + 1];
-        double c = 1.0, s = 0.0;
-        const double apq = S2[pp * JNE_LD + qq];
-        const double app = S2[pp * JNE_LD + pp], aqq = S2[qq * JNE_LD + qq];
-        const double diff = aqq - app;
-        // Leaving a_pq in place moves the two eigenvalues by about a_pq^2 / |diff| (second order) and never by
-        // more than |a_pq|: skip the rotation when that is below 1e-14 of the smaller one, or below 2^-50 outright.
-        if (fabs(apq) > tol && apq * apq > 1e-14 * fabs(diff) * fmin(app, aqq)) {
-          float th, h, tf;
-          asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(th) : "f"((float)diff), "f"(2.0f * (float)apq));
-          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(fmaf(th, th, 1.0f)));
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tf) : "f"(fabsf(th) + h));
-          const double t = (double)copysignf(tf, th);
-          c = jne_rsqrt(fma(t, t, 1.0));
-          s = t * c;
-          rotated = 1;
+    const uint32_t* ts = tab;
+    for (int step = 0; step < ne - 1; ++step, ts += stride) {
+#pragma unroll
+      for (int q = 0; q < NPR; ++q) {
+        if (rrole[q] != NONE) {
+          const uint32_t w = __ldg(ts + ((rrole[q] >> 16) & 63u));
+          const double* gm = Gs + (rrole[q] & 1023u);
+          const double app = gm[w & 255u], aqq = gm[(w >> 8) & 255u], apq = gm[(w >> 16) & 255u];
+          double c = 1.0, s = 0.0;
+          const double diff = aqq - app;
+          if (fabs(apq) > tol && apq * apq > 1e-14 * fabs(diff) * fmin(app, aqq)) {
+            float th, hy, tf;
+            asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(th) : "f"((float)diff), "f"(2.0f * (float)apq));
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(hy) : "f"(fmaf(th, th, 1.0f)));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tf) : "f"(fabsf(th) + hy));
+            const double t = (double)copysignf(tf, th);
+            c = jne_rsqrt(fma(t, t, 1.0));
+            s = t * c;
+            rotated = 1;
+          }
+          cs[(rrole[q] >> 10) & 63u] = make_double2(c, s);
         }
-        *reinterpret_cast<double2*>(cs + 2 * lane) = make_double2(c, s);
-        *reinterpret_cast<int2*>(pq + 2 * lane) = make_int2(pp, qq);
       }
       __syncwarp();
       // block pass: B <- J1' B J2 for the 2x2 block (rows of slot P1) x (cols of slot P2)
 #pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const int P1 = pass ? b2p : b1p, P2 = pass ? b2q : b1q;
-        if (P1 >= 0) {
-          const double2 r1 = *reinterpret_cast<const double2*>(cs + 2 * P1);
-          const double2 r2 = *reinterpret_cast<const double2*>(cs + 2 * P2);
+      for (int q = 0; q < NPB; ++q) {
+        if (brole[q] != NONE) {
+          const double2 r1 = cs[(brole[q] >> 10) & 63u], r2 = cs[(brole[q] >> 16) & 63u];
           const double c1 = r1.x, s1 = r1.y, c2 = r2.x, s2 = r2.y;
           if (s1 != 0.0 || s2 != 0.0) {
-            const int2 i1 = *reinterpret_cast<const int2*>(pq + 2 * P1);
-            const int2 i2 = *reinterpret_cast<const int2*>(pq + 2 * P2);
-            const int p1 = i1.x, q1 = i1.y, p2 = i2.x, q2 = i2.y;
-            const double x00 = S2[p1 * JNE_LD + p2], x01 = S2[p1 * JNE_LD + q2];
-            const double x10 = S2[q1 * JNE_LD + p2], x11 = S2[q1 * JNE_LD + q2];
+            const uint32_t w = __ldg(ts + npairs + ((brole[q] >> 22) & 63u));
+            double* gm = Gs + (brole[q] & 1023u);
+            double* e00 = gm + (w & 255u);
+            double* e01 = gm + ((w >> 8) & 255u);
+            double* e10 = gm + ((w >> 16) & 255u);
+            double* e11 = gm + (w >> 24);
+            const double x00 = *e00, x01 = *e01, x10 = *e10, x11 = *e11;
             const double r00 = fma(c1, x00, -s1 * x10), r01 = fma(c1, x01, -s1 * x11);   // J1' B
             const double r10 = fma(s1, x00, c1 * x10), r11 = fma(s1, x01, c1 * x11);
             const double y00 = fma(c2, r00, -s2 * r01), y11 = fma(s2, r10, c2 * r11);    // (.) J2
             double y01 = fma(s2, r00, c2 * r01), y10 = fma(c2, r10, -s2 * r11);
-            if (P1 == P2) { y01 = 0.5 * (y01 + y10); y10 = y01; }   // the (nearly) annihilated element, kept symmetric
-            S2[p1 * JNE_LD + p2] = y00; S2[p1 * JNE_LD + q2] = y01;
-            S2[q1 * JNE_LD + p2] = y10; S2[q1 * JNE_LD + q2] = y11;
-            if (P1 != P2) {                                 // mirror: the matrix is kept in full storage
-              S2[p2 * JNE_LD + p1] = y00; S2[q2 * JNE_LD + p1] = y01;
-              S2[p2 * JNE_LD + q1] = y10; S2[q2 * JNE_LD + q1] = y11;
-            }
+            if (brole[q] & (1u << 28)) { y01 = 0.5 * (y01 + y10); y10 = y01; }   // diagonal block: the (nearly) annihilated element (e01 == e10)
+            *e00 = y00; *e01 = y01; *e10 = y10; *e11 = y11;
           }
         }
       }
@@ -270,10 +284,16 @@ __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, doub
     }
     if (!__any_sync(0xffffffffu, rotated)) break;
   }
-  // --- eigenvalues = factor * |diag| (d of them, the other p - d are 0), sorted descending by rank counting ---
+}
+
+// Eigenvalues of one model = factor * |diag| (d of them, the other p - d are 0), sorted descending by rank
+// counting.  Returns false when a value is not finite (the reference panics at src/johansen_statistics.rs:45).
+__device__ __forceinline__ bool jne_warp_emit(const double* __restrict__ Gm, double factor, int p, int d, int ne,
+                                              double* __restrict__ ev, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
   double v = 0.0;
   if (lane < p) {
-    v = (lane < d) ? fabs(S2[lane * JNE_LD + lane]) * factor : 0.0 * factor;   // 0 * NaN keeps a failure visible
+    v = (lane < d) ? fabs(Gm[jne_tri(lane, lane, ne)]) * factor : 0.0 * factor;   // 0 * NaN keeps a failure visible
     ev[lane] = v;
   }
   __syncwarp();
@@ -288,6 +308,7 @@ __device__ __noinline__ bool jne_warp_pencil_solve(double* __restrict__ S2, doub
     if (!finite) rank = lane;   // NaN compares false everywhere: keep slots distinct
     out[rank] = v;
   }
+  __syncwarp();
   return __all_sync(0xffffffffu, finite);
 }
 
@@ -369,6 +390,7 @@ __device__ __forceinline__ void jne_warp_stitch(const double* VV, const double* 
 template <int DP>
 __device__ __forceinline__ void jne_warp_assemble(const double* MBB, const double* MBZ, const double* tot,
                                                   double* S2, double* R, const JneRunParams& prm, int model, int p) {
+  constexpr int LDW = JneGeo<DP>::LDW;
   const int lane = threadIdx.x & 31;
   const int d = prm.dim;
   const double T = prm.T;
@@ -421,16 +443,72 @@ __device__ __forceinline__ void jne_warp_assemble(const double* MBB, const doubl
   for (int q = 0; q < NQ; ++q) {
     const int i = 2 * q + (lane >> 4);
     if (i < nb) {
-      if (j < nb) S2[i * JNE_LD + j] = r_bb[q];
-      if (j < d) R[i * JNE_LD + j] = r_bz[q];
+      if (j < nb) S2[i * LDW + j] = r_bb[q];
+      if (j < d) R[i * LDW + j] = r_bz[q];
     }
   }
   if (p > nb && lane < 16) {
-    if (j < nb) { S2[nb * JNE_LD + j] = s2v; S2[j * JNE_LD + nb] = s2v; }
-    if (j == nb) S2[nb * JNE_LD + nb] = dg;
-    if (j < d) R[nb * JNE_LD + j] = rv;
+    if (j < nb) { S2[nb * LDW + j] = s2v; S2[j * LDW + nb] = s2v; }
+    if (j == nb) S2[nb * LDW + nb] = dg;
+    if (j < d) R[nb * LDW + j] = rv;
   }
   __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue part 3: every selected model of the run.  wsm holds the totals and the stitched moments (layout JneEpi).
+// dbg (optional): the last selected model's S2 (16 x 16) then R (16 x 16).
+// ---------------------------------------------------------------------------------------------
+template <int DP, int NM>
+__device__ __forceinline__ bool jne_warp_models(double* __restrict__ wsm, const JneRunParams& prm, double* __restrict__ out,
+                                                double* __restrict__ dbg) {
+  using G = JneGeo<DP>;
+  using E = JneEpi<DP, NM>;
+  const int lane = threadIdx.x & 31;
+  const double* tot = wsm;
+  const double* MBB = wsm + G::TOT_SZ;
+  const double* MBZ = MBB + G::STITCH_HALF;
+  double* S2 = wsm + E::OFF_S2;
+  double* R = wsm + E::OFF_R;
+  double* Gs = wsm + E::OFF_G;
+  double2* cs = reinterpret_cast<double2*>(wsm + E::OFF_CS);
+  double* ev = wsm + E::OFF_EV;
+  double* fac = wsm + E::OFF_FAC;
+  const int d = prm.dim, ne = (d + 1) & ~1, gsz = ne * (ne + 1) / 2;   // odd d: index d is an all-zero row / column
+  int nm = 0;
+#pragma unroll 1
+  for (int model = 0; model < 5; ++model) {
+    if (!((prm.model_mask >> model) & 1u)) continue;
+    const int p = (model == 1 || model == 3) ? d + 1 : d;
+    jne_warp_assemble<DP>(MBB, MBZ, tot, S2, R, prm, model, p);
+    if (dbg != nullptr) {
+      for (int e = lane; e < 256; e += 32) {
+        const int i = e >> 4, j = e & 15;
+        dbg[e] = (i < p && j < p) ? S2[i * G::LDW + j] : 0.0;
+        dbg[256 + e] = (i < p && j < d) ? R[i * G::LDW + j] : 0.0;
+      }
+      __syncwarp();
+    }
+    const double tr = jne_warp_gram<DP>(S2, R, p, d, ne, Gs + nm * gsz);
+    if (lane == 0) fac[nm] = prm.factor * tr;
+    ++nm;
+    if (NM == 1) break;
+    __syncwarp();
+  }
+  __syncwarp();
+  jne_warp_jacobi<E::NPASS_B, E::NPASS_R>(Gs, cs, prm.jtab, nm, ne, gsz);
+  bool ok = true;
+  int k = 0;
+#pragma unroll 1
+  for (int model = 0; model < 5; ++model) {
+    if (!((prm.model_mask >> model) & 1u)) continue;
+    const int p = (model == 1 || model == 3) ? d + 1 : d;
+    ok &= jne_warp_emit(Gs + k * gsz, fac[k], p, d, ne, ev, out);
+    out += p;
+    ++k;
+    if (NM == 1) break;
+  }
+  return ok;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -592,24 +670,19 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t run = (uint64_t)blockIdx.x * JNE_WARPS_PER_CTA + warp;
   if (run >= n) return;
-  double* wsm = smem + (size_t)warp * (MULTI ? G::WARP_SMEM_MULTI : G::WARP_SMEM);
+  using E = JneEpi<DP, MULTI ? 5 : 1>;
+  double* wsm = smem + (size_t)warp * E::WARP_SMEM;
   double* tot = wsm;                // whole-run totals (live through the epilogue)
   double* VV = tot + G::TOT_SZ;     // raw view
   double* vec = VV + G::VV_SZ;
   double* MBB = tot + G::TOT_SZ;    // stitched view (aliases the raw view, see jne_warp_stitch)
   double* MBZ = MBB + G::STITCH_HALF;
-  // work view: single-model launches alias it onto the stitched view (see jne_warp_assemble); multi-model
-  // launches keep the stitched moments live for the next model and place it behind them
-  double* S2 = MULTI ? MBZ + G::STITCH_HALF : MBB;
-  double* R = S2 + G::MAT_SZ;
-  double* misc = R + G::MAT_SZ;
 
   const int g = lane >> 2, k = lane & 3;
   const uint32_t d = prm.dim, T = prm.steps;
   const uint32_t t_begin = min((uint32_t)k * prm.seg_len, T);
   const uint32_t t_end = min(T, t_begin + prm.seg_len);
   const jne_keys keys = jne_make_keys(SRC_RNG ? seeds[run] : 0u, reinterpret_cast<volatile uint32_t*>(wsm));
-  const unsigned char* sched_src = prm.sched;
   const double* dBrun = SRC_RNG ? nullptr : dB + run * (uint64_t)d * T;
   float rowscale[G::NRT];
 #pragma unroll
@@ -681,32 +754,12 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
     }
   }
   __syncwarp();
-  // ---- per model: assemble (Schur complements for the deterministic terms) and solve ----
+  // ---- stitch once, then per model: assemble + reduce to the Gram matrix; one Jacobi for all; emit ----
   // One Brownian path serves every selected model: the reference draws the path from (dim, steps, seed)
   // only (src/rng_matrix.rs:11) and its CLI loops the models over the same seeds (src/main.rs:109).
   jne_warp_stitch<DP>(VV, vec, tot, MBB, MBZ, prm);
-  bool ok = true;
-  uint32_t off = 0;
-#pragma unroll 1
-  for (int model = 0; model < 5; ++model) {
-    if (!((prm.model_mask >> model) & 1u)) continue;
-    const int p = (model == 1 || model == 3) ? (int)d + 1 : (int)d;
-    jne_warp_assemble<DP>(MBB, MBZ, tot, S2, R, prm, model, p);
-    if (dbg != nullptr) {
-      double* o = dbg + run * 512;
-      for (int e = lane; e < 256; e += 32) {
-        const int i = e >> 4, j = e & 15;
-        o[e] = (i < p && j < p) ? S2[i * JNE_LD + j] : 0.0;
-        o[256 + e] = (i < p && j < (int)d) ? R[i * JNE_LD + j] : 0.0;
-      }
-      __syncwarp();
-    }
-    ok &= jne_warp_pencil_solve(S2, R, misc, p, d, prm.factor, out + run * prm.out_stride + off,
-                                off == 0 ? sched_src : nullptr);
-    off += p;
-    if (!MULTI) break;
-    __syncwarp();
-  }
+  const bool ok = jne_warp_models<DP, MULTI ? 5 : 1>(wsm, prm, out + run * prm.out_stride,
+                                                     dbg != nullptr ? dbg + run * 512 : nullptr);
   if (!ok && lane == 0) atomicAdd(err_count, 1u);
 }
 
@@ -719,18 +772,25 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
 __global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA)
 jne_pencil_kernel(const double* __restrict__ S1, const double* __restrict__ S2in, uint64_t n, int p, int d,
                   double factor, double* __restrict__ out, unsigned int* __restrict__ err_count,
-                  const unsigned char* __restrict__ sched) {
+                  const uint32_t* __restrict__ jtab) {
+  using G = JneGeo<16>;
+  using E = JneEpi<16, 1>;
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t run = (uint64_t)blockIdx.x * JNE_WARPS_PER_CTA + warp;
   if (run >= n) return;
-  double* S2 = smem + (size_t)warp * (2 * 16 * JNE_LD + 96);
-  double* R = S2 + 16 * JNE_LD;
-  double* misc = R + 16 * JNE_LD;
-  for (int e = lane; e < p * p; e += 32) S2[(e / p) * JNE_LD + (e % p)] = S2in[run * p * p + e];
-  for (int e = lane; e < p * d; e += 32) R[(e / d) * JNE_LD + (e % d)] = S1[run * p * d + e];
+  double* wsm = smem + (size_t)warp * E::END;
+  double* S2 = wsm + E::OFF_S2;
+  double* R = wsm + E::OFF_R;
+  double* Gm = wsm + E::OFF_G;
+  for (int e = lane; e < p * p; e += 32) S2[(e / p) * G::LDW + (e % p)] = S2in[run * p * p + e];
+  for (int e = lane; e < p * d; e += 32) R[(e / d) * G::LDW + (e % d)] = S1[run * p * d + e];
   __syncwarp();
-  const bool ok = jne_warp_pencil_solve(S2, R, misc, p, d, factor, out + run * p, sched);
+  const int ne = (d + 1) & ~1;
+  const double tr = jne_warp_gram<16>(S2, R, p, d, ne, Gm);
+  __syncwarp();
+  jne_warp_jacobi<E::NPASS_B, E::NPASS_R>(Gm, reinterpret_cast<double2*>(wsm + E::OFF_CS), jtab, 1, ne, ne * (ne + 1) / 2);
+  const bool ok = jne_warp_emit(Gm, factor * tr, p, d, ne, wsm + E::OFF_EV, out + run * p);
   if (!ok && lane == 0) atomicAdd(err_count, 1u);
 }
 

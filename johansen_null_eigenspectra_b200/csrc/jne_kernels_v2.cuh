@@ -258,18 +258,15 @@ __global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA)
 jne_solve_kernel(const double* __restrict__ mom, uint64_t n, JneRunParams prm, double* __restrict__ out,
                  unsigned int* __restrict__ err_count, double* __restrict__ dbg) {
   using G = JneGeo<12>;
+  using E = JneEpi<12, MULTI ? 5 : 1>;
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t run = (uint64_t)blockIdx.x * JNE_WARPS_PER_CTA + warp;
   if (run >= n) return;
-  constexpr int WS = G::TOT_SZ + G::STITCH_SZ + (MULTI ? G::WORK_SZ : (G::WORK_SZ > G::STITCH_SZ ? G::WORK_SZ - G::STITCH_SZ : 0));
-  double* wsm = smem + (size_t)warp * WS;
+  double* wsm = smem + (size_t)warp * E::END;
   double* tot = wsm;
   double* MBB = tot + G::TOT_SZ;
   double* MBZ = MBB + G::STITCH_HALF;
-  double* S2 = MULTI ? MBZ + G::STITCH_HALF : MBB;
-  double* R = S2 + G::MAT_SZ;
-  double* misc = R + G::MAT_SZ;
   const int d = prm.dim;
   const double* M = mom + run * (uint64_t)JNE_MOM_DOUBLES;
   for (int e = lane; e < G::STITCH_HALF; e += 32) {   // 12 rows x 16 columns of each 16 x 16 global array
@@ -279,33 +276,11 @@ jne_solve_kernel(const double* __restrict__ mom, uint64_t n, JneRunParams prm, d
   }
   for (int e = lane; e < 96; e += 32) tot[e] = ((e & 15) < d) ? M[512 + e] : 0.0;
   __syncwarp();
-  bool ok = true;
-  uint32_t off = 0;
-#pragma unroll 1
-  for (int model = 0; model < 5; ++model) {
-    if (!((prm.model_mask >> model) & 1u)) continue;
-    const int p = (model == 1 || model == 3) ? d + 1 : d;
-    jne_warp_assemble<12>(MBB, MBZ, tot, S2, R, prm, model, p);
-    if (dbg != nullptr) {
-      double* o = dbg + run * 512;
-      for (int e = lane; e < 256; e += 32) {
-        const int i = e >> 4, j = e & 15;
-        o[e] = (i < p && j < p) ? S2[i * JNE_LD + j] : 0.0;
-        o[256 + e] = (i < p && j < d) ? R[i * JNE_LD + j] : 0.0;
-      }
-      __syncwarp();
-    }
-    ok &= jne_warp_pencil_solve(S2, R, misc, p, d, prm.factor, out + run * prm.out_stride + off,
-                                off == 0 ? prm.sched : nullptr);
-    off += p;
-    if (!MULTI) break;
-    __syncwarp();
-  }
+  const bool ok = jne_warp_models<12, MULTI ? 5 : 1>(wsm, prm, out + run * prm.out_stride,
+                                                     dbg != nullptr ? dbg + run * 512 : nullptr);
   if (!ok && lane == 0) atomicAdd(err_count, 1u);
 }
 
 template <bool MULTI> constexpr size_t jne_solve_smem() {
-  using G = JneGeo<12>;
-  return (size_t)JNE_WARPS_PER_CTA * sizeof(double) *
-         (G::TOT_SZ + G::STITCH_SZ + (MULTI ? G::WORK_SZ : (G::WORK_SZ > G::STITCH_SZ ? G::WORK_SZ - G::STITCH_SZ : 0)));
+  return (size_t)JNE_WARPS_PER_CTA * sizeof(double) * JneEpi<12, MULTI ? 5 : 1>::END;
 }
