@@ -148,9 +148,31 @@ __device__ __forceinline__ int jne_tri(int i, int j, int ne) { return i * ne - (
 // noise for it).  G is zero-padded to ne x ne (ne even), scaled to unit trace (makes the solve invariant to
 // the scale of the caller's increments and keeps the FP32-seeded reciprocals of the Jacobi in range) and
 // written as a packed upper triangle; the trace is returned on every lane.
+// unit-trace packed store of the lane-distributed accumulators; returns the trace on every lane
+template <int NQ>
+__device__ __forceinline__ double jne_gram_store(const double (&acc)[NQ], int ne, double* __restrict__ Gm) {
+  const int lane = threadIdx.x & 31, x = lane & 15, h = lane >> 4;
+  double tr = 0.0;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+    if (2 * q + h == x) tr += acc[q];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
+  const double inv_tr = 1.0 / tr;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int i = 2 * q + h;
+    if (i < ne && x <= i) Gm[jne_tri(x, i, ne)] = acc[q] * inv_tr;
+  }
+  return tr;
+}
+
+// snap_at > 0: after snap_at pivots the Gram matrix of the leading snap_at rows of F is also stored (Gsnap, its trace
+// to *tr_snap): the elimination of a model whose F extends another model's F by trailing rows serves both.
 template <int DP>
 __device__ __forceinline__ double jne_warp_gram(double* __restrict__ S2, double* __restrict__ R, int p, int d, int ne,
-                                                double* __restrict__ Gm) {
+                                                double* __restrict__ Gm, int snap_at = -1,
+                                                double* __restrict__ Gsnap = nullptr, double* tr_snap = nullptr) {
   constexpr int LDW = JneGeo<DP>::LDW, NQ = (DP + 1) / 2;
   const int lane = threadIdx.x & 31, x = lane & 15, h = lane >> 4;
   const bool row_s = x < p, col_r = x < d;
@@ -175,21 +197,13 @@ __device__ __forceinline__ double jne_warp_gram(double* __restrict__ S2, double*
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
       if (2 * q < d) acc[q] = fma(__shfl_sync(0xffffffffu, v, 16 + ((2 * q + h) & 15)), wjx, acc[q]);
+    if (j + 1 == snap_at) {
+      const double trs = jne_gram_store<NQ>(acc, ne, Gsnap);
+      if (lane == 0) *tr_snap = trs;
+    }
     __syncwarp();
   }
-  double tr = 0.0;
-#pragma unroll
-  for (int q = 0; q < NQ; ++q)
-    if (2 * q + h == x) tr += acc[q];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
-  const double inv_tr = 1.0 / tr;
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    const int i = 2 * q + h;
-    if (i < ne && x <= i) Gm[jne_tri(x, i, ne)] = acc[q] * inv_tr;
-  }
-  return tr;
+  return jne_gram_store<NQ>(acc, ne, Gm);
 }
 
 // Cyclic Jacobi on nm packed matrices Gs[m * gsz ..] at once.  Step table (per step: npairs rotation words, then
@@ -384,8 +398,10 @@ __device__ __forceinline__ void jne_warp_stitch(const double* VV, const double* 
 // moments, with demeaning / detrending as Schur complements.  F per model follows
 // src/johansen_statistics.rs:102-197.  Row scalings of F leave the pencil's
 // eigenvalues unchanged, so the trend row is carried as (w1+1)/T (= 2 (tau - 1/2)) and the detrended
-// tau^2 row as w2/T^2 (= 12 x its residual on [1, tau]).  ALIASED: S2 / R may overlap MBB / MBZ
-// (single-model launches); entries pass through registers and a warp barrier.
+// tau^2 row as w2/T^2 (= 12 x its residual on [1, tau]).  Row ORDER does not change them either (G = R'S2^-1 R is
+// invariant under any invertible map of F's rows): model 3 is laid out as [B_0 .. B_{d-2}, trend, B_{d-1}] so that
+// its first d rows are exactly model 2's F and one elimination serves both (jne_warp_models).  ALIASED: S2 / R may
+// overlap MBB / MBZ (single-model launches); entries pass through registers and a warp barrier.
 // ---------------------------------------------------------------------------------------------
 template <int DP>
 __device__ __forceinline__ void jne_warp_assemble(const double* MBB, const double* MBZ, const double* tot,
@@ -395,6 +411,7 @@ __device__ __forceinline__ void jne_warp_assemble(const double* MBB, const doubl
   const int d = prm.dim;
   const double T = prm.T;
   const int nb = (model == 2 || model == 4) ? d - 1 : d;   // Brownian rows kept in F
+  const int rdet = (model == 3) ? d - 1 : nb;              // position of the deterministic row
   const double invT = 1.0 / T;
   const double nu = T * (T * T - 1.0) / 3.0;               // sum w1^2
   const double inv_nu = 1.0 / nu;                          // inf at T = 1 (model 4 needs T >= 3)
@@ -421,7 +438,7 @@ __device__ __forceinline__ void jne_warp_assemble(const double* MBB, const doubl
     r_bb[q] = mbb;
     r_bz[q] = mbz;
   }
-  // --- deterministic row (index nb), lanes 0..15 ---
+  // --- deterministic row (position rdet), lanes 0..15 ---
   double s2v = 0.0, rv = 0.0, dg = 0.0;
   if (p > nb && lane < 16) {
     if (model == 1) {                 // constant row  :108-113
@@ -439,18 +456,20 @@ __device__ __forceinline__ void jne_warp_assemble(const double* MBB, const doubl
     }
   }
   __syncwarp();   // all reads of the stitched moments are done: S2 / R may overwrite them (single-model)
+  const int jp = (j >= rdet && j < nb) ? j + 1 : j;        // position of Brownian row j (model 3: B_{d-1} sits behind the trend)
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const int i = 2 * q + (lane >> 4);
     if (i < nb) {
-      if (j < nb) S2[i * LDW + j] = r_bb[q];
-      if (j < d) R[i * LDW + j] = r_bz[q];
+      const int ip = (i >= rdet) ? i + 1 : i;
+      if (j < nb) S2[ip * LDW + jp] = r_bb[q];
+      if (j < d) R[ip * LDW + j] = r_bz[q];
     }
   }
   if (p > nb && lane < 16) {
-    if (j < nb) { S2[nb * LDW + j] = s2v; S2[j * LDW + nb] = s2v; }
-    if (j == nb) S2[nb * LDW + nb] = dg;
-    if (j < d) R[nb * LDW + j] = rv;
+    if (j < nb) { S2[rdet * LDW + jp] = s2v; S2[jp * LDW + rdet] = s2v; }
+    if (j == nb) S2[rdet * LDW + rdet] = dg;
+    if (j < d) R[rdet * LDW + j] = rv;
   }
   __syncwarp();
 }
@@ -473,37 +492,48 @@ __device__ __forceinline__ bool jne_warp_models(double* __restrict__ wsm, const 
   double* Gs = wsm + E::OFF_G;
   double2* cs = reinterpret_cast<double2*>(wsm + E::OFF_CS);
   double* ev = wsm + E::OFF_EV;
-  double* fac = wsm + E::OFF_FAC;
+  double* fac = wsm + E::OFF_FAC;    // per slot: trace of G (x prm.factor at emit)
   const int d = prm.dim, ne = (d + 1) & ~1, gsz = ne * (ne + 1) / 2;   // odd d: index d is an all-zero row / column
-  int nm = 0;
+  const uint32_t mask = prm.model_mask;
+  // Three eliminations serve the five models: F of model 1 is F of model 0 plus the constant row, F of model 3
+  // (in the row order of jne_warp_assemble) is F of model 2 plus B_{d-1}; the shorter model's Gram matrix is the
+  // snapshot after its own d pivots -- bit for bit what its own elimination produces.  Slots are in model order.
 #pragma unroll 1
-  for (int model = 0; model < 5; ++model) {
-    if (!((prm.model_mask >> model) & 1u)) continue;
+  for (int c = 0; c < 3; ++c) {
+    const uint32_t bits = (mask >> (2 * c)) & (c < 2 ? 3u : 1u);
+    if (bits == 0u) continue;
+    const int model = (bits & 2u) ? 2 * c + 1 : 2 * c;
     const int p = (model == 1 || model == 3) ? d + 1 : d;
+    const int slot_lo = __popc(mask & ((1u << (2 * c)) - 1u));
     jne_warp_assemble<DP>(MBB, MBZ, tot, S2, R, prm, model, p);
-    if (dbg != nullptr) {
+    if (NM == 1 && dbg != nullptr) {   // reference row order: model 3 carries its trend row last (:152-160)
+      const int rdet = (model == 3) ? d - 1 : p;
       for (int e = lane; e < 256; e += 32) {
         const int i = e >> 4, j = e & 15;
-        dbg[e] = (i < p && j < p) ? S2[i * G::LDW + j] : 0.0;
-        dbg[256 + e] = (i < p && j < d) ? R[i * G::LDW + j] : 0.0;
+        const int ip = (model != 3 || i < rdet) ? i : (i == d ? rdet : i + 1);
+        const int jp = (model != 3 || j < rdet) ? j : (j == d ? rdet : j + 1);
+        dbg[e] = (i < p && j < p) ? S2[ip * G::LDW + jp] : 0.0;
+        dbg[256 + e] = (i < p && j < d) ? R[ip * G::LDW + j] : 0.0;
       }
       __syncwarp();
     }
-    const double tr = jne_warp_gram<DP>(S2, R, p, d, ne, Gs + nm * gsz);
-    if (lane == 0) fac[nm] = prm.factor * tr;
-    ++nm;
+    const bool both = bits == 3u;
+    const double tr = jne_warp_gram<DP>(S2, R, p, d, ne, Gs + (slot_lo + (both ? 1 : 0)) * gsz, both ? d : -1,
+                                        Gs + slot_lo * gsz, fac + slot_lo);
+    if (lane == 0) fac[slot_lo + (both ? 1 : 0)] = tr;
     if (NM == 1) break;
     __syncwarp();
   }
   __syncwarp();
+  const int nm = __popc(mask);
   jne_warp_jacobi<E::NPASS_B, E::NPASS_R>(Gs, cs, prm.jtab, nm, ne, gsz);
   bool ok = true;
   int k = 0;
 #pragma unroll 1
   for (int model = 0; model < 5; ++model) {
-    if (!((prm.model_mask >> model) & 1u)) continue;
+    if (!((mask >> model) & 1u)) continue;
     const int p = (model == 1 || model == 3) ? d + 1 : d;
-    ok &= jne_warp_emit(Gs + k * gsz, fac[k], p, d, ne, ev, out);
+    ok &= jne_warp_emit(Gs + k * gsz, prm.factor * fac[k], p, d, ne, ev, out);
     out += p;
     ++k;
     if (NM == 1) break;
