@@ -5,7 +5,7 @@
 //                                              dmatrix_cumsum RowWise            src/matrix_utils.rs:51-63,
 //                                              construct_f_matrix                src/johansen_statistics.rs:102-197,
 //                                              2 x sum_of_outer_products         src/matrix_utils.rs:67-85
-//   K3  jne_warp_pencil_solve                  replaces GeneralizedEigen::new + |alpha|/beta + sort
+//   K3  jne_warp_gram / _jacobi / _emit        replaces GeneralizedEigen::new + |alpha|/beta + sort
 //                                                                                src/johansen_statistics.rs:35-46
 //
 // One warp owns one run.  Lane (g = lane>>2, k = lane&3) owns Brownian rows g, g+8 of time
@@ -23,7 +23,9 @@
 #include "jne_rng.cuh"
 
 #define JNE_MAX_DIM 15           // p = dim+1 <= 16: one half-warp covers a row / column of the work matrices
+#ifndef JNE_WARPS_PER_CTA
 #define JNE_WARPS_PER_CTA 4
+#endif
 
 struct JneRunParams {
   uint32_t dim;        // d
@@ -169,7 +171,7 @@ __device__ __forceinline__ double jne_gram_store(const double (&acc)[NQ], int ne
 
 // snap_at > 0: after snap_at pivots the Gram matrix of the leading snap_at rows of F is also stored (Gsnap, its trace
 // to *tr_snap): the elimination of a model whose F extends another model's F by trailing rows serves both.
-template <int DP>
+template <int DP, bool SNAP = false>
 __device__ __forceinline__ double jne_warp_gram(double* __restrict__ S2, double* __restrict__ R, int p, int d, int ne,
                                                 double* __restrict__ Gm, int snap_at = -1,
                                                 double* __restrict__ Gsnap = nullptr, double* tr_snap = nullptr) {
@@ -197,7 +199,7 @@ __device__ __forceinline__ double jne_warp_gram(double* __restrict__ S2, double*
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
       if (2 * q < d) acc[q] = fma(__shfl_sync(0xffffffffu, v, 16 + ((2 * q + h) & 15)), wjx, acc[q]);
-    if (j + 1 == snap_at) {
+    if (SNAP && j + 1 == snap_at) {
       const double trs = jne_gram_store<NQ>(acc, ne, Gsnap);
       if (lane == 0) *tr_snap = trs;
     }
@@ -518,7 +520,7 @@ __device__ __forceinline__ bool jne_warp_models(double* __restrict__ wsm, const 
       __syncwarp();
     }
     const bool both = bits == 3u;
-    const double tr = jne_warp_gram<DP>(S2, R, p, d, ne, Gs + (slot_lo + (both ? 1 : 0)) * gsz, both ? d : -1,
+    const double tr = jne_warp_gram<DP, (NM > 1)>(S2, R, p, d, ne, Gs + (slot_lo + (both ? 1 : 0)) * gsz, both ? d : -1,
                                         Gs + slot_lo * gsz, fac + slot_lo);
     if (lane == 0) fac[slot_lo + (both ? 1 : 0)] = tr;
     if (NM == 1) break;
@@ -594,90 +596,119 @@ __device__ __forceinline__ void jne_gen8(uint32_t t, uint32_t t_end, uint32_t d,
   }
 }
 
+// State of a run's time loop carried from block to block.
+template <int DP> struct JneLoopState {
+  using G = JneGeo<DP>;
+  double c[G::NRT], s0[G::NRT], s1[G::NRT], s2[G::NRT];
+  double acc[G::NT][2];
+  double w1;
+};
+// Per-block trend sums (see jne_consume8).
+template <int DP> struct JneBlockSums { double bA[JneGeo<DP>::NRT], bB[JneGeo<DP>::NRT], bQ[JneGeo<DP>::NRT]; };
+
+// One step s of a block: path update, operand exchange, the tile MMAs, the block-local trend sums.
 // MASKED blocks (only the ragged tail of the last segment, or tiny T) zero the contributions of
 // steps at or beyond t_end.
-template <int DP, int DET, bool SRC_RNG, bool MASKED>
-__device__ __forceinline__ void jne_consume8(uint32_t t, uint32_t t_end, int g, int src_lane,
-                                             const typename JneZ<DP, SRC_RNG>::type (&z)[JneGeo<DP>::NRT][8],
-                                             double (&c)[JneGeo<DP>::NRT], double (&s0)[JneGeo<DP>::NRT],
-                                             double (&s1)[JneGeo<DP>::NRT], double (&s2)[JneGeo<DP>::NRT],
-                                             double (&acc)[JneGeo<DP>::NT][2], double& w1, double w2c) {
+template <int DP, int DET, bool SRC_RNG, bool MASKED, int S>
+__device__ __forceinline__ void jne_step(uint32_t t, uint32_t t_end, int g, int src_lane,
+                                         const typename JneZ<DP, SRC_RNG>::type (&z)[JneGeo<DP>::NRT][8],
+                                         JneLoopState<DP>& L, JneBlockSums<DP>& bs) {
   using G = JneGeo<DP>;
-  // Trend moments per 8-step block.  With w1_s = w1 + 2s and w2_s = 3 w1_s^2 + w2c = w2 + 12 w1 s + 12 s^2:
-  //   sum_s w1_s f_s = w1 A + 2 B,   sum_s w2_s f_s = w2 A + 12 w1 B + 12 Q,   A = sum f_s, B = sum s f_s, Q = sum s^2 f_s
-  // so the per-step work is one add and one or two FMAs with small exact multipliers, and the weights are
-  // touched once per block instead of three FP64 operations per lane and step.
-  double bA[G::NRT], bB[G::NRT], bQ[G::NRT];
+  constexpr int s = S;
+  const bool active = !MASKED || (t + s) < t_end;
+  double f[G::NRT], dz[G::NRT], cn[G::NRT];
 #pragma unroll
-  for (int j = 0; j < G::NRT; ++j) { bA[j] = 0.0; bB[j] = 0.0; bQ[j] = 0.0; }
-#pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    const bool active = !MASKED || (t + s) < t_end;
-    double f[G::NRT], dz[G::NRT], cn[G::NRT];
-#pragma unroll
-    for (int j = 0; j < G::NRT; ++j) {
-      f[j] = active ? c[j] : 0.0;
-      dz[j] = active ? (double)z[j][s] : 0.0;
-      cn[j] = c[j] + dz[j];                  // B_t = B_{t-1} + dB_t   (src/matrix_utils.rs:51-63)
-      if (!SRC_RNG) dz[j] = cn[j] - c[j];    // dB re-derived by subtraction (src/johansen_statistics.rs:80-82)
-    }
-    // V tiles: index i = 8*jt + g;  i < DP -> F_i (own);  DP <= i < 2DP -> dB_{i-DP}, owned by lane
-    // g' = (g - B) & 7 in its slot jt-A (receivers g >= B) or jt-A-1 (receivers g < B).  Every lane
-    // publishes each of its increments once; the receiver picks.
-    double recv[G::NRT];
-#pragma unroll
-    for (int m = 0; m < G::NRT; ++m) recv[m] = (G::B == 0) ? dz[m] : __shfl_sync(0xffffffffu, dz[m], src_lane);
-    double V[G::NCT];
-#pragma unroll
-    for (int jt = 0; jt < G::NCT; ++jt) {
-      const int i = 8 * jt + g;
-      const int ja = jt - G::A, jb = jt - G::A - 1;
-      const double ra = (ja >= 0 && ja < G::NRT) ? recv[(ja >= 0 && ja < G::NRT) ? ja : 0] : 0.0;
-      const double rb = (jb >= 0 && jb < G::NRT) ? recv[(jb >= 0 && jb < G::NRT) ? jb : 0] : 0.0;
-      const double r = (G::B == 0 || g >= G::B) ? ra : rb;
-      const double own = (jt < G::NRT) ? f[jt < G::NRT ? jt : 0] : 0.0;
-      V[jt] = (i < DP) ? own : ((i < 2 * DP) ? r : 0.0);
-    }
-    int ti = 0;
-#pragma unroll
-    for (int a = 0; a < G::NRT; ++a)
-#pragma unroll
-      for (int b = a; b < G::NCT; ++b) {
-#ifdef JNE_EXP_NOMMA   // experiment only: no tensor work
-        acc[ti][0] += V[a]; acc[ti][1] += V[b];
-#else
-        jne_dmma(acc[ti][0], acc[ti][1], V[a], V[b]);
-#endif
-        ++ti;
-      }
-    // deterministic cross moments of the path (those of the increments follow by summation by parts in
-    // the epilogue: sum w z = w_last c_end - sum (w_t - w_{t-1}) c_t) and the running path
-#pragma unroll
-    for (int j = 0; j < G::NRT; ++j) {
-      bA[j] += f[j];     // every DET sums sum c the same way: records stay bit-identical across kernels
-      if (DET >= 1 && s > 0) bB[j] = fma((double)s, f[j], bB[j]);
-      if (DET >= 2 && s > 0) bQ[j] = fma((double)(s * s), f[j], bQ[j]);
-      c[j] = cn[j];
-    }
+  for (int j = 0; j < G::NRT; ++j) {
+    f[j] = active ? L.c[j] : 0.0;
+    dz[j] = active ? (double)z[j][s] : 0.0;
+    cn[j] = L.c[j] + dz[j];                  // B_t = B_{t-1} + dB_t   (src/matrix_utils.rs:51-63)
+    if (!SRC_RNG) dz[j] = cn[j] - L.c[j];    // dB re-derived by subtraction (src/johansen_statistics.rs:80-82)
   }
+  // V tiles: index i = 8*jt + g;  i < DP -> F_i (own);  DP <= i < 2DP -> dB_{i-DP}, owned by lane
+  // g' = (g - B) & 7 in its slot jt-A (receivers g >= B) or jt-A-1 (receivers g < B).  Every lane
+  // publishes each of its increments once; the receiver picks.
+  double recv[G::NRT];
+#pragma unroll
+  for (int m = 0; m < G::NRT; ++m) recv[m] = (G::B == 0) ? dz[m] : __shfl_sync(0xffffffffu, dz[m], src_lane);
+  double V[G::NCT];
+#pragma unroll
+  for (int jt = 0; jt < G::NCT; ++jt) {
+    const int i = 8 * jt + g;
+    const int ja = jt - G::A, jb = jt - G::A - 1;
+    const double ra = (ja >= 0 && ja < G::NRT) ? recv[(ja >= 0 && ja < G::NRT) ? ja : 0] : 0.0;
+    const double rb = (jb >= 0 && jb < G::NRT) ? recv[(jb >= 0 && jb < G::NRT) ? jb : 0] : 0.0;
+    const double r = (G::B == 0 || g >= G::B) ? ra : rb;
+    const double own = (jt < G::NRT) ? f[jt < G::NRT ? jt : 0] : 0.0;
+    V[jt] = (i < DP) ? own : ((i < 2 * DP) ? r : 0.0);
+  }
+  int ti = 0;
+#pragma unroll
+  for (int a = 0; a < G::NRT; ++a)
+#pragma unroll
+    for (int b = a; b < G::NCT; ++b) {
+#ifdef JNE_EXP_NOMMA   // experiment only: no tensor work
+      L.acc[ti][0] += V[a]; L.acc[ti][1] += V[b];
+#else
+      jne_dmma(L.acc[ti][0], L.acc[ti][1], V[a], V[b]);
+#endif
+      ++ti;
+    }
+  // deterministic cross moments of the path (those of the increments follow by summation by parts in
+  // the epilogue: sum w z = w_last c_end - sum (w_t - w_{t-1}) c_t) and the running path.  The first term of
+  // each block sum is assigned, not added to zero (x + 0 is not a no-op the compiler may drop).
+#pragma unroll
+  for (int j = 0; j < G::NRT; ++j) {
+    if (s == 0) bs.bA[j] = f[j]; else bs.bA[j] += f[j];   // every DET sums sum c the same way: records stay bit-identical across kernels
+    if (DET >= 1 && s == 1) bs.bB[j] = f[j];
+    if (DET >= 1 && s > 1) bs.bB[j] = fma((double)s, f[j], bs.bB[j]);
+    if (DET >= 2 && s == 1) bs.bQ[j] = f[j];
+    if (DET >= 2 && s > 1) bs.bQ[j] = fma((double)(s * s), f[j], bs.bQ[j]);
+    L.c[j] = cn[j];
+  }
+}
+
+// Trend moments per 8-step block.  With w1_s = w1 + 2s and w2_s = 3 w1_s^2 + w2c = w2 + 12 w1 s + 12 s^2:
+//   sum_s w1_s f_s = w1 A + 2 B,   sum_s w2_s f_s = w2 A + 12 w1 B + 12 Q,   A = sum f_s, B = sum s f_s, Q = sum s^2 f_s
+// so the per-step work is one add and one or two FMAs with small exact multipliers, and the weights are
+// touched once per block instead of three FP64 operations per lane and step.
+template <int DP, int DET>
+__device__ __forceinline__ void jne_block_end(JneLoopState<DP>& L, const JneBlockSums<DP>& bs, double w2c) {
+  using G = JneGeo<DP>;
   if (DET == 0) {
 #pragma unroll
-    for (int j = 0; j < G::NRT; ++j) s0[j] += bA[j];
+    for (int j = 0; j < G::NRT; ++j) L.s0[j] += bs.bA[j];
   } else {
+    const double w1 = L.w1;
     const double w2 = fma(3.0 * w1, w1, w2c), w1x12 = 12.0 * w1;
 #pragma unroll
     for (int j = 0; j < G::NRT; ++j) {
-      s0[j] += bA[j];
-      s1[j] = fma(w1, bA[j], s1[j]);
-      s1[j] = fma(2.0, bB[j], s1[j]);
+      L.s0[j] += bs.bA[j];
+      L.s1[j] = fma(w1, bs.bA[j], L.s1[j]);
+      L.s1[j] = fma(2.0, bs.bB[j], L.s1[j]);
       if (DET >= 2) {
-        s2[j] = fma(w2, bA[j], s2[j]);
-        s2[j] = fma(w1x12, bB[j], s2[j]);
-        s2[j] = fma(12.0, bQ[j], s2[j]);
+        L.s2[j] = fma(w2, bs.bA[j], L.s2[j]);
+        L.s2[j] = fma(w1x12, bs.bB[j], L.s2[j]);
+        L.s2[j] = fma(12.0, bs.bQ[j], L.s2[j]);
       }
     }
-    w1 += 16.0;
+    L.w1 += 16.0;
   }
+}
+
+template <int DP, int DET, bool SRC_RNG, bool MASKED>
+__device__ __forceinline__ void jne_consume8(uint32_t t, uint32_t t_end, int g, int src_lane,
+                                             const typename JneZ<DP, SRC_RNG>::type (&z)[JneGeo<DP>::NRT][8],
+                                             JneLoopState<DP>& L, double w2c) {
+  JneBlockSums<DP> bs;
+  jne_step<DP, DET, SRC_RNG, MASKED, 0>(t, t_end, g, src_lane, z, L, bs);
+  jne_step<DP, DET, SRC_RNG, MASKED, 1>(t, t_end, g, src_lane, z, L, bs);
+  jne_step<DP, DET, SRC_RNG, MASKED, 2>(t, t_end, g, src_lane, z, L, bs);
+  jne_step<DP, DET, SRC_RNG, MASKED, 3>(t, t_end, g, src_lane, z, L, bs);
+  jne_step<DP, DET, SRC_RNG, MASKED, 4>(t, t_end, g, src_lane, z, L, bs);
+  jne_step<DP, DET, SRC_RNG, MASKED, 5>(t, t_end, g, src_lane, z, L, bs);
+  jne_step<DP, DET, SRC_RNG, MASKED, 6>(t, t_end, g, src_lane, z, L, bs);
+  jne_step<DP, DET, SRC_RNG, MASKED, 7>(t, t_end, g, src_lane, z, L, bs);
+  jne_block_end<DP, DET>(L, bs, w2c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -690,7 +721,7 @@ __device__ __forceinline__ void jne_consume8(uint32_t t, uint32_t t_end, int g, 
 #define JNE_MULTI_MINB 5
 #endif
 template <int DP, int DET, bool SRC_RNG, bool MULTI>
-__global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA, SRC_RNG ? (MULTI ? JNE_MULTI_MINB : (DET == 0 ? 6 : 5)) : 1)
+__global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA, SRC_RNG ? (MULTI ? JNE_MULTI_MINB : (DET == 0 ? 6 : 5)) * 4 / JNE_WARPS_PER_CTA : 1)
 jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB, uint64_t n,
                JneRunParams prm, double* __restrict__ out, unsigned int* __restrict__ err_count,
                double* __restrict__ dbg /* optional: per run S2 (16x16) then R (16x16) */) {
@@ -719,15 +750,14 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   for (int j = 0; j < G::NRT; ++j) rowscale[j] = (8u * j + g < d) ? 1.0f : 0.0f;
   const float xscale = (8u * (G::NRT - 1) + (g & 3) < d) ? 1.0f : 0.0f;   // the shared row slot (DP = 4, 12)
 
-  double c[G::NRT], s0[G::NRT], s1[G::NRT], s2[G::NRT];
+  JneLoopState<DP> L;
 #pragma unroll
-  for (int j = 0; j < G::NRT; ++j) { c[j] = s0[j] = s1[j] = s2[j] = 0.0; }
-  double acc[G::NT][2];
+  for (int j = 0; j < G::NRT; ++j) { L.c[j] = L.s0[j] = L.s1[j] = L.s2[j] = 0.0; }
 #pragma unroll
-  for (int i = 0; i < G::NT; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  for (int i = 0; i < G::NT; ++i) { L.acc[i][0] = 0.0; L.acc[i][1] = 0.0; }
 
   const double w1_first = 2.0 * (double)t_begin + 1.0 - prm.T;
-  double w1 = w1_first;
+  L.w1 = w1_first;
   const double w2c = -(prm.T * prm.T - 1.0);
   const int src_lane = (((g - G::B) & 7) << 2) | k;
 
@@ -737,12 +767,17 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   const uint32_t t_full = t_begin + 8u * prm.full_blocks, t_stop = t_begin + prm.seg_len;
   for (; t < t_full; t += 8) {
     jne_gen8<DP, SRC_RNG>(t, t_end, d, g, keys, rowscale, xscale, dBrun, z);
-    jne_consume8<DP, DET, SRC_RNG, false>(t, t_end, g, src_lane, z, c, s0, s1, s2, acc, w1, w2c);
+    jne_consume8<DP, DET, SRC_RNG, false>(t, t_end, g, src_lane, z, L, w2c);
   }
   for (; t < t_stop; t += 8) {
     jne_gen8<DP, SRC_RNG>(t, t_end, d, g, keys, rowscale, xscale, dBrun, z);
-    jne_consume8<DP, DET, SRC_RNG, true>(t, t_end, g, src_lane, z, c, s0, s1, s2, acc, w1, w2c);
+    jne_consume8<DP, DET, SRC_RNG, true>(t, t_end, g, src_lane, z, L, w2c);
   }
+  double (&c)[G::NRT] = L.c;
+  double (&s0)[G::NRT] = L.s0;
+  double (&s1)[G::NRT] = L.s1;
+  double (&s2)[G::NRT] = L.s2;
+  double (&acc)[G::NT][2] = L.acc;
 
   // sum w1 z and sum w2 z over the lane's segment by summation by parts (z_t = c_{t+1} - c_t, c_0 = 0,
   // w1_t - w1_{t-1} = 2, w2_t - w2_{t-1} = 12 w1_t - 12):
