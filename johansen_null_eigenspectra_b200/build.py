@@ -10,7 +10,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libjne.so"
 SOURCES = [CSRC / "jne_api.cu", CSRC / "jne_dat.cpp", CSRC / "jne_host.cpp"]
-HEADERS = [CSRC / "jne_kernels.cuh", CSRC / "jne_kernels_v2.cuh", CSRC / "jne_rng.cuh", CSRC / "jne_host.hpp",
+HEADERS = [CSRC / "jne_kernels.cuh", CSRC / "jne_kernels_v2.cuh", CSRC / "jne_kernels_ws.cuh", CSRC / "jne_rng.cuh", CSRC / "jne_host.hpp",
            PKG_DIR.parent / "include" / "jne.h", PKG_DIR.parent / "include" / "jne_dat.h"]
 
 NVCC_FLAGS = [

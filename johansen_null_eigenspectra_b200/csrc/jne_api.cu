@@ -18,6 +18,7 @@
 #include "../../include/jne.h"
 #include "jne_kernels.cuh"
 #include "jne_kernels_v2.cuh"
+#include "jne_kernels_ws.cuh"
 
 #define JNE_VERSION_STR "jne-b200 0.1.0 (sm_100a)"
 
@@ -49,6 +50,7 @@ struct Device {
   uint32_t* d_jtab = nullptr;   // 8 Jacobi step tables (ne = 2, 4, .., 16), kTabWords words each
   double* d_mom[2] = {nullptr, nullptr};   // v2 path: per-run moments between jne_moments12_kernel and jne_solve_kernel,
   uint64_t mom_runs[2] = {0, 0};           // one buffer per concurrently used stream (capacity in runs)
+  int sm_count = 0;
   double* d_scratch = nullptr;    // increments / pencil inputs, grown on demand
   size_t scratch_bytes = 0;
 };
@@ -56,7 +58,8 @@ struct Device {
 }  // namespace
 
 struct jne_ctx {
-  int kernel_family = 1;   // 1: tensor path for every dim (default); 2: FMA-tiled path for 9 <= dim <= 12 (env JNE_KERNEL=v2)
+  int kernel_family = 1;   // 1: tensor path, one warp per run start to end; 2: FMA-tiled path for 9 <= dim <= 12 (env JNE_KERNEL=v2);
+                           // 3: tensor path with producer / consumer warps for dim <= 12 (env JNE_KERNEL=ws)
   std::vector<Device> devs;
   std::string err;
   std::mutex err_mu;
@@ -204,6 +207,30 @@ cudaError_t launch_det(int det, const uint32_t* s, const double* b, uint64_t n, 
   }
 }
 
+// warp-specialised persistent kernel (jne_kernels_ws.cuh): one CTA per SM, RNG path, dim <= 12
+template <int DP, int DET, bool MULTI>
+cudaError_t launch_ws_one(const Device& dv, const uint32_t* d_seeds, uint64_t n, const JneRunParams& prm, double* d_out,
+                          unsigned int* d_err, cudaStream_t st) {
+  using W = JneWs<DP, MULTI>;
+  auto kern = jne_run_kernel_ws<DP, DET, MULTI>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::CTA_SMEM);
+  if (e != cudaSuccess) return e;
+  const uint64_t ctas = std::min<uint64_t>((uint64_t)dv.sm_count, (n + JNE_WS_CONS - 1) / JNE_WS_CONS);
+  kern<<<(unsigned)ctas, 32 * (JNE_WS_CONS + JNE_WS_PROD), W::CTA_SMEM, st>>>(d_seeds, n, prm, d_out, d_err);
+  return cudaGetLastError();
+}
+template <int DP>
+cudaError_t launch_ws(const Device& dv, const uint32_t* s, uint64_t n, const JneRunParams& prm, double* o, unsigned int* e,
+                      cudaStream_t st) {
+  if (prm.model_mask & (prm.model_mask - 1u)) return launch_ws_one<DP, 2, true>(dv, s, n, prm, o, e, st);
+  const int det = (prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2);
+  switch (det) {
+    case 0: return launch_ws_one<DP, 0, false>(dv, s, n, prm, o, e, st);
+    case 1: return launch_ws_one<DP, 1, false>(dv, s, n, prm, o, e, st);
+    default: return launch_ws_one<DP, 2, false>(dv, s, n, prm, o, e, st);
+  }
+}
+
 constexpr uint64_t kMomChunk = 1ull << 18;   // runs per v2 moments/solve pair (1.27 GB of moments)
 
 template <int DET, bool RNG>
@@ -258,6 +285,11 @@ template <bool RNG>
 cudaError_t launch_run(jne_ctx* ctx, Device& dv, const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm,
                        double* o, unsigned int* e, double* dbg, cudaStream_t st, int mom_slot = 0) {
   if (ctx->kernel_family == 2 && prm.dim >= 9 && prm.dim <= 12) return launch_v2<RNG>(ctx, dv, s, b, n, prm, o, e, dbg, st, mom_slot);
+  if (RNG && ctx->kernel_family == 3 && prm.dim <= 12 && dbg == nullptr) {
+    if (prm.dim <= 4) return launch_ws<4>(dv, s, n, prm, o, e, st);
+    if (prm.dim <= 8) return launch_ws<8>(dv, s, n, prm, o, e, st);
+    return launch_ws<12>(dv, s, n, prm, o, e, st);
+  }
   const int det = (prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2);
   if (prm.dim <= 4) return launch_det<4, RNG>(det, s, b, n, prm, o, e, dbg, st);
   if (prm.dim <= 8) return launch_det<8, RNG>(det, s, b, n, prm, o, e, dbg, st);
@@ -485,7 +517,7 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
   if (n_devices < 0) return fail(nullptr, JNE_ERR_INVALID_ARG, "n_devices < 0");
   if (n_devices == 0) n_devices = visible;
   jne_ctx* ctx = new jne_ctx();
-  if (const char* kf = std::getenv("JNE_KERNEL")) ctx->kernel_family = (std::strcmp(kf, "v2") == 0) ? 2 : 1;
+  if (const char* kf = std::getenv("JNE_KERNEL")) ctx->kernel_family = (std::strcmp(kf, "v2") == 0) ? 2 : (std::strcmp(kf, "ws") == 0) ? 3 : 1;
   ctx->devs.resize(n_devices);
   for (int i = 0; i < n_devices; ++i) {
     Device& dv = ctx->devs[i];
@@ -501,6 +533,7 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
       JNE_CUDA(nullptr, cudaGetDeviceProperties(&prop, dv.id));
       if (prop.major != 10)
         return fail(nullptr, JNE_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100 (B200); the kernels are built for sm_100a only");
+      dv.sm_count = prop.multiProcessorCount;
       JNE_CUDA(nullptr, cudaStreamCreateWithFlags(&dv.stream, cudaStreamNonBlocking));
       for (auto& s : dv.slot) {
         JNE_CUDA(nullptr, cudaMalloc(&s.d_seeds, kChunkRuns * sizeof(uint32_t)));

@@ -658,6 +658,11 @@ __device__ __forceinline__ void jne_step(uint32_t t, uint32_t t_end, int g, int 
   // each block sum is assigned, not added to zero (x + 0 is not a no-op the compiler may drop).
 #pragma unroll
   for (int j = 0; j < G::NRT; ++j) {
+#ifdef JNE_EXP_NODET   // experiment only: no block-local trend sums
+    if (s == 0) { bs.bA[j] = f[j]; bs.bB[j] = f[j]; bs.bQ[j] = f[j]; }
+    L.c[j] = cn[j];
+    continue;
+#endif
     if (s == 0) bs.bA[j] = f[j]; else bs.bA[j] += f[j];   // every DET sums sum c the same way: records stay bit-identical across kernels
     if (DET >= 1 && s == 1) bs.bB[j] = f[j];
     if (DET >= 1 && s > 1) bs.bB[j] = fma((double)s, f[j], bs.bB[j]);
@@ -709,6 +714,60 @@ __device__ __forceinline__ void jne_consume8(uint32_t t, uint32_t t_end, int g, 
   jne_step<DP, DET, SRC_RNG, MASKED, 6>(t, t_end, g, src_lane, z, L, bs);
   jne_step<DP, DET, SRC_RNG, MASKED, 7>(t, t_end, g, src_lane, z, L, bs);
   jne_block_end<DP, DET>(L, bs, w2c);
+}
+
+// End of the time loop: the increment moments by summation by parts, then the lane-distributed raw moments go to
+// the warp's shared memory (VV, vec: the raw view read by jne_warp_stitch).
+template <int DP>
+__device__ __forceinline__ void jne_warp_dump(JneLoopState<DP>& L, double* __restrict__ VV, double* __restrict__ vec,
+                                              uint32_t t_begin, uint32_t t_end, double w1_first, double w2c, int g, int k) {
+  using G = JneGeo<DP>;
+  double (&c)[G::NRT] = L.c;
+  double (&s0)[G::NRT] = L.s0;
+  double (&s1)[G::NRT] = L.s1;
+  double (&s2)[G::NRT] = L.s2;
+  double (&acc)[G::NT][2] = L.acc;
+
+  // sum w1 z and sum w2 z over the lane's segment by summation by parts (z_t = c_{t+1} - c_t, c_0 = 0,
+  // w1_t - w1_{t-1} = 2, w2_t - w2_{t-1} = 12 w1_t - 12):
+  //   u1 = w1_last c_end - 2 sum c,      u2 = w2_last c_end - 12 sum w1 c + 12 sum c
+  double u1[G::NRT], u2[G::NRT];
+  {
+    const double nseg = (double)(t_end - t_begin);
+    const double w1_last = w1_first + 2.0 * (nseg - 1.0);
+    const double w2_last = fma(3.0 * w1_last, w1_last, w2c);
+#pragma unroll
+    for (int j = 0; j < G::NRT; ++j) {
+      const bool any = t_end > t_begin;
+      u1[j] = any ? fma(w1_last, c[j], -2.0 * s0[j]) : 0.0;
+      u2[j] = any ? fma(w2_last, c[j], 12.0 * (s0[j] - s1[j])) : 0.0;
+    }
+  }
+
+  // ---- dump raw moments to the warp's shared memory ----
+  {
+    int ti = 0;
+#pragma unroll
+    for (int a = 0; a < G::NRT; ++a)
+#pragma unroll
+      for (int b = a; b < G::NCT; ++b) {
+        VV[(8 * a + g) * G::VV_LD + 8 * b + 2 * k] = acc[ti][0];
+        VV[(8 * a + g) * G::VV_LD + 8 * b + 2 * k + 1] = acc[ti][1];
+        ++ti;
+      }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int r = 8 * j + g;
+      const bool has = j < G::NRT;
+      vec[(0 * 4 + k) * 16 + r] = has ? c[has ? j : 0] : 0.0;
+      vec[(1 * 4 + k) * 16 + r] = has ? s0[has ? j : 0] : 0.0;
+      vec[(2 * 4 + k) * 16 + r] = has ? s1[has ? j : 0] : 0.0;
+      vec[(3 * 4 + k) * 16 + r] = has ? s2[has ? j : 0] : 0.0;
+      vec[(4 * 4 + k) * 16 + r] = has ? u1[has ? j : 0] : 0.0;
+      vec[(5 * 4 + k) * 16 + r] = has ? u2[has ? j : 0] : 0.0;
+    }
+  }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -773,52 +832,7 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
     jne_gen8<DP, SRC_RNG>(t, t_end, d, g, keys, rowscale, xscale, dBrun, z);
     jne_consume8<DP, DET, SRC_RNG, true>(t, t_end, g, src_lane, z, L, w2c);
   }
-  double (&c)[G::NRT] = L.c;
-  double (&s0)[G::NRT] = L.s0;
-  double (&s1)[G::NRT] = L.s1;
-  double (&s2)[G::NRT] = L.s2;
-  double (&acc)[G::NT][2] = L.acc;
-
-  // sum w1 z and sum w2 z over the lane's segment by summation by parts (z_t = c_{t+1} - c_t, c_0 = 0,
-  // w1_t - w1_{t-1} = 2, w2_t - w2_{t-1} = 12 w1_t - 12):
-  //   u1 = w1_last c_end - 2 sum c,      u2 = w2_last c_end - 12 sum w1 c + 12 sum c
-  double u1[G::NRT], u2[G::NRT];
-  {
-    const double nseg = (double)(t_end - t_begin);
-    const double w1_last = w1_first + 2.0 * (nseg - 1.0);
-    const double w2_last = fma(3.0 * w1_last, w1_last, w2c);
-#pragma unroll
-    for (int j = 0; j < G::NRT; ++j) {
-      const bool any = t_end > t_begin;
-      u1[j] = any ? fma(w1_last, c[j], -2.0 * s0[j]) : 0.0;
-      u2[j] = any ? fma(w2_last, c[j], 12.0 * (s0[j] - s1[j])) : 0.0;
-    }
-  }
-
-  // ---- dump raw moments to the warp's shared memory ----
-  {
-    int ti = 0;
-#pragma unroll
-    for (int a = 0; a < G::NRT; ++a)
-#pragma unroll
-      for (int b = a; b < G::NCT; ++b) {
-        VV[(8 * a + g) * G::VV_LD + 8 * b + 2 * k] = acc[ti][0];
-        VV[(8 * a + g) * G::VV_LD + 8 * b + 2 * k + 1] = acc[ti][1];
-        ++ti;
-      }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int r = 8 * j + g;
-      const bool has = j < G::NRT;
-      vec[(0 * 4 + k) * 16 + r] = has ? c[has ? j : 0] : 0.0;
-      vec[(1 * 4 + k) * 16 + r] = has ? s0[has ? j : 0] : 0.0;
-      vec[(2 * 4 + k) * 16 + r] = has ? s1[has ? j : 0] : 0.0;
-      vec[(3 * 4 + k) * 16 + r] = has ? s2[has ? j : 0] : 0.0;
-      vec[(4 * 4 + k) * 16 + r] = has ? u1[has ? j : 0] : 0.0;
-      vec[(5 * 4 + k) * 16 + r] = has ? u2[has ? j : 0] : 0.0;
-    }
-  }
-  __syncwarp();
+  jne_warp_dump<DP>(L, VV, vec, t_begin, t_end, w1_first, w2c, g, k);
   // ---- stitch once, then per model: assemble + reduce to the Gram matrix; one Jacobi for all; emit ----
   // One Brownian path serves every selected model: the reference draws the path from (dim, steps, seed)
   // only (src/rng_matrix.rs:11) and its CLI loops the models over the same seeds (src/main.rs:109).
