@@ -231,6 +231,24 @@ cudaError_t launch_ws(const Device& dv, const uint32_t* s, uint64_t n, const Jne
   }
 }
 
+// Runs in one full wave of the kernel launch_run would pick for prm (resident CTAs per SM x SMs x runs per CTA):
+// the host-buffer path sizes its chunks in whole waves so that a chunk does not end on a mostly empty wave.
+template <int DP, int DET, bool MULTI>
+uint64_t wave_one(const Device& dv) {
+  auto kern = jne_run_kernel<DP, DET, true, MULTI>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem<DP, MULTI>()) != cudaSuccess) return 0;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * JNE_WARPS_PER_CTA, cta_smem<DP, MULTI>()) != cudaSuccess) return 0;
+  return (uint64_t)nb * dv.sm_count * JNE_WARPS_PER_CTA;
+}
+template <int DP>
+uint64_t wave_det(const Device& dv, const JneRunParams& prm) {
+  if (prm.model_mask & (prm.model_mask - 1u)) return wave_one<DP, 2, true>(dv);
+  const int det = (prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2);
+  return det == 0 ? wave_one<DP, 0, false>(dv) : det == 1 ? wave_one<DP, 1, false>(dv) : wave_one<DP, 2, false>(dv);
+}
+uint64_t wave_runs(const jne_ctx* ctx, const Device& dv, const JneRunParams& prm);
+
 constexpr uint64_t kMomChunk = 1ull << 18;   // runs per v2 moments/solve pair (1.27 GB of moments)
 
 template <int DET, bool RNG>
@@ -297,6 +315,14 @@ cudaError_t launch_run(jne_ctx* ctx, Device& dv, const uint32_t* s, const double
   return launch_det<16, RNG>(det, s, b, n, prm, o, e, dbg, st);
 }
 
+uint64_t wave_runs(const jne_ctx* ctx, const Device& dv, const JneRunParams& prm) {
+  if (ctx->kernel_family != 1) return 0;     // the other families have their own geometry: keep the fixed chunk
+  uint64_t w = prm.dim <= 4 ? wave_det<4>(dv, prm) : prm.dim <= 8 ? wave_det<8>(dv, prm)
+             : prm.dim <= 12 ? wave_det<12>(dv, prm) : wave_det<16>(dv, prm);
+  cudaGetLastError();
+  return w;
+}
+
 int ensure_scratch(jne_ctx* ctx, Device& dv, size_t bytes) {
   if (dv.scratch_bytes >= bytes) return JNE_OK;
   if (dv.d_scratch) { cudaFree(dv.d_scratch); dv.d_scratch = nullptr; dv.scratch_bytes = 0; }
@@ -326,11 +352,15 @@ int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32
     JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
     uint64_t done = 0;
     int which = 0;
+    // whole waves per chunk (the last wave of a launch is otherwise mostly idle SMs: 7 % at dim 12)
+    uint64_t chunk = kChunkRuns;
+    const uint64_t wave = wave_runs(ctx, dv, prm);
+    if (wave > 0 && wave <= kChunkRuns) chunk = (kChunkRuns / wave) * wave;
     while (done < n) {
       Slot& s = dv.slot[which];
       int rc = drain(ctx, s, prm.p, out);
       if (rc) return rc;
-      const uint64_t m = std::min<uint64_t>(kChunkRuns, n - done);
+      const uint64_t m = std::min<uint64_t>(chunk, n - done);
       std::memcpy(s.h_seeds, seeds + done, m * sizeof(uint32_t));
       // each slot has its own stream: the copies of one chunk and the tail wave of its kernel overlap the
       // kernel of the other slot's chunk
