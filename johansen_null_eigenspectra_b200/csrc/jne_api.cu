@@ -24,7 +24,8 @@
 
 namespace {
 
-constexpr uint64_t kChunkRuns = 1ull << 15;   // runs per launch on the host-buffer path (D2H of chunk i overlaps the kernel of chunk i+1)
+constexpr uint64_t kChunkRuns = 1ull << 15;   // capacity of a staging slot, in runs
+constexpr uint64_t kChunkTarget = 1ull << 13; // runs per launch on the host-buffer path (D2H of chunk i overlaps the kernel of chunk i+1)
 constexpr uint64_t kMaxWidth = 5 * 16;        // doubles per run: all five models at dim 15
 
 std::mutex g_init_err_mu;
@@ -352,10 +353,11 @@ int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32
     JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
     uint64_t done = 0;
     int which = 0;
-    // whole waves per chunk (the last wave of a launch is otherwise mostly idle SMs: 7 % at dim 12)
-    uint64_t chunk = kChunkRuns;
+    // Chunks are whole waves (a launch does not end on a mostly idle wave) and small (what stays exposed at the end
+    // of a call is the last chunk's D2H and the hand-over of the last two chunks to the caller's array).
+    uint64_t chunk = kChunkTarget;
     const uint64_t wave = wave_runs(ctx, dv, prm);
-    if (wave > 0 && wave <= kChunkRuns) chunk = (kChunkRuns / wave) * wave;
+    if (wave > 0 && wave <= kChunkRuns) chunk = std::max<uint64_t>(1, kChunkTarget / wave) * wave;
     while (done < n) {
       Slot& s = dv.slot[which];
       int rc = drain(ctx, s, prm.p, out);
