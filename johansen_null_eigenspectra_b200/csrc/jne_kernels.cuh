@@ -779,8 +779,13 @@ __device__ __forceinline__ void jne_warp_dump(JneLoopState<DP>& L, double* __res
 #ifndef JNE_MULTI_MINB
 #define JNE_MULTI_MINB 5
 #endif
+#ifdef JNE_MINB_OVERRIDE
+#define JNE_MINB(MULTI, DET) JNE_MINB_OVERRIDE
+#else
+#define JNE_MINB(MULTI, DET) (((MULTI) ? JNE_MULTI_MINB : ((DET) == 0 ? 6 : 5)) * 4 / JNE_WARPS_PER_CTA)
+#endif
 template <int DP, int DET, bool SRC_RNG, bool MULTI>
-__global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA, SRC_RNG ? (MULTI ? JNE_MULTI_MINB : (DET == 0 ? 6 : 5)) * 4 / JNE_WARPS_PER_CTA : 1)
+__global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA, SRC_RNG ? JNE_MINB(MULTI, DET) : 1)
 jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB, uint64_t n,
                JneRunParams prm, double* __restrict__ out, unsigned int* __restrict__ err_count,
                double* __restrict__ dbg /* optional: per run S2 (16x16) then R (16x16) */) {

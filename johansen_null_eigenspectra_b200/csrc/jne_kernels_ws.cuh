@@ -108,6 +108,13 @@ jne_run_kernel_ws(const uint32_t* __restrict__ seeds, uint64_t n, JneRunParams p
         uint64_t* full = bars + (size_t)cw * 2 * JNE_WS_SLOTS + slot;
         if (JNE_WS_EXP == 1) return;                                         // experiment: consumers only
         if (JNE_WS_EXP != 2 && !jne_mbar_poll(full + JNE_WS_SLOTS, parity)) continue;   // slot still in use: serve the next consumer
+        // First block of a further run: the ring aliases the consumer's epilogue workspace, so nothing may be written
+        // before the consumer has handed back the LAST block of its previous run (it does so after the epilogue).
+        // Runs shorter than the ring (NB < JNE_WS_SLOTS) leave free slots that the test above would let through.
+        if (JNE_WS_EXP != 2 && blk[i] == 0u && B[i] > 0u) {
+          const uint32_t Bp = B[i] - 1u;
+          if (!jne_mbar_poll(full + JNE_WS_SLOTS - slot + Bp % JNE_WS_SLOTS, (Bp / JNE_WS_SLOTS) & 1u)) continue;
+        }
         jne_keys ks;
         const uint32_t seed = seeds[run[i]];
 #pragma unroll

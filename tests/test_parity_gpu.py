@@ -338,3 +338,55 @@ def test_fma_tiled_kernel_family():
         assert worst <= 1.0, (fam, worst)
         out[fam] = np.load(path)
     assert np.allclose(out["v1"], out["v2"], rtol=1e-10, atol=1e-12 * out["v1"].max())
+
+
+def test_warp_specialised_kernel_family():
+    """JNE_KERNEL=ws selects the producer / consumer family (csrc/jne_kernels_ws.cuh) for dim <= 12.  Its generator
+    warps compute the very values the default family computes in place, so every record must be bit-identical --
+    for partial CTAs (fewer runs than consumer warps), several runs per consumer warp, ragged T, all models."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import sys, numpy as np
+        sys.path.insert(0, ".")
+        import johansen_null_eigenspectra_b200 as jne
+        eng = jne.Engine([0])
+        out = {}
+        for dim, T, n in [(1, 9, 7), (4, 37, 50), (5, 300, 3500), (8, 64, 6000), (9, 1001, 333), (12, 103, 3100), (12, 4000, 64)]:
+            seeds = np.arange(5, 5 + n, dtype=np.uint32)
+            res = eng.eigs_batch_multi(range(5), dim, T, seeds)
+            for m in range(5):
+                out[f"multi_{dim}_{T}_{m}"] = res[m]
+            for m in (0, 3, 4):
+                if m == 4 and T < 3: continue
+                out[f"single_{dim}_{T}_{m}"] = eng.eigs_batch(m, dim, T, seeds[: min(n, 500)])
+        np.savez(sys.argv[1], **out)
+    ''')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for fam in ("ws", "v1"):
+        path = f"/tmp/jne_family_{fam}.npz"
+        env = dict(os.environ, JNE_KERNEL=fam)
+        r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[fam] = np.load(path)
+    assert set(res["ws"].files) == set(res["v1"].files)
+    for k in res["v1"].files:
+        assert np.array_equal(res["ws"][k], res["v1"][k]), k
+
+
+def test_host_path_chunking_is_invisible(engine):
+    """jne_eigs_batch cuts a batch into chunks of whole kernel waves on two streams; the records must not depend on
+    it: compare with the one-launch device-pointer entry, over several chunks and a ragged last one."""
+    import torch
+    n = 20011
+    seeds = np.arange(1, n + 1, dtype=np.uint32)
+    for model, dim, T in ((2, 3, 40), (4, 12, 24)):
+        host = engine.eigs_batch(model, dim, T, seeds)
+        ds = torch.from_numpy(seeds.astype(np.int64)).to(torch.int32).cuda().contiguous()
+        do = torch.empty((n, host.shape[1]), dtype=torch.float64, device="cuda")
+        engine.eigs_batch_device(model, dim, T, ds.data_ptr(), n, do.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        engine.check_async()
+        assert np.array_equal(do.cpu().numpy(), host)
+    multi = engine.eigs_batch_multi(range(5), 6, 16, seeds)
+    for m in range(5):
+        assert np.array_equal(multi[m], engine.eigs_batch(m, 6, 16, seeds))
