@@ -166,6 +166,13 @@ uint64_t jne_launch_count(const jne_ctx* ctx);
 /* Algorithmic flops per run: 2 T [p(p+1)/2 + p d]. */
 double jne_flops_per_run(uint8_t model, uint32_t dim, uint32_t steps);
 
+/* The step table the device Jacobi walks for an ne x ne problem (ne even, 2..16): ne-1 round-robin steps, each
+ * ne/2 rotation words  o(p,p) | o(q,q) << 8 | o(p,q) << 16  followed by one word per 2x2 block of pair slots
+ * P1 <= P2,  o(p1,p2) | o(p1,q2) << 8 | o(q1,p2) << 16 | o(q1,q2) << 24,  o(i,j) = offset of element (min, max)
+ * in the packed upper triangle.  Host-only (no device needed): lets the CPU tests check the schedule.  Returns the
+ * number of words (written when it is <= capacity) or a negative error code. */
+int jne_jacobi_table(uint32_t ne, uint32_t* words, uint32_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

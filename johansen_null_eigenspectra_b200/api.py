@@ -56,6 +56,7 @@ def _load() -> C.CDLL:
         "jne_fp64_peak_tflops": (C.c_int, [vp, C.c_int, dbl, C.POINTER(dbl)]),
         "jne_launch_count": (u64, [vp]),
         "jne_flops_per_run": (dbl, [u8, u32, u32]),
+        "jne_jacobi_table": (C.c_int, [u32, vp, u32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
@@ -80,6 +81,16 @@ def num_eigs(model: int, dim: int) -> int:
 
 def flops_per_run(model: int, dim: int, steps: int) -> float:
     return float(lib.jne_flops_per_run(int(model), int(dim), int(steps)))
+
+
+def jacobi_table(ne: int) -> np.ndarray:
+    """The device Jacobi's step table for an ne x ne problem as (ne - 1, ne/2 + blocks) uint32 words (host-only)."""
+    n = lib.jne_jacobi_table(int(ne), None, 0)
+    if n < 0:
+        raise JneError(n, "jne_jacobi_table: ne must be even, 2..16")
+    words = np.empty(n, dtype=np.uint32)
+    lib.jne_jacobi_table(int(ne), words.ctypes.data, n)
+    return words.reshape(ne - 1, -1)
 
 
 class JohansenModel(enum.IntEnum):

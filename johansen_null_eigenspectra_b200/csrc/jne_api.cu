@@ -512,6 +512,18 @@ const char* jne_last_error(const jne_ctx* ctx) {
 
 uint64_t jne_launch_count(const jne_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
+int jne_jacobi_table(uint32_t ne, uint32_t* words, uint32_t capacity) {
+  if (ne < 2 || ne > 16 || (ne & 1u)) return JNE_ERR_INVALID_ARG;
+  const uint32_t np = ne / 2, n = (ne - 1) * (np + np * (np + 1) / 2);
+  if (n <= capacity) {
+    if (!words) return JNE_ERR_INVALID_ARG;
+    std::vector<uint32_t> all(8 * kTabWords);
+    make_jacobi_tables(all.data());
+    std::memcpy(words, all.data() + (np - 1) * kTabWords, n * sizeof(uint32_t));
+  }
+  return (int)n;
+}
+
 void jne_shutdown(jne_ctx* ctx) {
   if (!ctx) return;
   join_worker(ctx);

@@ -94,3 +94,49 @@ def test_shard_bounds_cover_and_disjoint():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
     s = np.concatenate([weak_scaling_seeds(5, 4, r) for r in range(4)])
     assert np.array_equal(s, np.arange(1, 21, dtype=np.uint32))
+
+
+@pytest.mark.parametrize("ne", [2, 4, 6, 8, 10, 12, 14, 16])
+def test_jacobi_step_table(ne):
+    """Host logic of K3 (make_jacobi_tables): a sweep of ne - 1 round-robin steps must rotate every pair exactly once,
+    the pairs of a step must be disjoint, and every word must address the packed upper triangle consistently."""
+    import johansen_null_eigenspectra_b200 as jne
+    tab = jne.jacobi_table(ne)
+    npair = ne // 2
+    nblk = npair * (npair + 1) // 2
+    assert tab.shape == (ne - 1, npair + nblk)
+    tri = {}
+    for i in range(ne):
+        for j in range(i, ne):
+            tri[i * ne - i * (i - 1) // 2 + (j - i)] = (i, j)
+    assert sorted(tri) == list(range(ne * (ne + 1) // 2))
+    seen = set()
+    for step in range(ne - 1):
+        pairs = []
+        for l in range(npair):
+            w = int(tab[step, l])
+            (p, p2), (q, q2), (a, b) = tri[w & 255], tri[(w >> 8) & 255], tri[(w >> 16) & 255]
+            assert p == p2 and q == q2 and (a, b) == (p, q) and p < q and w >> 24 == 0
+            pairs.append((p, q))
+        assert sorted(x for pq in pairs for x in pq) == list(range(ne))       # disjoint, everybody plays
+        assert not (set(pairs) & seen)
+        seen |= set(pairs)
+        blk = 0
+        touched = []
+        for P1 in range(npair):
+            for P2 in range(P1, npair):
+                w = int(tab[step, npair + blk]); blk += 1
+                (p1, q1), (p2, q2) = pairs[P1], pairs[P2]
+                want = [tuple(sorted(e)) for e in ((p1, p2), (p1, q2), (q1, p2), (q1, q2))]
+                got = [tri[(w >> s) & 255] for s in (0, 8, 16, 24)]
+                assert got == want
+                touched += got if P1 != P2 else [got[0], got[1], got[3]]
+        assert sorted(touched) == sorted(tri.values())      # the blocks of a step tile the whole triangle once
+    assert len(seen) == ne * (ne - 1) // 2
+
+
+def test_jacobi_table_rejects_bad_sizes():
+    import johansen_null_eigenspectra_b200 as jne
+    for ne in (0, 1, 3, 18):
+        with pytest.raises(jne.JneError):
+            jne.jacobi_table(ne)
