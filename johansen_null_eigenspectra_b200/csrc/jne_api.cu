@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -52,6 +53,8 @@ struct Device {
   double* d_mom[2] = {nullptr, nullptr};   // v2 path: per-run moments between jne_moments12_kernel and jne_solve_kernel,
   uint64_t mom_runs[2] = {0, 0};           // one buffer per concurrently used stream (capacity in runs)
   int sm_count = 0;
+  std::map<uint32_t, double*> aux_tabs;   // trend-weight tables of the AUX kernels, by steps (make_aux_table)
+  unsigned int* d_smslots[2] = {nullptr, nullptr};   // phase stagger: per-SM arrival counters, one array per stream in use
   double* d_scratch = nullptr;    // increments / pencil inputs, grown on demand
   size_t scratch_bytes = 0;
 };
@@ -59,6 +62,9 @@ struct Device {
 }  // namespace
 
 struct jne_ctx {
+  bool use_aux = true;        // trend moments through the MMA for dim <= 4 and 9..12 (env JNE_AUX=0: scalar FP64 sums)
+  std::mutex aux_mu;
+  uint32_t skew_cycles = 0;   // phase stagger of the first wave (jne_run_kernel), SM clocks per resident-CTA slot
   int kernel_family = 1;   // 1: tensor path, one warp per run start to end; 2: FMA-tiled path for 9 <= dim <= 12 (env JNE_KERNEL=v2);
                            // 3: tensor path with producer / consumer warps for dim <= 12 (env JNE_KERNEL=ws)
   std::vector<Device> devs;
@@ -110,6 +116,35 @@ void segment_weights(uint64_t a, uint64_t b, uint64_t T, double* w1, double* w2)
   const __int128 q = 1 - TT;
   const __int128 m2 = 4 * S2 + 4 * q * S1 + q * q * n;                    // sum (2i+1-T)^2
   *w2 = (double)(3 * m2 - (TT * TT - 1) * n);
+}
+
+// Trend weights fed to the MMA by the AUX kernels (jne_step): table[j][m][k] for local step j of segment k
+// (global step i = a_k + j, segment [a_k, e_k)), with w1_i = 2i + 1 - T and w2_i = 3 w1_i^2 - (T^2 - 1):
+//   m = 0: sum_{i < i' < e_k} w1_i'   (so that sum_i w1_i c_i = sum_s dB_s * weight, c = segment-local path before step i)
+//   m = 1: sum_{i < i' < e_k} w2_i'
+//   m = 2: w2_i        m = 3: w1_i
+// Integer-valued, evaluated in 128-bit integers and rounded once; steps outside the segment carry 0.
+constexpr uint32_t kAuxMaxSteps = 1u << 22;   // 128 MiB of table; longer runs use the scalar-sum kernels
+std::vector<double> make_aux_table(uint32_t steps) {
+  const uint32_t seg_len = 8u * ((steps + 31u) / 32u);
+  std::vector<double> tab((size_t)seg_len * 16, 0.0);
+  const __int128 T = steps;
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t a = std::min<uint64_t>((uint64_t)k * seg_len, steps);
+    const uint64_t e = std::min<uint64_t>(a + seg_len, steps);
+    __int128 u1 = 0, u2 = 0;
+    for (uint64_t i = e; i-- > a;) {
+      const __int128 w1 = 2 * (__int128)i + 1 - T, w2 = 3 * w1 * w1 - (T * T - 1);
+      double* row = tab.data() + (size_t)(i - a) * 16;
+      row[0 * 4 + k] = (double)u1;
+      row[1 * 4 + k] = (double)u2;
+      row[2 * 4 + k] = (double)w2;
+      row[3 * 4 + k] = (double)w1;
+      u1 += w1;
+      u2 += w2;
+    }
+  }
+  return tab;
 }
 
 uint32_t mask_width(uint32_t mask, uint32_t dim) {
@@ -185,10 +220,10 @@ template <int DP, bool MULTI> constexpr size_t cta_smem() {
 }
 constexpr size_t pencil_smem() { return (size_t)JNE_WARPS_PER_CTA * JneEpi<16, 1>::END * sizeof(double); }
 
-template <int DP, int DET, bool RNG, bool MULTI>
+template <int DP, int DET, bool RNG, bool MULTI, bool AUXT = false>
 cudaError_t launch_one(const uint32_t* d_seeds, const double* d_dB, uint64_t n, const JneRunParams& prm,
                        double* d_out, unsigned int* d_err, double* d_dbg, cudaStream_t st) {
-  auto kern = jne_run_kernel<DP, DET, RNG, MULTI>;
+  auto kern = jne_run_kernel<DP, DET, RNG, MULTI, AUXT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem<DP, MULTI>());
   if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)((n + JNE_WARPS_PER_CTA - 1) / JNE_WARPS_PER_CTA);
@@ -199,8 +234,15 @@ cudaError_t launch_one(const uint32_t* d_seeds, const double* d_dB, uint64_t n, 
 template <int DP, bool RNG>
 cudaError_t launch_det(int det, const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm, double* o,
                        unsigned int* e, double* dbg, cudaStream_t st) {
-  if (prm.model_mask & (prm.model_mask - 1u))   // more than one model: superset accumulation
-    return launch_one<DP, 2, RNG, true>(s, b, n, prm, o, e, dbg, st);
+  const bool multi = (prm.model_mask & (prm.model_mask - 1u)) != 0;   // more than one model: superset accumulation
+  if constexpr (JneGeo<DP>::B == 4) {
+    if (prm.aux_tab != nullptr && (multi || det >= 1)) {   // trend moments through the MMA
+      if (multi) return launch_one<DP, 2, RNG, true, true>(s, b, n, prm, o, e, dbg, st);
+      if (det == 1) return launch_one<DP, 1, RNG, false, true>(s, b, n, prm, o, e, dbg, st);
+      return launch_one<DP, 2, RNG, false, true>(s, b, n, prm, o, e, dbg, st);
+    }
+  }
+  if (multi) return launch_one<DP, 2, RNG, true>(s, b, n, prm, o, e, dbg, st);
   switch (det) {
     case 0: return launch_one<DP, 0, RNG, false>(s, b, n, prm, o, e, dbg, st);
     case 1: return launch_one<DP, 1, RNG, false>(s, b, n, prm, o, e, dbg, st);
@@ -234,21 +276,52 @@ cudaError_t launch_ws(const Device& dv, const uint32_t* s, uint64_t n, const Jne
 
 // Runs in one full wave of the kernel launch_run would pick for prm (resident CTAs per SM x SMs x runs per CTA):
 // the host-buffer path sizes its chunks in whole waves so that a chunk does not end on a mostly empty wave.
-template <int DP, int DET, bool MULTI>
+template <int DP, int DET, bool MULTI, bool AUXT = false>
 uint64_t wave_one(const Device& dv) {
-  auto kern = jne_run_kernel<DP, DET, true, MULTI>;
+  auto kern = jne_run_kernel<DP, DET, true, MULTI, AUXT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem<DP, MULTI>()) != cudaSuccess) return 0;
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * JNE_WARPS_PER_CTA, cta_smem<DP, MULTI>()) != cudaSuccess) return 0;
   return (uint64_t)nb * dv.sm_count * JNE_WARPS_PER_CTA;
 }
 template <int DP>
-uint64_t wave_det(const Device& dv, const JneRunParams& prm) {
-  if (prm.model_mask & (prm.model_mask - 1u)) return wave_one<DP, 2, true>(dv);
+uint64_t wave_det(const Device& dv, const JneRunParams& prm, bool aux) {
   const int det = (prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2);
+  const bool multi = (prm.model_mask & (prm.model_mask - 1u)) != 0;
+  if constexpr (JneGeo<DP>::B == 4) {
+    if (aux && det >= 1)
+      return multi ? wave_one<DP, 2, true, true>(dv) : det == 1 ? wave_one<DP, 1, false, true>(dv) : wave_one<DP, 2, false, true>(dv);
+  }
+  if (multi) return wave_one<DP, 2, true>(dv);
   return det == 0 ? wave_one<DP, 0, false>(dv) : det == 1 ? wave_one<DP, 1, false>(dv) : wave_one<DP, 2, false>(dv);
 }
 uint64_t wave_runs(const jne_ctx* ctx, const Device& dv, const JneRunParams& prm);
+
+// The AUX kernels serve dim <= 4 and 9..12 (the MMA tile layouts with four F rows and four dB rows in one group)
+// when a selected model has a trend row and the weight table fits.
+bool aux_wanted(const jne_ctx* ctx, const JneRunParams& prm) {
+  return ctx->use_aux && ctx->kernel_family == 1 && prm.model >= 2 && prm.steps <= kAuxMaxSteps &&
+         (prm.dim <= 4 || (prm.dim >= 9 && prm.dim <= 12));
+}
+// Device copy of make_aux_table(steps), built on first use; nullptr when it cannot be had (callers fall back).
+const double* aux_table_for(jne_ctx* ctx, Device& dv, uint32_t steps) {
+  std::lock_guard<std::mutex> lk(ctx->aux_mu);
+  auto it = dv.aux_tabs.find(steps);
+  if (it != dv.aux_tabs.end()) return it->second;
+  if (dv.aux_tabs.size() >= 8) {   // bounded cache: drop everything once eight horizons are resident
+    cudaDeviceSynchronize();
+    for (auto& kv : dv.aux_tabs) cudaFree(kv.second);
+    dv.aux_tabs.clear();
+  }
+  const std::vector<double> tab = make_aux_table(steps);
+  double* d = nullptr;
+  if (cudaMalloc(&d, tab.size() * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cudaMemcpy(d, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError(); cudaFree(d); return nullptr;
+  }
+  dv.aux_tabs[steps] = d;
+  return d;
+}
 
 constexpr uint64_t kMomChunk = 1ull << 18;   // runs per v2 moments/solve pair (1.27 GB of moments)
 
@@ -310,16 +383,29 @@ cudaError_t launch_run(jne_ctx* ctx, Device& dv, const uint32_t* s, const double
     return launch_ws<12>(dv, s, n, prm, o, e, st);
   }
   const int det = (prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2);
-  if (prm.dim <= 4) return launch_det<4, RNG>(det, s, b, n, prm, o, e, dbg, st);
-  if (prm.dim <= 8) return launch_det<8, RNG>(det, s, b, n, prm, o, e, dbg, st);
-  if (prm.dim <= 12) return launch_det<12, RNG>(det, s, b, n, prm, o, e, dbg, st);
-  return launch_det<16, RNG>(det, s, b, n, prm, o, e, dbg, st);
+  JneRunParams q = prm;
+  q.aux_tab = aux_wanted(ctx, prm) ? aux_table_for(ctx, dv, prm.steps) : nullptr;
+  if (RNG && ctx->skew_cycles != 0u) {
+    const uint64_t wave = wave_runs(ctx, dv, prm);
+    if (wave > 0 && n > wave) {   // more than one wave: stagger the phases of the CTAs that share an SM
+      q.sm_slots = dv.d_smslots[mom_slot];
+      q.skew_cycles = ctx->skew_cycles;
+      q.first_wave = (uint32_t)(wave / JNE_WARPS_PER_CTA);
+      cudaError_t me = cudaMemsetAsync(q.sm_slots, 0, 1024 * sizeof(unsigned int), st);
+      if (me != cudaSuccess) return me;
+    }
+  }
+  if (prm.dim <= 4) return launch_det<4, RNG>(det, s, b, n, q, o, e, dbg, st);
+  if (prm.dim <= 8) return launch_det<8, RNG>(det, s, b, n, q, o, e, dbg, st);
+  if (prm.dim <= 12) return launch_det<12, RNG>(det, s, b, n, q, o, e, dbg, st);
+  return launch_det<16, RNG>(det, s, b, n, q, o, e, dbg, st);
 }
 
 uint64_t wave_runs(const jne_ctx* ctx, const Device& dv, const JneRunParams& prm) {
   if (ctx->kernel_family != 1) return 0;     // the other families have their own geometry: keep the fixed chunk
-  uint64_t w = prm.dim <= 4 ? wave_det<4>(dv, prm) : prm.dim <= 8 ? wave_det<8>(dv, prm)
-             : prm.dim <= 12 ? wave_det<12>(dv, prm) : wave_det<16>(dv, prm);
+  const bool aux = aux_wanted(ctx, prm);
+  uint64_t w = prm.dim <= 4 ? wave_det<4>(dv, prm, aux) : prm.dim <= 8 ? wave_det<8>(dv, prm, aux)
+             : prm.dim <= 12 ? wave_det<12>(dv, prm, aux) : wave_det<16>(dv, prm, aux);
   cudaGetLastError();
   return w;
 }
@@ -539,6 +625,8 @@ void jne_shutdown(jne_ctx* ctx) {
     }
     if (dv.d_err) cudaFree(dv.d_err);
     if (dv.d_jtab) cudaFree(dv.d_jtab);
+    for (unsigned int* q : dv.d_smslots) if (q) cudaFree(q);
+    for (auto& kv : dv.aux_tabs) cudaFree(kv.second);
     for (double* m : dv.d_mom) if (m) cudaFree(m);
     if (dv.h_err) cudaFreeHost(dv.h_err);
     if (dv.d_scratch) cudaFree(dv.d_scratch);
@@ -562,6 +650,8 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
   if (n_devices == 0) n_devices = visible;
   jne_ctx* ctx = new jne_ctx();
   if (const char* kf = std::getenv("JNE_KERNEL")) ctx->kernel_family = (std::strcmp(kf, "v2") == 0) ? 2 : (std::strcmp(kf, "ws") == 0) ? 3 : 1;
+  if (const char* ax = std::getenv("JNE_AUX")) ctx->use_aux = std::strcmp(ax, "0") != 0;
+  if (const char* sk = std::getenv("JNE_SKEW_CYCLES")) ctx->skew_cycles = (uint32_t)std::strtoul(sk, nullptr, 10);
   ctx->devs.resize(n_devices);
   for (int i = 0; i < n_devices; ++i) {
     Device& dv = ctx->devs[i];
@@ -591,6 +681,7 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
       make_jacobi_tables(tables.data());
       JNE_CUDA(nullptr, cudaMalloc(&dv.d_jtab, tables.size() * sizeof(uint32_t)));
       JNE_CUDA(nullptr, cudaMemcpy(dv.d_jtab, tables.data(), tables.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      for (auto& q : dv.d_smslots) JNE_CUDA(nullptr, cudaMalloc(&q, 1024 * sizeof(unsigned int)));
       JNE_CUDA(nullptr, cudaMalloc(&dv.d_err, sizeof(unsigned int)));
       JNE_CUDA(nullptr, cudaMemset(dv.d_err, 0, sizeof(unsigned int)));
       JNE_CUDA(nullptr, cudaMallocHost(&dv.h_err, sizeof(unsigned int)));

@@ -37,6 +37,10 @@ struct JneRunParams {
   uint32_t model_mask;   // bit m set: solve model m (multi-model launches; single-model launches set one bit)
   uint32_t out_stride;   // doubles per run in `out` (sum of p over the selected models)
   const uint32_t* jtab;  // device pointer: Jacobi step table for ne = even(dim) (jne_api.cu, make_jacobi_tables)
+  const double* aux_tab;   // trend weights for the MMA (jne_step, AUX): [seg_len][4 weights][4 segments], see make_aux_table
+  unsigned int* sm_slots;  // phase stagger (see jne_run_kernel): per-SM arrival counters, zeroed before the launch
+  uint32_t skew_cycles;    // start delay per resident-CTA slot of an SM, in SM clocks; 0 = no stagger
+  uint32_t first_wave;     // CTAs resident at launch (only these are delayed)
   double T;            // (double)steps
   double factor;       // s^2 * T: 1 for the RNG path (s^2 = dt), T for caller-supplied increments
   double seg_n[4];     // steps in segment k
@@ -340,7 +344,7 @@ __device__ __forceinline__ bool jne_warp_emit(const double* __restrict__ Gm, dou
 //                        n b0 b0' + b0 (sum c)' + (sum c) b0' + sum c c'   
 // MBB / MBZ ALIAS the raw area: every entry is computed into registers, then, after a warp barrier, stored.
 // ---------------------------------------------------------------------------------------------
-template <int DP>
+template <int DP, bool AUX = false>
 __device__ __forceinline__ void jne_warp_stitch(const double* VV, const double* vec, double* tot,
                                                 double* MBB, double* MBZ, const JneRunParams& prm) {
   using G = JneGeo<DP>;
@@ -353,12 +357,24 @@ __device__ __forceinline__ void jne_warp_stitch(const double* VV, const double* 
     for (int k = 0; k < 4; ++k) {
       const double e = vec[(0 * 4 + k) * 16 + r];
       sB += vec[(1 * 4 + k) * 16 + r] + prm.seg_n[k] * b0;
-      s1B += vec[(2 * 4 + k) * 16 + r] + prm.seg_w1[k] * b0;
-      s2B += vec[(3 * 4 + k) * 16 + r] + prm.seg_w2[k] * b0;
-      s1z += vec[(4 * 4 + k) * 16 + r];
-      s2z += vec[(5 * 4 + k) * 16 + r];
+      if (AUX) {
+        s1B += prm.seg_w1[k] * b0;
+        s2B += prm.seg_w2[k] * b0;
+      } else {
+        s1B += vec[(2 * 4 + k) * 16 + r] + prm.seg_w1[k] * b0;
+        s2B += vec[(3 * 4 + k) * 16 + r] + prm.seg_w2[k] * b0;
+        s1z += vec[(4 * 4 + k) * 16 + r];
+        s2z += vec[(5 * 4 + k) * 16 + r];
+      }
       sz += e;
       b0 += e;
+    }
+    if (AUX && r < DP) {   // rows 8A+4+m of VV: sum over steps and segments of weight_m(step) * dB_r (jne_step)
+      const double* wr = VV + (8 * G::A + 4) * G::VV_LD + DP + r;
+      s1B += wr[0 * G::VV_LD];   // weight 0: sum_{i > s, same segment} w1_i  ->  sum w1_i c_i
+      s2B += wr[1 * G::VV_LD];   // weight 1: the same for w2
+      s2z = wr[2 * G::VV_LD];    // weight 2: w2_s
+      s1z = wr[3 * G::VV_LD];    // weight 3: w1_s
     }
     tot[0 * 16 + r] = sB;  tot[1 * 16 + r] = s1B; tot[2 * 16 + r] = s2B;
     tot[3 * 16 + r] = sz;  tot[4 * 16 + r] = s1z; tot[5 * 16 + r] = s2z;
@@ -609,10 +625,10 @@ template <int DP> struct JneBlockSums { double bA[JneGeo<DP>::NRT], bB[JneGeo<DP
 // One step s of a block: path update, operand exchange, the tile MMAs, the block-local trend sums.
 // MASKED blocks (only the ragged tail of the last segment, or tiny T) zero the contributions of
 // steps at or beyond t_end.
-template <int DP, int DET, bool SRC_RNG, bool MASKED, int S>
+template <int DP, int DET, bool SRC_RNG, bool MASKED, int S, bool AUX = false>
 __device__ __forceinline__ void jne_step(uint32_t t, uint32_t t_end, int g, int src_lane,
                                          const typename JneZ<DP, SRC_RNG>::type (&z)[JneGeo<DP>::NRT][8],
-                                         JneLoopState<DP>& L, JneBlockSums<DP>& bs) {
+                                         JneLoopState<DP>& L, JneBlockSums<DP>& bs, double auxv = 0.0) {
   using G = JneGeo<DP>;
   constexpr int s = S;
   const bool active = !MASKED || (t + s) < t_end;
@@ -641,6 +657,12 @@ __device__ __forceinline__ void jne_step(uint32_t t, uint32_t t_end, int g, int 
     const double own = (jt < G::NRT) ? f[jt < G::NRT ? jt : 0] : 0.0;
     V[jt] = (i < DP) ? own : ((i < 2 * DP) ? r : 0.0);
   }
+  // AUX (DP = 4, 12: the group G::A holds four F rows and four dB rows): as the A operand of its own tiles that
+  // group's dB half only produces dB x dB products nobody reads, so lanes g >= 4 put a trend weight of the step
+  // there instead and the tensor pipe delivers sum_t weight_t dB_t' for all rows in the slots it wasted before
+  // (rows 8 G::A + 4 + m of VV, m = weight index g - 4).  See make_aux_table (jne_api.cu) for the four weights.
+  double Vx = V[G::A < G::NCT ? G::A : 0];
+  if (AUX && DET >= 1) Vx = (g >= 4) ? auxv : Vx;
   int ti = 0;
 #pragma unroll
   for (int a = 0; a < G::NRT; ++a)
@@ -649,7 +671,7 @@ __device__ __forceinline__ void jne_step(uint32_t t, uint32_t t_end, int g, int 
 #ifdef JNE_EXP_NOMMA   // experiment only: no tensor work
       L.acc[ti][0] += V[a]; L.acc[ti][1] += V[b];
 #else
-      jne_dmma(L.acc[ti][0], L.acc[ti][1], V[a], V[b]);
+      jne_dmma(L.acc[ti][0], L.acc[ti][1], (AUX && a == G::A) ? Vx : V[a], V[b]);
 #endif
       ++ti;
     }
@@ -664,10 +686,12 @@ __device__ __forceinline__ void jne_step(uint32_t t, uint32_t t_end, int g, int 
     continue;
 #endif
     if (s == 0) bs.bA[j] = f[j]; else bs.bA[j] += f[j];   // every DET sums sum c the same way: records stay bit-identical across kernels
-    if (DET >= 1 && s == 1) bs.bB[j] = f[j];
-    if (DET >= 1 && s > 1) bs.bB[j] = fma((double)s, f[j], bs.bB[j]);
-    if (DET >= 2 && s == 1) bs.bQ[j] = f[j];
-    if (DET >= 2 && s > 1) bs.bQ[j] = fma((double)(s * s), f[j], bs.bQ[j]);
+    if (!AUX) {
+      if (DET >= 1 && s == 1) bs.bB[j] = f[j];
+      if (DET >= 1 && s > 1) bs.bB[j] = fma((double)s, f[j], bs.bB[j]);
+      if (DET >= 2 && s == 1) bs.bQ[j] = f[j];
+      if (DET >= 2 && s > 1) bs.bQ[j] = fma((double)(s * s), f[j], bs.bQ[j]);
+    }
     L.c[j] = cn[j];
   }
 }
@@ -676,10 +700,10 @@ __device__ __forceinline__ void jne_step(uint32_t t, uint32_t t_end, int g, int 
 //   sum_s w1_s f_s = w1 A + 2 B,   sum_s w2_s f_s = w2 A + 12 w1 B + 12 Q,   A = sum f_s, B = sum s f_s, Q = sum s^2 f_s
 // so the per-step work is one add and one or two FMAs with small exact multipliers, and the weights are
 // touched once per block instead of three FP64 operations per lane and step.
-template <int DP, int DET>
+template <int DP, int DET, bool AUX = false>
 __device__ __forceinline__ void jne_block_end(JneLoopState<DP>& L, const JneBlockSums<DP>& bs, double w2c) {
   using G = JneGeo<DP>;
-  if (DET == 0) {
+  if (DET == 0 || AUX) {
 #pragma unroll
     for (int j = 0; j < G::NRT; ++j) L.s0[j] += bs.bA[j];
   } else {
@@ -700,25 +724,29 @@ __device__ __forceinline__ void jne_block_end(JneLoopState<DP>& L, const JneBloc
   }
 }
 
-template <int DP, int DET, bool SRC_RNG, bool MASKED>
+// aux (AUX only): the lane's column of the weight table at the block's first step; a step is 16 doubles further on.
+template <int DP, int DET, bool SRC_RNG, bool MASKED, bool AUX = false>
 __device__ __forceinline__ void jne_consume8(uint32_t t, uint32_t t_end, int g, int src_lane,
                                              const typename JneZ<DP, SRC_RNG>::type (&z)[JneGeo<DP>::NRT][8],
-                                             JneLoopState<DP>& L, double w2c) {
+                                             JneLoopState<DP>& L, double w2c, const double* __restrict__ aux = nullptr) {
   JneBlockSums<DP> bs;
-  jne_step<DP, DET, SRC_RNG, MASKED, 0>(t, t_end, g, src_lane, z, L, bs);
-  jne_step<DP, DET, SRC_RNG, MASKED, 1>(t, t_end, g, src_lane, z, L, bs);
-  jne_step<DP, DET, SRC_RNG, MASKED, 2>(t, t_end, g, src_lane, z, L, bs);
-  jne_step<DP, DET, SRC_RNG, MASKED, 3>(t, t_end, g, src_lane, z, L, bs);
-  jne_step<DP, DET, SRC_RNG, MASKED, 4>(t, t_end, g, src_lane, z, L, bs);
-  jne_step<DP, DET, SRC_RNG, MASKED, 5>(t, t_end, g, src_lane, z, L, bs);
-  jne_step<DP, DET, SRC_RNG, MASKED, 6>(t, t_end, g, src_lane, z, L, bs);
-  jne_step<DP, DET, SRC_RNG, MASKED, 7>(t, t_end, g, src_lane, z, L, bs);
-  jne_block_end<DP, DET>(L, bs, w2c);
+  double av[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) av[s] = (AUX && DET >= 1) ? __ldg(aux + 16 * s) : 0.0;
+  jne_step<DP, DET, SRC_RNG, MASKED, 0, AUX>(t, t_end, g, src_lane, z, L, bs, av[0]);
+  jne_step<DP, DET, SRC_RNG, MASKED, 1, AUX>(t, t_end, g, src_lane, z, L, bs, av[1]);
+  jne_step<DP, DET, SRC_RNG, MASKED, 2, AUX>(t, t_end, g, src_lane, z, L, bs, av[2]);
+  jne_step<DP, DET, SRC_RNG, MASKED, 3, AUX>(t, t_end, g, src_lane, z, L, bs, av[3]);
+  jne_step<DP, DET, SRC_RNG, MASKED, 4, AUX>(t, t_end, g, src_lane, z, L, bs, av[4]);
+  jne_step<DP, DET, SRC_RNG, MASKED, 5, AUX>(t, t_end, g, src_lane, z, L, bs, av[5]);
+  jne_step<DP, DET, SRC_RNG, MASKED, 6, AUX>(t, t_end, g, src_lane, z, L, bs, av[6]);
+  jne_step<DP, DET, SRC_RNG, MASKED, 7, AUX>(t, t_end, g, src_lane, z, L, bs, av[7]);
+  jne_block_end<DP, DET, AUX>(L, bs, w2c);
 }
 
 // End of the time loop: the increment moments by summation by parts, then the lane-distributed raw moments go to
 // the warp's shared memory (VV, vec: the raw view read by jne_warp_stitch).
-template <int DP>
+template <int DP, bool AUX = false>
 __device__ __forceinline__ void jne_warp_dump(JneLoopState<DP>& L, double* __restrict__ VV, double* __restrict__ vec,
                                               uint32_t t_begin, uint32_t t_end, double w1_first, double w2c, int g, int k) {
   using G = JneGeo<DP>;
@@ -732,7 +760,10 @@ __device__ __forceinline__ void jne_warp_dump(JneLoopState<DP>& L, double* __res
   // w1_t - w1_{t-1} = 2, w2_t - w2_{t-1} = 12 w1_t - 12):
   //   u1 = w1_last c_end - 2 sum c,      u2 = w2_last c_end - 12 sum w1 c + 12 sum c
   double u1[G::NRT], u2[G::NRT];
-  {
+  if (AUX) {   // the trend moments come out of the MMA (jne_step); vec rows 2..5 are not read
+#pragma unroll
+    for (int j = 0; j < G::NRT; ++j) { u1[j] = 0.0; u2[j] = 0.0; }
+  } else {
     const double nseg = (double)(t_end - t_begin);
     const double w1_last = w1_first + 2.0 * (nseg - 1.0);
     const double w2_last = fma(3.0 * w1_last, w1_last, w2c);
@@ -784,16 +815,33 @@ __device__ __forceinline__ void jne_warp_dump(JneLoopState<DP>& L, double* __res
 #else
 #define JNE_MINB(MULTI, DET) (((MULTI) ? JNE_MULTI_MINB : ((DET) == 0 ? 6 : 5)) * 4 / JNE_WARPS_PER_CTA)
 #endif
-template <int DP, int DET, bool SRC_RNG, bool MULTI>
+template <int DP, int DET, bool SRC_RNG, bool MULTI, bool AUXT = false>
 __global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA, SRC_RNG ? JNE_MINB(MULTI, DET) : 1)
 jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB, uint64_t n,
                JneRunParams prm, double* __restrict__ out, unsigned int* __restrict__ err_count,
                double* __restrict__ dbg /* optional: per run S2 (16x16) then R (16x16) */) {
   using G = JneGeo<DP>;
   using ZT = typename JneZ<DP, SRC_RNG>::type;
+  constexpr bool AUX = AUXT && G::B == 4 && DET >= 1;   // trend moments through the MMA (jne_step)
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t run = (uint64_t)blockIdx.x * JNE_WARPS_PER_CTA + warp;
+  // Phase stagger.  Every CTA takes the same time, so the CTAs resident on an SM stay in lockstep from the first
+  // wave on and all of an SM sub-partition's warps reach the (issue- and latency-bound) epilogue together, where
+  // they can only overlap each other.  Delaying the first-wave CTA that arrives c-th on its SM by c * skew_cycles
+  // shifts the phases once; later CTAs inherit the phase of the CTA whose slot they take, so from then on one
+  // warp's epilogue runs under the other warps' FP64-bound time loops.
+  if (SRC_RNG && prm.skew_cycles != 0u && blockIdx.x < prm.first_wave) {
+    __shared__ unsigned int s_arrival;
+    if (threadIdx.x == 0) {
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      s_arrival = atomicAdd(prm.sm_slots + smid, 1u);
+    }
+    __syncthreads();
+    const long long until = clock64() + (long long)s_arrival * (long long)prm.skew_cycles;
+    while (clock64() < until) __nanosleep(2000);
+  }
   if (run >= n) return;
   using E = JneEpi<DP, MULTI ? 5 : 1>;
   double* wsm = smem + (size_t)warp * E::WARP_SMEM;
@@ -829,19 +877,29 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   ZT z[G::NRT][8];
   uint32_t t = t_begin;
   const uint32_t t_full = t_begin + 8u * prm.full_blocks, t_stop = t_begin + prm.seg_len;
+  // weight table: [local step][weight m][segment k]; lane (g, k) reads weight m = g & 3 (used when g >= 4)
+  const double* aux = AUX ? prm.aux_tab + (((g & 3) << 2) | k) : nullptr;
   for (; t < t_full; t += 8) {
     jne_gen8<DP, SRC_RNG>(t, t_end, d, g, keys, rowscale, xscale, dBrun, z);
-    jne_consume8<DP, DET, SRC_RNG, false>(t, t_end, g, src_lane, z, L, w2c);
+    jne_consume8<DP, DET, SRC_RNG, false, AUX>(t, t_end, g, src_lane, z, L, w2c, aux);
+    if (AUX) aux += 128;
   }
   for (; t < t_stop; t += 8) {
     jne_gen8<DP, SRC_RNG>(t, t_end, d, g, keys, rowscale, xscale, dBrun, z);
-    jne_consume8<DP, DET, SRC_RNG, true>(t, t_end, g, src_lane, z, L, w2c);
+    jne_consume8<DP, DET, SRC_RNG, true, AUX>(t, t_end, g, src_lane, z, L, w2c, aux);
+    if (AUX) aux += 128;
   }
-  jne_warp_dump<DP>(L, VV, vec, t_begin, t_end, w1_first, w2c, g, k);
+  jne_warp_dump<DP, AUX>(L, VV, vec, t_begin, t_end, w1_first, w2c, g, k);
+#ifdef JNE_EXP_NOEPI   // experiment only: time loop without the epilogue (NOT valid records)
+  { double acc0 = 0.0;
+    for (int e = lane; e < G::VV_SZ + G::VEC_SZ; e += 32) acc0 += VV[e];
+    if (lane < (int)prm.out_stride) out[run * prm.out_stride + lane] = acc0;
+    return; }
+#endif
   // ---- stitch once, then per model: assemble + reduce to the Gram matrix; one Jacobi for all; emit ----
   // One Brownian path serves every selected model: the reference draws the path from (dim, steps, seed)
   // only (src/rng_matrix.rs:11) and its CLI loops the models over the same seeds (src/main.rs:109).
-  jne_warp_stitch<DP>(VV, vec, tot, MBB, MBZ, prm);
+  jne_warp_stitch<DP, AUX>(VV, vec, tot, MBB, MBZ, prm);
   const bool ok = jne_warp_models<DP, MULTI ? 5 : 1>(wsm, prm, out + run * prm.out_stride,
                                                      dbg != nullptr ? dbg + run * 512 : nullptr);
   if (!ok && lane == 0) atomicAdd(err_count, 1u);
