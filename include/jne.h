@@ -173,6 +173,17 @@ double jne_flops_per_run(uint8_t model, uint32_t dim, uint32_t steps);
  * number of words (written when it is <= capacity) or a negative error code. */
 int jne_jacobi_table(uint32_t ne, uint32_t* words, uint32_t capacity);
 
+/* The trend-weight table the AUX kernels (dim <= 4 and 9..12, a model with a trend row) feed to the tensor pipe for a
+ * run of `steps` steps: seg_len = 8 ceil(steps / 32) local steps x 4 weights x 4 time segments, doubles,
+ * table[(j * 4 + m) * 4 + k] for local step j of segment k (global step i = k seg_len + j, segment end e_k), with
+ * w1_i = 2i + 1 - T, w2_i = 3 w1_i^2 - (T^2 - 1) (the integer forms of the reference's trend regressors
+ * (i+1)/T - 1/2 and the residual of ((i+1)/T)^2 on [1, (i+1)/T], src/johansen_statistics.rs:127-135,170-194):
+ *   m = 0: sum_{i < i' < e_k} w1_i'    m = 1: sum_{i < i' < e_k} w2_i'    m = 2: w2_i    m = 3: w1_i
+ * and 0 for steps at or beyond the end of the segment.  Host-only (no device needed): lets the CPU tests check the
+ * table against exact integer arithmetic.  Returns the number of doubles (written when it is <= capacity) or a
+ * negative error code; steps must be 1..2^22 (longer runs use the scalar-sum kernels). */
+int64_t jne_trend_weight_table(uint32_t steps, double* table, uint64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

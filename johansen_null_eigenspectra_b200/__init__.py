@@ -28,11 +28,12 @@ from .api import (  # noqa: F401
     num_eigs,
     flops_per_run,
     jacobi_table,
+    trend_weight_table,
     version,
 )
 
 __all__ = [
     "Engine", "JneError", "JohansenModel", "brownian_motion_matrix", "calculate_eigenvalues",
     "calculate_eigenvalues_parallel", "default_engine", "gen_normal_matrix", "lib", "num_eigs",
-    "flops_per_run", "jacobi_table", "version",
+    "flops_per_run", "jacobi_table", "trend_weight_table", "version",
 ]

@@ -57,6 +57,7 @@ def _load() -> C.CDLL:
         "jne_launch_count": (u64, [vp]),
         "jne_flops_per_run": (dbl, [u8, u32, u32]),
         "jne_jacobi_table": (C.c_int, [u32, vp, u32]),
+        "jne_trend_weight_table": (C.c_int64, [u32, vp, u64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
@@ -91,6 +92,17 @@ def jacobi_table(ne: int) -> np.ndarray:
     words = np.empty(n, dtype=np.uint32)
     lib.jne_jacobi_table(int(ne), words.ctypes.data, n)
     return words.reshape(ne - 1, -1)
+
+
+def trend_weight_table(steps: int) -> np.ndarray:
+    """The AUX kernels' trend-weight table for a run of `steps` steps as (seg_len, 4 weights, 4 segments) doubles
+    (host-only; see include/jne.h)."""
+    n = lib.jne_trend_weight_table(int(steps), None, 0)
+    if n < 0:
+        raise JneError(int(n), "jne_trend_weight_table: steps must be 1..2^22")
+    tab = np.empty(n, dtype=np.float64)
+    lib.jne_trend_weight_table(int(steps), tab.ctypes.data, n)
+    return tab.reshape(-1, 4, 4)
 
 
 class JohansenModel(enum.IntEnum):

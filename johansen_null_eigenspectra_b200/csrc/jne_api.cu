@@ -54,7 +54,6 @@ struct Device {
   uint64_t mom_runs[2] = {0, 0};           // one buffer per concurrently used stream (capacity in runs)
   int sm_count = 0;
   std::map<uint32_t, double*> aux_tabs;   // trend-weight tables of the AUX kernels, by steps (make_aux_table)
-  unsigned int* d_smslots[2] = {nullptr, nullptr};   // phase stagger: per-SM arrival counters, one array per stream in use
   double* d_scratch = nullptr;    // increments / pencil inputs, grown on demand
   size_t scratch_bytes = 0;
 };
@@ -64,7 +63,6 @@ struct Device {
 struct jne_ctx {
   bool use_aux = true;        // trend moments through the MMA for dim <= 4 and 9..12 (env JNE_AUX=0: scalar FP64 sums)
   std::mutex aux_mu;
-  uint32_t skew_cycles = 0;   // phase stagger of the first wave (jne_run_kernel), SM clocks per resident-CTA slot
   int kernel_family = 1;   // 1: tensor path, one warp per run start to end; 2: FMA-tiled path for 9 <= dim <= 12 (env JNE_KERNEL=v2);
                            // 3: tensor path with producer / consumer warps for dim <= 12 (env JNE_KERNEL=ws)
   std::vector<Device> devs;
@@ -385,16 +383,6 @@ cudaError_t launch_run(jne_ctx* ctx, Device& dv, const uint32_t* s, const double
   const int det = (prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2);
   JneRunParams q = prm;
   q.aux_tab = aux_wanted(ctx, prm) ? aux_table_for(ctx, dv, prm.steps) : nullptr;
-  if (RNG && ctx->skew_cycles != 0u) {
-    const uint64_t wave = wave_runs(ctx, dv, prm);
-    if (wave > 0 && n > wave) {   // more than one wave: stagger the phases of the CTAs that share an SM
-      q.sm_slots = dv.d_smslots[mom_slot];
-      q.skew_cycles = ctx->skew_cycles;
-      q.first_wave = (uint32_t)(wave / JNE_WARPS_PER_CTA);
-      cudaError_t me = cudaMemsetAsync(q.sm_slots, 0, 1024 * sizeof(unsigned int), st);
-      if (me != cudaSuccess) return me;
-    }
-  }
   if (prm.dim <= 4) return launch_det<4, RNG>(det, s, b, n, q, o, e, dbg, st);
   if (prm.dim <= 8) return launch_det<8, RNG>(det, s, b, n, q, o, e, dbg, st);
   if (prm.dim <= 12) return launch_det<12, RNG>(det, s, b, n, q, o, e, dbg, st);
@@ -610,6 +598,17 @@ int jne_jacobi_table(uint32_t ne, uint32_t* words, uint32_t capacity) {
   return (int)n;
 }
 
+int64_t jne_trend_weight_table(uint32_t steps, double* table, uint64_t capacity) {
+  if (steps < 1 || steps > kAuxMaxSteps) return JNE_ERR_INVALID_ARG;
+  const uint64_t n = (uint64_t)(8u * ((steps + 31u) / 32u)) * 16u;
+  if (n <= capacity) {
+    if (!table) return JNE_ERR_INVALID_ARG;
+    const std::vector<double> tab = make_aux_table(steps);
+    std::memcpy(table, tab.data(), n * sizeof(double));
+  }
+  return (int64_t)n;
+}
+
 void jne_shutdown(jne_ctx* ctx) {
   if (!ctx) return;
   join_worker(ctx);
@@ -625,7 +624,6 @@ void jne_shutdown(jne_ctx* ctx) {
     }
     if (dv.d_err) cudaFree(dv.d_err);
     if (dv.d_jtab) cudaFree(dv.d_jtab);
-    for (unsigned int* q : dv.d_smslots) if (q) cudaFree(q);
     for (auto& kv : dv.aux_tabs) cudaFree(kv.second);
     for (double* m : dv.d_mom) if (m) cudaFree(m);
     if (dv.h_err) cudaFreeHost(dv.h_err);
@@ -651,7 +649,6 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
   jne_ctx* ctx = new jne_ctx();
   if (const char* kf = std::getenv("JNE_KERNEL")) ctx->kernel_family = (std::strcmp(kf, "v2") == 0) ? 2 : (std::strcmp(kf, "ws") == 0) ? 3 : 1;
   if (const char* ax = std::getenv("JNE_AUX")) ctx->use_aux = std::strcmp(ax, "0") != 0;
-  if (const char* sk = std::getenv("JNE_SKEW_CYCLES")) ctx->skew_cycles = (uint32_t)std::strtoul(sk, nullptr, 10);
   ctx->devs.resize(n_devices);
   for (int i = 0; i < n_devices; ++i) {
     Device& dv = ctx->devs[i];
@@ -681,7 +678,6 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
       make_jacobi_tables(tables.data());
       JNE_CUDA(nullptr, cudaMalloc(&dv.d_jtab, tables.size() * sizeof(uint32_t)));
       JNE_CUDA(nullptr, cudaMemcpy(dv.d_jtab, tables.data(), tables.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-      for (auto& q : dv.d_smslots) JNE_CUDA(nullptr, cudaMalloc(&q, 1024 * sizeof(unsigned int)));
       JNE_CUDA(nullptr, cudaMalloc(&dv.d_err, sizeof(unsigned int)));
       JNE_CUDA(nullptr, cudaMemset(dv.d_err, 0, sizeof(unsigned int)));
       JNE_CUDA(nullptr, cudaMallocHost(&dv.h_err, sizeof(unsigned int)));

@@ -38,9 +38,6 @@ struct JneRunParams {
   uint32_t out_stride;   // doubles per run in `out` (sum of p over the selected models)
   const uint32_t* jtab;  // device pointer: Jacobi step table for ne = even(dim) (jne_api.cu, make_jacobi_tables)
   const double* aux_tab;   // trend weights for the MMA (jne_step, AUX): [seg_len][4 weights][4 segments], see make_aux_table
-  unsigned int* sm_slots;  // phase stagger (see jne_run_kernel): per-SM arrival counters, zeroed before the launch
-  uint32_t skew_cycles;    // start delay per resident-CTA slot of an SM, in SM clocks; 0 = no stagger
-  uint32_t first_wave;     // CTAs resident at launch (only these are delayed)
   double T;            // (double)steps
   double factor;       // s^2 * T: 1 for the RNG path (s^2 = dt), T for caller-supplied increments
   double seg_n[4];     // steps in segment k
@@ -826,22 +823,6 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t run = (uint64_t)blockIdx.x * JNE_WARPS_PER_CTA + warp;
-  // Phase stagger.  Every CTA takes the same time, so the CTAs resident on an SM stay in lockstep from the first
-  // wave on and all of an SM sub-partition's warps reach the (issue- and latency-bound) epilogue together, where
-  // they can only overlap each other.  Delaying the first-wave CTA that arrives c-th on its SM by c * skew_cycles
-  // shifts the phases once; later CTAs inherit the phase of the CTA whose slot they take, so from then on one
-  // warp's epilogue runs under the other warps' FP64-bound time loops.
-  if (SRC_RNG && prm.skew_cycles != 0u && blockIdx.x < prm.first_wave) {
-    __shared__ unsigned int s_arrival;
-    if (threadIdx.x == 0) {
-      unsigned int smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      s_arrival = atomicAdd(prm.sm_slots + smid, 1u);
-    }
-    __syncthreads();
-    const long long until = clock64() + (long long)s_arrival * (long long)prm.skew_cycles;
-    while (clock64() < until) __nanosleep(2000);
-  }
   if (run >= n) return;
   using E = JneEpi<DP, MULTI ? 5 : 1>;
   double* wsm = smem + (size_t)warp * E::WARP_SMEM;

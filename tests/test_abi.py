@@ -140,3 +140,43 @@ def test_jacobi_table_rejects_bad_sizes():
     for ne in (0, 1, 3, 18):
         with pytest.raises(jne.JneError):
             jne.jacobi_table(ne)
+
+
+@pytest.mark.parametrize("T", [1, 2, 7, 31, 32, 33, 100, 1000, 10000])
+def test_trend_weight_table(T):
+    """Host logic of the AUX kernels (make_aux_table): the table fed to the tensor pipe holds, per local step of each
+    of the four time segments, the exact integer tail sums of w1 / w2 and the weights themselves -- and with them
+    sum_s weight_s dB_s reproduces the trend moments of the path, sum_i w_i c_i (c = segment-local path before step i),
+    which is the identity the kernels rely on (summation by parts)."""
+    import johansen_null_eigenspectra_b200 as jne
+    tab = jne.trend_weight_table(T)
+    seg_len = 8 * ((T + 31) // 32)
+    assert tab.shape == (seg_len, 4, 4)
+    w1 = [2 * i + 1 - T for i in range(T)]
+    w2 = [3 * w * w - (T * T - 1) for w in w1]
+    rng = np.random.default_rng(T)
+    z = rng.standard_normal(T)
+    for k in range(4):
+        a, e = min(k * seg_len, T), min((k + 1) * seg_len, T)
+        for j in range(seg_len):
+            i = a + j
+            if i >= e:
+                assert not tab[j, :, k].any()
+                continue
+            want = (sum(w1[i + 1:e]), sum(w2[i + 1:e]), w2[i], w1[i])
+            for m in range(4):
+                assert tab[j, m, k] == float(want[m]), (k, j, m)
+        if e > a:
+            c = np.concatenate([[0.0], np.cumsum(z[a:e])[:-1]])       # segment-local path before each step
+            n = e - a
+            for m, w in ((0, w1), (1, w2)):
+                direct = float(np.dot(np.array(w[a:e], dtype=np.float64), c))
+                by_parts = float(np.dot(tab[:n, m, k], z[a:e]))
+                assert abs(direct - by_parts) <= 1e-11 * max(1.0, np.abs(np.array(w[a:e], dtype=np.float64)).sum())
+
+
+def test_trend_weight_table_rejects_bad_sizes():
+    import johansen_null_eigenspectra_b200 as jne
+    for T in (0, (1 << 22) + 1):
+        with pytest.raises(jne.JneError):
+            jne.trend_weight_table(T)

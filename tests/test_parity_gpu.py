@@ -149,6 +149,29 @@ def test_rng_path_pathwise_vs_oracle(engine, model):
         assert_close(got, ref, f"model {model} dim {dim} T {T}")
 
 
+@pytest.mark.parametrize("model", [2, 3, 4])
+def test_trend_weight_kernels_vs_oracle(engine, model):
+    """The AUX kernels (dim <= 4 and 9..12: trend moments through the tensor pipe, table-driven weights) against the
+    oracle on the device normals, for every dim they serve, ragged step counts (masked tail blocks, empty segments),
+    and both sides of the table-size limit (T = 2^22 uses the table, 2^22 + 1 falls back to the scalar sums)."""
+    # (T >= 2 dim + 6: with fewer steps than rows F F' is singular and the reference itself fails)
+    cases = [(d, T) for d in (1, 2, 3, 4, 9, 10, 11, 12) for T in (31, 33, 67, 250)]
+    cases += [(d, 14) for d in (1, 2, 3, 4)] + [(12, 2999), (4, 10000)]      # T = 14: two empty segments
+    for dim, T in cases:
+        seeds = np.array([7, 8], dtype=np.uint32)
+        got = engine.eigs_batch(model, dim, T, seeds)
+        ref = np.stack([orc.eigs_from_normals(engine.gen_normal_matrix(dim, T, int(s)), model) for s in seeds])
+        assert_close(got, ref, f"model {model} dim {dim} T {T}")
+        multi = engine.eigs_batch_multi(range(5), dim, T, seeds)
+        assert np.array_equal(multi[model], got), f"fused pass differs from the single-model kernel: model {model} dim {dim} T {T}"
+    for T in ((1 << 22), (1 << 22) + 1):
+        seeds = np.array([11], dtype=np.uint32)
+        got = engine.eigs_batch(model, 2, T, seeds)
+        ref = np.stack([orc.eigs_from_normals(engine.gen_normal_matrix(2, T, int(s)), model) for s in seeds])
+        tol = 1e-8 * np.abs(ref) + 1e-11 * ref.max()      # T = 4.2e6: the oracle's own two-pass sums carry ~1e-10
+        assert np.all(np.abs(got - ref) <= tol), f"model {model} T {T}: {np.max(np.abs(got - ref) / tol):.3g}"
+
+
 def test_determinism_and_geometry_independence(engine):
     """Same (model, dim, steps, seed) => bit-identical record, whatever the batch, order or entry point
     (stronger than src/tests/data_storage/integration/resumable.rs:62-70)."""
