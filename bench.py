@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--runs", type=int, default=133200, help="runs per model per step per GPU")
     ap.add_argument("--cpu-runs", type=int, default=0, help="CPU sample: runs per model (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dat", action="store_true", help="skip the end-to-end figure that includes the .dat files")
     return ap.parse_args()
 
 
@@ -284,6 +285,25 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total_runs / float(te.item())
+    # ---- e2e incl. the .dat files: the CLI's model loop for this dim as one fused job (run_models_simulation):
+    #      resume scan, GPU batches, batched EIGENVALS_V6 encode + write of five files, trailers ----
+    dat_value = None
+    dat_bytes = 0
+    if rank == 0 and not args.no_dat:
+        import shutil, tempfile
+        from johansen_null_eigenspectra_b200 import dat as jdat
+        n_dat = R * max(1, args.steps)
+        tmpdir = tempfile.mkdtemp(prefix="jne_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            names = {m: os.path.join(tmpdir, f"eigenvalues_model{m}_dim{dim}_steps{T}.dat") for m in MODELS}
+            d0 = time.perf_counter()
+            st = jdat.run_models_simulation(MODELS, dim, T, n_dat, names, quiet=True, engine=eng)
+            dat_s = time.perf_counter() - d0
+            assert all(st[m]["total_in_file"] == n_dat for m in MODELS)
+            dat_bytes = sum(os.path.getsize(f) for f in names.values())
+            dat_value = len(MODELS) * n_dat / dat_s
+        finally:
+            shutil.rmtree(tmpdir, ignore_errors=True)
     h2d = 4 * R
     d2h = 8 * R * width
     tp = torch.tensor([pm_ms], dtype=torch.float64, device="cuda")
@@ -342,6 +362,12 @@ def main():
             "gpu_launches": int(gpu_launches),
             "clocks": clocks.summary(),
         }
+        if dat_value is not None:
+            line["e2e_dat"] = {
+                "value": dat_value, "unit": "runs/s", "file_bytes": dat_bytes,
+                "note": f"rank 0: run_models_simulation of {R * max(1, args.steps)} seeds x 5 models into five EIGENVALS_V6 files "
+                        "(tmpfs), resume scan + GPU + batched encode/write + trailers inside",
+            }
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             runs = args.cpu_runs or max(threads * 1024, 4096)      # ~10 s of CPU work on the box's cores

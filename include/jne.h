@@ -89,6 +89,9 @@ int jne_multi_width(uint32_t model_mask, uint32_t dim);   /* sum of jne_num_eigs
  * (src/data_storage/thread_manager.rs:25-92). */
 int64_t jne_submit(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps,
                    const uint32_t* seeds, uint64_t n, double* out);
+/* The same for the fused multi-model batch (rows of jne_multi_width(model_mask, dim) doubles). */
+int64_t jne_submit_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps,
+                         const uint32_t* seeds, uint64_t n, double* out);
 int jne_wait(jne_ctx* ctx, int64_t ticket);
 
 /* Same computation with everything already resident on device 0 of the context: d_seeds and
@@ -148,10 +151,20 @@ int jne_simulate_percentiles(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t
 
 /* run_model_simulation (src/data_storage/parallel_compute.rs:150-232) for one (model, dim, steps, num_runs) job:
  * resume scan of `filename` -> remaining seeds of 1..=num_runs -> GPU batches -> batched EIGENVALS_V6 append ->
- * trailer.  Creates its own context over device_ids (NULL / 0 = all GPUs); `ctx` is reserved and may be NULL.
+ * trailer.  Runs on `ctx` when it is not NULL, else on a context of its own over device_ids (NULL / 0 = all GPUs).
  * stats (3 x u64, may be NULL): records present before, records computed now, records in the file after. */
 int jne_run_model_simulation(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, uint64_t num_runs,
                              const char* filename, int quiet, const int* device_ids, int n_devices, uint64_t* stats);
+
+/* The CLI's model loop over one dim (`for &model in &models_vec { ... run_simulation() }`, src/main.rs:109-114) as ONE
+ * fused pass: every model selected in model_mask gets its own EIGENVALS_V6 file (filenames[m] for bit m; entries of
+ * unselected models may be NULL), resumed independently (scan, parameter mismatch -> restart, complete -> untouched);
+ * seeds are grouped by the set of models that still lack them and each group is one jne_eigs_batch_multi stream, so a
+ * fresh five-model job evaluates every Brownian path once instead of five times.  Each file is byte-identical to the
+ * one jne_run_model_simulation writes for that model.  stats (5 x 3 x u64, may be NULL): per model as above. */
+int jne_run_models_simulation(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps, uint64_t num_runs,
+                              const char* const* filenames, int quiet, const int* device_ids, int n_devices,
+                              uint64_t* stats);
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 

@@ -44,6 +44,10 @@ int jne_dat_open(const char* path, uint8_t model, uint8_t dim, uint32_t steps,
 /* Append n records: seeds[i] with eigs[i*p .. i*p+p).  One encode pass, one write.  p must be 1..255 and
  * constant within a file ("Eigenvalue count mismatch", writer.rs:224-239). */
 int jne_dat_append_batch(jne_dat_writer* w, const uint32_t* seeds, const double* eigs, uint64_t n, uint32_t p);
+/* The same with record i's values at eigs[i*stride .. i*stride+p): appends one model's block of the rows of a fused
+ * multi-model batch (jne_eigs_batch_multi) without a de-interleaving copy.  stride >= p. */
+int jne_dat_append_batch_strided(jne_dat_writer* w, const uint32_t* seeds, const double* eigs, uint64_t n, uint32_t p,
+                                 uint64_t stride);
 
 /* Flush buffered records to the OS (the reference flushes every 10 000 records, config.rs:5). */
 int jne_dat_flush(jne_dat_writer* w);

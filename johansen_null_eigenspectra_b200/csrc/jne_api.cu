@@ -755,6 +755,23 @@ int64_t jne_submit(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, co
   return ctx->pending_ticket;
 }
 
+int64_t jne_submit_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
+                         double* out) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  if (ctx->pending_ticket) return fail(ctx, JNE_ERR_INVALID_ARG, "a ticket is already outstanding; call jne_wait first");
+  if (model_mask == 0 || model_mask > 31u) return fail(ctx, JNE_ERR_INVALID_ARG, "model_mask must select models 0..4");
+  for (int m = 0; m < 5; ++m)
+    if ((model_mask >> m) & 1u) { int rc = validate(ctx, (uint8_t)m, dim, steps); if (rc) return rc; }
+  if (n && (!seeds || !out)) return fail(ctx, JNE_ERR_INVALID_ARG, "seeds/out is NULL");
+  join_worker(ctx);
+  auto copy = std::make_shared<std::vector<uint32_t>>(seeds, seeds + n);
+  ctx->pending_ticket = ctx->next_ticket++;
+  ctx->worker = std::thread([ctx, model_mask, dim, steps, copy, n, out]() {
+    ctx->pending_status = eigs_batch_sync(ctx, model_mask, dim, steps, copy->data(), n, out);
+  });
+  return ctx->pending_ticket;
+}
+
 int jne_wait(jne_ctx* ctx, int64_t ticket) {
   if (!ctx) return JNE_ERR_INVALID_ARG;
   if (ticket <= 0 || ticket != ctx->pending_ticket) return fail(ctx, JNE_ERR_INVALID_ARG, "unknown ticket");

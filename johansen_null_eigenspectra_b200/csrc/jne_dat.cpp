@@ -266,7 +266,13 @@ int jne_dat_open(const char* path, uint8_t model, uint8_t dim, uint32_t steps, u
 }
 
 int jne_dat_append_batch(jne_dat_writer* w, const uint32_t* seeds, const double* eigs, uint64_t n, uint32_t p) {
+  return jne_dat_append_batch_strided(w, seeds, eigs, n, p, p);
+}
+
+int jne_dat_append_batch_strided(jne_dat_writer* w, const uint32_t* seeds, const double* eigs, uint64_t n, uint32_t p,
+                                 uint64_t stride) {
   if (!w || !w->f) return fail("writer is closed");
+  if (stride < p) return fail("stride is smaller than the eigenvalue count");
   if (p > 255) return fail("Too many eigenvalues: " + std::to_string(p) + " exceeds maximum of 255");
   if (n == 0) return JNE_OK;
   if (w->per_run == 0) w->per_run = p;
@@ -282,7 +288,7 @@ int jne_dat_append_batch(jne_dat_writer* w, const uint32_t* seeds, const double*
     for (uint64_t i = 0; i < m; ++i) {
       q += jne_uleb128_encode(seeds[a + i], q);
       *q++ = (unsigned char)p;
-      memcpy(q, eigs + (a + i) * p, 8 * (size_t)p);   // f64 little-endian == host representation
+      memcpy(q, eigs + (a + i) * stride, 8 * (size_t)p);   // f64 little-endian == host representation
       q += 8 * (size_t)p;
     }
     const size_t bytes = q - w->buf.data();

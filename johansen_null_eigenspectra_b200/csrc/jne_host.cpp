@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <memory>
+#include <thread>
 
 #include "jne_host.hpp"
 
@@ -70,18 +72,143 @@ SimulationStats run_model_simulation(const Engine& gpu, Model model, uint32_t di
   return st;
 }
 
+void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim, uint32_t steps, uint64_t num_runs,
+                           const std::string (&filenames)[5], bool quiet, SimulationStats (&stats)[5]) {
+  if (model_mask == 0 || model_mask > 31u) throw Error(JNE_ERR_INVALID_ARG, "model_mask must select models 0..4");
+  if (dim > 255) throw Error(JNE_ERR_INVALID_ARG, "dim must fit the u8 header field");
+  // ---- resume scan per file; need[s-1] = models that still lack seed s ----
+  std::vector<uint8_t> need(num_runs, 0);
+  {
+    std::vector<uint8_t> bitmap((num_runs + 7) / 8);
+    for (int m = 0; m < 5; ++m) {
+      stats[m] = SimulationStats{};
+      if (!((model_mask >> m) & 1u)) continue;
+      uint64_t completed = 0;
+      int rc = jne_dat_completed_bitmap(filenames[m].c_str(), (uint8_t)m, (uint8_t)dim, steps, num_runs, bitmap.data(), &completed);
+      if (rc != JNE_OK) {
+        const std::string msg = jne_dat_last_error();
+        if (msg.find("mismatch") == std::string::npos) throw Error(rc, msg);
+        if (!quiet) printf("WARNING: Existing file has incompatible parameters:\n  %s\n", msg.c_str());
+        std::remove(filenames[m].c_str());               // parallel_compute.rs:159-175
+        std::fill(bitmap.begin(), bitmap.end(), 0);
+        completed = 0;
+      }
+      stats[m].completed_before = completed;
+      stats[m].total_in_file = completed;
+      for (uint64_t s = 0; s < num_runs; ++s)
+        if (!((bitmap[s >> 3] >> (s & 7)) & 1u)) need[s] |= (uint8_t)(1u << m);
+    }
+  }
+  // ---- writers for the files that lack something (a complete file is not touched, parallel_compute.rs:182-198) ----
+  jne_dat_writer* w[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint64_t existing[5] = {0, 0, 0, 0, 0};
+  uint32_t lacking = 0;
+  for (uint64_t s = 0; s < num_runs; ++s) lacking |= need[s];
+  auto abandon_all = [&]() { for (auto& x : w) if (x) { jne_dat_abandon(x); x = nullptr; } };
+  for (int m = 0; m < 5; ++m) {
+    if (!((lacking >> m) & 1u)) continue;
+    const int rc = jne_dat_open(filenames[m].c_str(), (uint8_t)m, (uint8_t)dim, steps, &existing[m], &w[m]);
+    if (rc != JNE_OK) { const std::string msg = jne_dat_last_error(); abandon_all(); throw Error(rc, msg); }
+  }
+  // ---- one fused pass per distinct set of lacking models, double-buffered against the writers ----
+  const size_t chunk = 1u << 16;      // ~20 ms of GPU work at dim 12, T 10 000: short tail, writers well ahead
+  std::vector<double> buf[2];
+  std::vector<uint32_t> seeds;
+  try {
+    for (uint32_t mask = 1; mask < 32; ++mask) {
+      if ((mask & ~lacking) != 0) continue;
+      seeds.clear();
+      for (uint64_t s = 0; s < num_runs; ++s)
+        if (need[s] == mask) seeds.push_back((uint32_t)(s + 1));
+      if (seeds.empty()) continue;
+      const uint32_t width = (uint32_t)jne_multi_width(mask, dim);
+      uint32_t off[5], pm[5];
+      { uint32_t o = 0; for (int m = 0; m < 5; ++m) { pm[m] = (uint32_t)Model((uint8_t)m).num_eigs(dim); off[m] = o; if ((mask >> m) & 1u) o += pm[m]; } }
+      size_t prev_a = 0, prev_n = 0;
+      int which = 0;
+      for (size_t a = 0;; a += chunk) {
+        const size_t n = a < seeds.size() ? std::min(chunk, seeds.size() - a) : 0;
+        int64_t ticket = 0;
+        if (n) {
+          buf[which].resize(n * width);
+          ticket = jne_submit_multi(gpu.ctx(), mask, dim, steps, seeds.data() + a, n, buf[which].data());
+          gpu.check(ticket);
+        }
+        if (prev_n) {                                  // one writer thread per file, as many files as models in the mask
+          std::thread th[5];
+          int rcs[5] = {0, 0, 0, 0, 0};
+          std::string errs[5];
+          const double* rows = buf[which ^ 1].data();
+          for (int m = 0; m < 5; ++m) {
+            if (!((mask >> m) & 1u)) continue;
+            th[m] = std::thread([&, m]() {
+              rcs[m] = jne_dat_append_batch_strided(w[m], seeds.data() + prev_a, rows + off[m], prev_n, pm[m], width);
+              if (rcs[m] != JNE_OK) errs[m] = jne_dat_last_error();
+            });
+          }
+          for (auto& t : th) if (t.joinable()) t.join();
+          for (int m = 0; m < 5; ++m) {
+            if (rcs[m] != JNE_OK) throw Error(rcs[m], errs[m]);
+            if ((mask >> m) & 1u) stats[m].computed += prev_n;
+          }
+          if (!quiet) printf("Simulation progress (models mask 0x%x): %llu/%llu seeds\n", mask,
+                             (unsigned long long)(prev_a + prev_n), (unsigned long long)seeds.size());
+        }
+        if (n) gpu.check(jne_wait(gpu.ctx(), ticket));
+        prev_a = a; prev_n = n; which ^= 1;
+        if (!n) break;
+      }
+    }
+  } catch (...) {
+    abandon_all();        // trailer-less, resumable files, like an interrupted reference run
+    throw;
+  }
+  for (int m = 0; m < 5; ++m) {
+    if (!w[m]) continue;
+    const int rc = jne_dat_finish(w[m]);
+    w[m] = nullptr;
+    if (rc != JNE_OK) { const std::string msg = jne_dat_last_error(); abandon_all(); throw Error(rc, msg); }
+    stats[m].total_in_file = existing[m] + stats[m].computed;
+  }
+}
+
 }  // namespace jne
 
 extern "C" {
 
-// C entry for run_model_simulation (used by the Python mirror and the tests).  stats: 3 x u64
-// {completed_before, computed, total_in_file}.  Not in include/jne.h's hot-path section: orchestration helper.
-int jne_run_model_simulation(jne_ctx* ctx_unused, uint8_t model, uint32_t dim, uint32_t steps, uint64_t num_runs,
-                             const char* filename, int quiet, const int* device_ids, int n_devices, uint64_t* stats) {
-  (void)ctx_unused;
+// C entry for run_models_simulation.  filenames: 5 entries (NULL for models outside model_mask); stats: 5 x 3 x u64.
+int jne_run_models_simulation(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps, uint64_t num_runs,
+                              const char* const* filenames, int quiet, const int* device_ids, int n_devices, uint64_t* stats) {
   try {
     std::vector<int> devs(device_ids, device_ids + (device_ids ? n_devices : 0));
-    jne::Engine gpu(devs);
+    std::string names[5];
+    for (int m = 0; m < 5; ++m) {
+      if (!((model_mask >> m) & 1u)) continue;
+      if (!filenames || !filenames[m]) throw jne::Error(JNE_ERR_INVALID_ARG, "filename missing for a selected model");
+      names[m] = filenames[m];
+    }
+    std::unique_ptr<jne::Engine> own(ctx ? jne::Engine::borrow(ctx) : new jne::Engine(devs));
+    const jne::Engine& gpu = *own;
+    jne::SimulationStats st[5];
+    jne::run_models_simulation(gpu, model_mask, dim, steps, num_runs, names, quiet != 0, st);
+    if (stats)
+      for (int m = 0; m < 5; ++m) { stats[3 * m] = st[m].completed_before; stats[3 * m + 1] = st[m].computed; stats[3 * m + 2] = st[m].total_in_file; }
+    return JNE_OK;
+  } catch (const jne::Error& e) {
+    fprintf(stderr, "jne_run_models_simulation: %s\n", e.what());
+    return e.status;
+  }
+}
+
+// C entry for run_model_simulation (used by the Python mirror and the tests).  stats: 3 x u64
+// {completed_before, computed, total_in_file}.  Not in include/jne.h's hot-path section: orchestration helper.
+// ctx != NULL: run on that context (device_ids ignored); ctx == NULL: a context over device_ids for this call.
+int jne_run_model_simulation(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, uint64_t num_runs,
+                             const char* filename, int quiet, const int* device_ids, int n_devices, uint64_t* stats) {
+  try {
+    std::vector<int> devs(device_ids, device_ids + (device_ids ? n_devices : 0));
+    std::unique_ptr<jne::Engine> own(ctx ? jne::Engine::borrow(ctx) : new jne::Engine(devs));
+    const jne::Engine& gpu = *own;
     const jne::SimulationStats st = jne::run_model_simulation(gpu, jne::Model(model), dim, steps, num_runs, filename, quiet != 0);
     if (stats) { stats[0] = st.completed_before; stats[1] = st.computed; stats[2] = st.total_in_file; }
     return JNE_OK;

@@ -4,6 +4,7 @@
 //   jne::calculate_eigenvalues              calculate_eigenvalues                 src/johansen_statistics.rs:59-85
 //   jne::calculate_eigenvalues_parallel     calculate_eigenvalues_parallel        src/data_storage/parallel_compute.rs:14-41
 //   jne::run_model_simulation               run_model_simulation                  src/data_storage/parallel_compute.rs:150-232
+//   jne::run_models_simulation              the CLI's model loop over one dim     src/main.rs:109-114
 //   jne::get_filename                       EigenvalueSimulation::get_filename    src/data_storage/simulation.rs:98-122
 // The reference panics on hot-path failures; here they surface as jne::Error (never abort, never a CPU fallback).
 #pragma once
@@ -40,7 +41,12 @@ class Engine {
     const int rc = jne_init(devices.empty() ? nullptr : devices.data(), (int)devices.size(), &ctx_);
     if (rc != JNE_OK) throw Error(rc, jne_last_error(nullptr));
   }
-  ~Engine() { jne_shutdown(ctx_); }
+  // borrow an existing context (not shut down by the returned object)
+  static Engine* borrow(jne_ctx* ctx) {
+    if (!ctx) throw Error(JNE_ERR_INVALID_ARG, "ctx is NULL");
+    return new Engine(ctx, 0);
+  }
+  ~Engine() { if (owned_) jne_shutdown(ctx_); }
   Engine(const Engine&) = delete;
   Engine& operator=(const Engine&) = delete;
   jne_ctx* ctx() const { return ctx_; }
@@ -53,7 +59,9 @@ class Engine {
   }
 
  private:
+  Engine(jne_ctx* ctx, int) : ctx_(ctx), owned_(false) {}
   jne_ctx* ctx_ = nullptr;
+  bool owned_ = true;
 };
 
 // src/johansen_statistics.rs:59-85: one run, eigenvalues descending
@@ -99,5 +107,15 @@ struct SimulationStats { uint64_t completed_before = 0, computed = 0, total_in_f
 // Parameter mismatch in an existing file: delete and restart (:159-175).  Implemented in jne_host.cpp.
 SimulationStats run_model_simulation(const Engine& gpu, Model model, uint32_t dim, uint32_t steps, uint64_t num_runs,
                                      const std::string& filename, bool quiet);
+
+
+// The CLI's loop `for &model in &models_vec { EigenvalueSimulation::new(model, dim, steps, num_runs).run_simulation() }`
+// (src/main.rs:109-114) as ONE pass: the Brownian path of a seed does not depend on the model (src/rng_matrix.rs:11),
+// so the fused kernel (jne_eigs_batch_multi) serves every selected model's file from one evaluation of the path.
+// Each file is resumed on its own (scan, mismatch -> restart, already complete -> untouched), seeds are grouped by
+// the set of models that still lack them, and every file ends up byte-identical to what run_model_simulation
+// writes for that model.  filenames[m] is used when bit m of model_mask is set.  stats[m] per selected model.
+void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim, uint32_t steps, uint64_t num_runs,
+                           const std::string (&filenames)[5], bool quiet, SimulationStats (&stats)[5]);
 
 }  // namespace jne

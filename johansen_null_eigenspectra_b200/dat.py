@@ -50,6 +50,11 @@ lib.jne_dat_remaining_seeds.argtypes = [_vp, C.c_uint64, _vp, C.c_uint64]
 lib.jne_run_model_simulation.restype = C.c_int
 lib.jne_run_model_simulation.argtypes = [_vp, C.c_uint8, C.c_uint32, C.c_uint32, C.c_uint64, C.c_char_p, C.c_int,
                                          C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_uint64)]
+lib.jne_run_models_simulation.restype = C.c_int
+lib.jne_run_models_simulation.argtypes = [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_char_p), C.c_int,
+                                          C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_uint64)]
+lib.jne_dat_append_batch_strided.restype = C.c_int
+lib.jne_dat_append_batch_strided.argtypes = [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint64]
 
 
 def _check(rc: int) -> None:
@@ -97,6 +102,14 @@ class AppendOnlyWriter:
             eigs = eigs.reshape(seeds.size, -1) if seeds.size else eigs.reshape(0, 1)
         assert eigs.shape[0] == seeds.size
         _check(lib.jne_dat_append_batch(self._w, seeds.ctypes.data, eigs.ctypes.data, seeds.size, eigs.shape[1]))
+
+    def append_batch_strided(self, seeds, rows, offset: int, p: int) -> None:
+        """Append columns [offset, offset + p) of the C-contiguous rows of a fused multi-model batch."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        assert rows.ndim == 2 and rows.shape[0] == seeds.size and offset + p <= rows.shape[1]
+        _check(lib.jne_dat_append_batch_strided(self._w, seeds.ctypes.data, rows.ctypes.data + 8 * offset, seeds.size, p,
+                                                rows.shape[1]))
 
     def append_eigenvalues(self, seed: int, eigenvalues) -> None:   # the reference's per-record call
         self.append_batch([seed], np.asarray(eigenvalues, dtype=np.float64)[None, :])
@@ -167,3 +180,22 @@ def run_model_simulation(model: int, dim: int, steps: int, num_runs: int, filena
     if rc < 0:
         raise JneError(rc, "run_model_simulation failed (see stderr)")
     return {"completed_before": stats[0], "computed": stats[1], "total_in_file": stats[2]}
+
+
+def run_models_simulation(models, dim: int, steps: int, num_runs: int, filenames: dict, quiet: bool = True,
+                          devices: Optional[list] = None, engine=None) -> dict:
+    """The CLI's model loop over one dim (src/main.rs:109-114) as one fused pass (C++: csrc/jne_host.cpp
+    run_models_simulation).  filenames: {model: path} for every model in `models`.  Returns {model: stats}."""
+    models = sorted(int(m) for m in models)
+    mask = 0
+    names = (C.c_char_p * 5)()
+    for m in models:
+        mask |= 1 << m
+        names[m] = str(filenames[m]).encode()
+    stats = (C.c_uint64 * 15)()
+    arr = (C.c_int * len(devices))(*devices) if devices is not None else None
+    rc = lib.jne_run_models_simulation(engine._ctx if engine is not None else None, mask, dim, steps, num_runs, names, int(quiet), arr,
+                                       len(devices) if devices is not None else 0, stats)
+    if rc < 0:
+        raise JneError(rc, "run_models_simulation failed (see stderr)")
+    return {m: {"completed_before": stats[3 * m], "computed": stats[3 * m + 1], "total_in_file": stats[3 * m + 2]} for m in models}

@@ -161,3 +161,21 @@ def test_resume_scan_bitmap(tmp_path):   # progress.rs:11-61, integration/helper
 
 def test_filename():   # simulation_test.rs:68
     assert dat.get_filename(0, 5, 999) == "data/eigenvalues_model0_dim5_steps999.dat"
+
+
+def test_strided_append_matches_contiguous(tmp_path):
+    """jne_dat_append_batch_strided writes one model's block of fused multi-model rows: same bytes as appending the
+    de-interleaved copy; a stride below the eigenvalue count is refused."""
+    rng = np.random.default_rng(3)
+    n, width = 1000, 12 + 13 + 12
+    rows = rng.standard_normal((n, width))
+    seeds = rng.permutation(np.arange(1, n + 1)).astype(np.uint32)
+    for off, p, model in ((0, 12, 0), (12, 13, 1), (25, 12, 2)):
+        a, b = tmp_path / f"a{model}.dat", tmp_path / f"b{model}.dat"
+        w = dat.AppendOnlyWriter(a, model, 12, 50); w.append_batch_strided(seeds, rows, off, p); w.finish()
+        w = dat.AppendOnlyWriter(b, model, 12, 50); w.append_batch(seeds, rows[:, off:off + p].copy()); w.finish()
+        assert a.read_bytes() == b.read_bytes()
+    w = dat.AppendOnlyWriter(tmp_path / "c.dat", 0, 2, 5)
+    rc = dat.lib.jne_dat_append_batch_strided(w._w, seeds.ctypes.data, rows.ctypes.data, 10, 3, 2)
+    assert rc < 0 and b"stride" in dat.lib.jne_dat_last_error()
+    w.finish()

@@ -52,6 +52,42 @@ def test_all_models_files_and_mismatch_restart(tmp_path, engine):
     assert dat.file_info(path)["steps"] == 212
 
 
+def test_fused_models_simulation(tmp_path, engine):
+    """run_models_simulation (the CLI's model loop of src/main.rs:109-114 as one fused pass): every file is
+    byte-identical to the one run_model_simulation writes for that model; files with different progress are resumed
+    independently (seeds grouped by the set of models that lack them); complete files are left alone; a header
+    mismatch restarts that file only."""
+    dim, T, n = 3, 150, 700
+    ref_dir, out_dir = tmp_path / "ref", tmp_path / "out"
+    ref_dir.mkdir(); out_dir.mkdir()
+    names = {m: str(out_dir / f"eigenvalues_model{m}_dim{dim}_steps{T}.dat") for m in range(5)}
+    for m in range(5):
+        dat.run_model_simulation(m, dim, T, n, str(ref_dir / f"m{m}.dat"), devices=[0])
+    # fresh job, all five models
+    st = dat.run_models_simulation(range(5), dim, T, n, names, devices=[0])
+    for m in range(5):
+        assert st[m] == {"completed_before": 0, "computed": n, "total_in_file": n}
+        assert open(names[m], "rb").read() == open(ref_dir / f"m{m}.dat", "rb").read()
+    # nothing left to do
+    st = dat.run_models_simulation(range(5), dim, T, n, names, devices=[0])
+    assert all(st[m]["computed"] == 0 and st[m]["total_in_file"] == n for m in range(5))
+    # uneven progress: model 2 has seeds 1..300 already, model 4 has an incompatible header, model 1 is complete
+    import os
+    os.remove(names[0]); os.remove(names[2]); os.remove(names[3]); os.remove(names[4])
+    dat.run_model_simulation(2, dim, T, 300, names[2], devices=[0])
+    dat.run_model_simulation(4, dim, T + 1, 50, names[4], devices=[0])
+    before1 = open(names[1], "rb").read()
+    st = dat.run_models_simulation([0, 1, 2, 4], dim, T, n, names, devices=[0])
+    assert st[0]["computed"] == n and st[1]["computed"] == 0 and st[4] == {"completed_before": 0, "computed": n, "total_in_file": n}
+    assert st[2] == {"completed_before": 300, "computed": n - 300, "total_in_file": n}
+    assert open(names[1], "rb").read() == before1 and not os.path.exists(names[3])
+    for m in (0, 2, 4):
+        seeds, eigs, mm, d, t = dat.read_append_file(names[m])
+        assert (mm, d, t) == (m, dim, T) and sorted(seeds) == list(range(1, n + 1))
+        assert np.array_equal(eigs[np.argsort(seeds)], engine.eigs_batch(m, dim, T, np.arange(1, n + 1)))
+        assert dat.file_info(names[m])["has_trailer"]
+
+
 def test_streaming_percentiles(engine):
     """Row f3: on-device trace / max-eig percentiles == the reference's analyser (src/simulation_analyzers.rs:4-65,
     restated in oracle.percentiles) applied to the same records on the host."""
