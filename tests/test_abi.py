@@ -180,3 +180,24 @@ def test_trend_weight_table_rejects_bad_sizes():
     for T in (0, (1 << 22) + 1):
         with pytest.raises(jne.JneError):
             jne.trend_weight_table(T)
+
+
+def test_rust_shim_binds_only_declared_and_exported_symbols():
+    """ffi/rust/src/gpu_ffi.rs (source only -- no Rust toolchain in this image): every function of its extern "C" block
+    must be declared in include/*.h and exported by libjne.so, with the same number of arguments as the C prototype."""
+    import johansen_null_eigenspectra_b200 as jne
+    text = (ROOT / "ffi" / "rust" / "src" / "gpu_ffi.rs").read_text()
+    block = re.search(r'extern "C" \{(.*?)\n\}', text, flags=re.S).group(1)
+    fns = re.findall(r"fn (jne_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->[^;]+)?;", block, flags=re.S)
+    assert len(fns) >= 10
+    header = ""
+    for h in sorted((ROOT / "include").glob("*.h")):
+        header += re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
+    lib = ctypes.CDLL(str(Path(jne.__file__).parent / "libjne.so"))
+    for name, args in fns:
+        assert hasattr(lib, name), name
+        proto = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", header, flags=re.S)
+        assert proto, f"{name} is not declared in include/*.h"
+        c_args = [a for a in proto.group(1).split(",") if a.strip() and a.strip() != "void"]
+        rust_args = [a for a in args.split(",") if a.strip()]
+        assert len(c_args) == len(rust_args), (name, c_args, rust_args)
