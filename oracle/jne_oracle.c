@@ -58,6 +58,16 @@ static inline uint64_t xo_next(xo_t* r) {
   s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
   return res;
 }
+/* Known-answer hooks (tests/test_oracle.py): the published vectors of the two generators -- SplitMix64 from seed
+ * 1234567 (Vigna's splitmix64.c) and xoshiro256++ from the state {1, 2, 3, 4} (the `reference` test of
+ * rand_xoshiro's xoshiro256plusplus.rs) -- pin this restatement of the third-party arithmetic. */
+void jne_oracle_splitmix64(uint64_t seed, size_t n, uint64_t* out) { for (size_t i = 0; i < n; ++i) out[i] = splitmix64(&seed); }
+void jne_oracle_xoshiro_from_state(const uint64_t* state, size_t n, uint64_t* out) {
+  xo_t r; memcpy(r.s, state, sizeof r.s);
+  for (size_t i = 0; i < n; ++i) out[i] = xo_next(&r);
+}
+void jne_oracle_xoshiro_seed_from_u64(uint64_t seed, uint64_t* state_out) { xo_t r; xo_seed(&r, seed); memcpy(state_out, r.s, sizeof r.s); }
+
 static inline double float_with_exponent(uint64_t bits52, int e) {
   uint64_t u = ((uint64_t)(1023 + e) << 52) | bits52;
   double d; memcpy(&d, &u, 8); return d;

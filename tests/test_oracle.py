@@ -208,3 +208,24 @@ def test_philox_normal_matrix_is_standard_normal():
     emp = np.searchsorted(np.sort(z.ravel()), stats.norm.ppf(qs)) / z.size
     assert np.abs(emp - qs).max() < 1e-2          # the reference's own criterion
     assert np.array_equal(z[:5, :40], philox_ref.normal_matrix(5, 40, 42))   # prefix property
+
+
+def test_port_generators_match_published_vectors():
+    """The CPU port's restatement of the reference's third-party generators (rand_xoshiro 0.7.0, not under
+    /root/reference) against their published known-answer vectors: SplitMix64 from seed 1234567 (Vigna's
+    splitmix64.c) and xoshiro256++ from the state {1, 2, 3, 4} (the `reference` test in rand_xoshiro's
+    xoshiro256plusplus.rs); seed_from_u64 fills the state with four SplitMix64 outputs."""
+    import ctypes as C
+    lib = c_oracle.load()
+    out = np.zeros(10, dtype=np.uint64)
+    lib.jne_oracle_splitmix64(C.c_uint64(1234567), C.c_size_t(5), C.c_void_p(out.ctypes.data))
+    assert out[:5].tolist() == [6457827717110365317, 3203168211198807973, 9817491932198370423,
+                                4593380528125082431, 16408922859458223821]
+    state = np.array([1, 2, 3, 4], dtype=np.uint64)
+    lib.jne_oracle_xoshiro_from_state(C.c_void_p(state.ctypes.data), C.c_size_t(10), C.c_void_p(out.ctypes.data))
+    assert out.tolist() == [41943041, 58720359, 3588806011781223, 3591011842654386, 9228616714210784205,
+                            9973669472204895162, 14011001112246962877, 12406186145184390807,
+                            15849039046786891736, 10450023813501588000]
+    st = np.zeros(4, dtype=np.uint64)
+    lib.jne_oracle_xoshiro_seed_from_u64(C.c_uint64(1234567), C.c_void_p(st.ctypes.data))
+    assert st.tolist() == [6457827717110365317, 3203168211198807973, 9817491932198370423, 4593380528125082431]
