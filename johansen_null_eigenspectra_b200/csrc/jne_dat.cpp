@@ -4,6 +4,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -19,16 +21,30 @@ constexpr long kHeader = 18, kTrailer = 17;
 thread_local std::string g_err;
 int fail(const std::string& m) { g_err = m; return JNE_ERR_IO; }
 
-// Cursor over a whole file held in memory-sized chunks: files are read through a large stdio buffer.
+// Read-only view of a whole file (mmap): the record walk touches every page once at memory speed instead of one
+// stdio seek + refill per record (a 10^7-record file is scanned in well under a second from the page cache).
 struct Reader {
-  FILE* f = nullptr;
-  std::vector<char> buf;
-  ~Reader() { if (f) fclose(f); }
+  const unsigned char* p = nullptr;
+  long len = 0;
+  int fd = -1;
+  ~Reader() { close_map(); }
+  void close_map() {
+    if (p && len > 0) munmap(const_cast<unsigned char*>(p), (size_t)len);
+    if (fd >= 0) ::close(fd);
+    p = nullptr; fd = -1; len = 0;
+  }
   bool open(const char* path) {
-    f = fopen(path, "rb");
-    if (!f) return false;
-    buf.resize(4u << 20);
-    setvbuf(f, buf.data(), _IOFBF, buf.size());
+    fd = ::open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0) { ::close(fd); fd = -1; return false; }
+    len = (long)st.st_size;
+    if (len > 0) {
+      void* m = mmap(nullptr, (size_t)len, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m == MAP_FAILED) { ::close(fd); fd = -1; len = 0; return false; }
+      p = static_cast<const unsigned char*>(m);
+      madvise(m, (size_t)len, MADV_SEQUENTIAL);
+    }
     return true;
   }
 };
@@ -36,20 +52,18 @@ struct Reader {
 struct Header { uint8_t model, dim; uint32_t steps; };
 
 // 0 ok, 1 file too short for a header, -1 magic mismatch
-int read_header(FILE* f, Header* h) {
-  unsigned char b[kHeader];
-  if (fread(b, 1, kHeader, f) != (size_t)kHeader) return 1;
+int read_header(const Reader& r, Header* h) {
+  if (r.len < kHeader) return 1;
+  const unsigned char* b = r.p;
   if (memcmp(b, kMagic, 12) != 0) return -1;
   h->model = b[12]; h->dim = b[13];
   h->steps = (uint32_t)b[14] | ((uint32_t)b[15] << 8) | ((uint32_t)b[16] << 16) | ((uint32_t)b[17] << 24);
   return 0;
 }
 
-bool read_trailer(FILE* f, long file_len, uint64_t* count, uint32_t* per_run) {
-  if (file_len < kHeader + kTrailer) return false;
-  if (fseek(f, file_len - kTrailer, SEEK_SET) != 0) return false;
-  unsigned char b[kTrailer];
-  if (fread(b, 1, kTrailer, f) != (size_t)kTrailer) return false;
+bool read_trailer(const Reader& r, uint64_t* count, uint32_t* per_run) {
+  if (r.len < kHeader + kTrailer) return false;
+  const unsigned char* b = r.p + (r.len - kTrailer);
   if (memcmp(b, kEof, 8) != 0) return false;
   uint64_t c = 0;
   for (int i = 0; i < 8; ++i) c |= (uint64_t)b[8 + i] << (8 * i);
@@ -57,15 +71,15 @@ bool read_trailer(FILE* f, long file_len, uint64_t* count, uint32_t* per_run) {
   return true;
 }
 
-// Reads one ULEB128 u32 from a stream: >0 bytes consumed, 0 clean EOF before the first byte, <0 error.
-int read_uleb(FILE* f, uint32_t* v) {
+// Reads one ULEB128 u32 at offset pos: >0 bytes consumed, 0 clean end of file before the first byte, <0 error.
+inline int read_uleb(const Reader& r, long pos, uint32_t* v) {
   uint32_t result = 0; int shift = 0, n = 0;
   for (;;) {
-    int c = fgetc(f);
-    if (c == EOF) return n == 0 ? 0 : -1;
+    if (pos + n >= r.len) return n == 0 ? 0 : -1;
+    const unsigned c = r.p[pos + n];
     ++n;
     if (n > 5) return -2;
-    const uint32_t bits = (uint32_t)c & 0x7F;
+    const uint32_t bits = c & 0x7F;
     if (shift == 28 && bits > 0x0F) return -3;
     result |= bits << shift;
     shift += 7;
@@ -73,41 +87,33 @@ int read_uleb(FILE* f, uint32_t* v) {
   }
 }
 
-// Walks the records from the current position (just behind the header).  on_record(seed, count, payload offset)
-// is called per COMPLETE record; returns the offset just behind the last complete record.
-// limit: stop after this many records (trailer-known fast path) or UINT64_MAX (scan path, reader.rs:157-216).
+// Walks the records behind the header.  on_record(seed, count, payload offset) is called per COMPLETE record;
+// returns the offset just behind the last complete record.  data_end: end of the record area (file length, or
+// file length minus the trailer).  limit: stop after this many records (trailer-known fast path) or UINT64_MAX
+// (scan path, reader.rs:157-216).
 template <class F>
-long walk(FILE* f, long file_len, uint64_t limit, bool scan, F&& on_record, uint64_t* n_out, std::string* err) {
-  long good_end = kHeader;
+long walk(const Reader& r, long data_end, uint64_t limit, bool scan, F&& on_record, uint64_t* n_out, std::string* err) {
+  long good_end = kHeader, pos = kHeader;
   uint64_t n = 0;
-  fseek(f, kHeader, SEEK_SET);
   while (n < limit) {
     uint32_t seed;
-    const int used = read_uleb(f, &seed);
+    const int used = read_uleb(r, pos, &seed);
     if (used <= 0) { if (!scan && err) *err = "Incomplete ULEB128 encoding"; break; }
-    const int cnt = fgetc(f);
-    if (cnt == EOF) break;
-    const long payload = ftell(f);
+    if (pos + used >= r.len) break;
+    const int cnt = r.p[pos + used];
+    const long payload = pos + used + 1;
     if (cnt == 0) {
       if (scan) {   // a zero count followed by the EOF marker ends the data (reader.rs:178-190)
-        char e[8];
-        if (fread(e, 1, 8, f) == 8 && memcmp(e, kEof, 8) == 0) break;
-        fseek(f, payload, SEEK_SET);
+        if (payload + 8 <= r.len && memcmp(r.p + payload, kEof, 8) == 0) break;
       } else { if (err) *err = "Invalid eigenvalue count: cannot be zero"; break; }
     }
-    if (payload + 8L * cnt > file_len) break;        // torn record: dropped (reader.rs:199-210)
+    if (payload + 8L * cnt > data_end) break;        // torn record: dropped (reader.rs:199-210)
     if (!on_record(seed, (uint32_t)cnt, payload)) break;
-    fseek(f, payload + 8L * cnt, SEEK_SET);
-    good_end = payload + 8L * cnt;
+    pos = good_end = payload + 8L * cnt;
     ++n;
   }
   *n_out = n;
   return good_end;
-}
-
-long file_length(FILE* f) {
-  fseek(f, 0, SEEK_END);
-  return ftell(f);
 }
 
 }  // namespace
@@ -167,17 +173,16 @@ int jne_dat_info(const char* path, uint8_t* model, uint8_t* dim, uint32_t* steps
                  uint32_t* per_run, int* has_trailer) {
   Reader r;
   if (!r.open(path)) return fail(std::string("cannot open ") + path + ": " + strerror(errno));
-  const long len = file_length(r.f);
-  fseek(r.f, 0, SEEK_SET);
+  const long len = r.len;
   Header h{};
-  const int hr = read_header(r.f, &h);
+  const int hr = read_header(r, &h);
   if (hr < 0) return fail("File format error: magic header mismatch");
   if (hr > 0) return fail("file too short for a header");
   uint64_t count = 0; uint32_t pr = 0;
-  const bool trailer = read_trailer(r.f, len, &count, &pr);
+  const bool trailer = read_trailer(r, &count, &pr);
   if (!trailer) {
     uint32_t first = 0;
-    walk(r.f, len, UINT64_MAX, true, [&](uint32_t, uint32_t c, long) { if (!first) first = c; return true; }, &count, nullptr);
+    walk(r, len, UINT64_MAX, true, [&](uint32_t, uint32_t c, long) { if (!first) first = c; return true; }, &count, nullptr);
     pr = first;
   }
   if (model) *model = h.model;
@@ -192,24 +197,22 @@ int jne_dat_info(const char* path, uint8_t* model, uint8_t* dim, uint32_t* steps
 int jne_dat_read(const char* path, uint32_t* seeds, double* eigs, uint64_t capacity, uint32_t p, uint64_t* n_read) {
   Reader r;
   if (!r.open(path)) return fail(std::string("cannot open ") + path + ": " + strerror(errno));
-  const long len = file_length(r.f);
-  fseek(r.f, 0, SEEK_SET);
+  const long len = r.len;
   Header h{};
-  const int hr = read_header(r.f, &h);
+  const int hr = read_header(r, &h);
   if (hr < 0) return fail("File format error: magic header mismatch");
   if (hr > 0) return fail("file too short for a header");
   uint64_t count = 0; uint32_t pr = 0;
-  const bool trailer = read_trailer(r.f, len, &count, &pr);
+  const bool trailer = read_trailer(r, &count, &pr);
   std::string err;
   bool mismatch = false;
   uint64_t n = 0;
   const uint64_t limit = trailer ? (count < capacity ? count : capacity) : capacity;
-  walk(r.f, trailer ? len - kTrailer : len, limit, !trailer,
+  walk(r, trailer ? len - kTrailer : len, limit, !trailer,
        [&](uint32_t seed, uint32_t c, long payload) {
          if (c != p) { mismatch = true; err = "Eigenvalue count mismatch: expected " + std::to_string(p) + ", actual " + std::to_string(c); return false; }
          seeds[n] = seed;
-         fseek(r.f, payload, SEEK_SET);
-         if (fread(eigs + n * p, 8, p, r.f) != p) return false;   // little-endian host assumed (x86-64 / aarch64)
+         memcpy(eigs + n * p, r.p + payload, 8 * (size_t)p);      // little-endian host assumed (x86-64 / aarch64)
          ++n;
          return true;
        }, &count, &err);
@@ -226,10 +229,9 @@ int jne_dat_open(const char* path, uint8_t model, uint8_t dim, uint32_t steps, u
   if (!fresh) {
     Reader r;
     if (!r.open(path)) return fail(std::string("cannot open ") + path + ": " + strerror(errno));
-    const long len = file_length(r.f);
-    fseek(r.f, 0, SEEK_SET);
+    const long len = r.len;
     Header h{};
-    const int hr = read_header(r.f, &h);
+    const int hr = read_header(r, &h);
     if (hr < 0) {
       fresh = true;                                  // foreign magic: recreate (writer.rs:116-150)
     } else if (hr > 0) {
@@ -239,12 +241,12 @@ int jne_dat_open(const char* path, uint8_t model, uint8_t dim, uint32_t steps, u
       if (h.dim != dim) return fail("Dimension mismatch: file has dim " + std::to_string(h.dim) + ", expected " + std::to_string(dim));
       if (h.steps != steps) return fail("Steps mismatch: file has steps " + std::to_string(h.steps) + ", expected " + std::to_string(steps));
       uint64_t count = 0; uint32_t pr = 0;
-      const bool trailer = read_trailer(r.f, len, &count, &pr);
+      const bool trailer = read_trailer(r, &count, &pr);
       uint32_t first = 0;
-      const long good_end = walk(r.f, trailer ? len - kTrailer : len, trailer ? count : UINT64_MAX, !trailer,
+      const long good_end = walk(r, trailer ? len - kTrailer : len, trailer ? count : UINT64_MAX, !trailer,
                                  [&](uint32_t, uint32_t c, long) { if (!first) first = c; return true; }, &have, nullptr);
       per_run = first;
-      fclose(r.f); r.f = nullptr;
+      r.close_map();
       // drop the trailer (writer.rs:181-203) and any torn tail so that appended records stay parseable
       if (truncate(path, good_end) != 0) return fail(std::string("truncate failed: ") + strerror(errno));
     }
@@ -329,17 +331,16 @@ int jne_dat_completed_bitmap(const char* path, uint8_t model, uint8_t dim, uint3
   if (access(path, F_OK) != 0) return JNE_OK;        // progress.rs:17-19
   Reader r;
   if (!r.open(path)) return JNE_OK;                  // unreadable: start over (progress.rs:51)
-  const long len = file_length(r.f);
-  fseek(r.f, 0, SEEK_SET);
+  const long len = r.len;
   Header h{};
-  if (read_header(r.f, &h) != 0) return JNE_OK;      // damaged: start over
+  if (read_header(r, &h) != 0) return JNE_OK;      // damaged: start over
   if (h.model != model) return fail("Model mismatch: file has model " + std::to_string(h.model) + ", expected " + std::to_string(model));
   if (h.dim != dim) return fail("Dimension mismatch: file has dim " + std::to_string(h.dim) + ", expected " + std::to_string(dim));
   if (h.steps != steps) return fail("Steps mismatch: file has steps " + std::to_string(h.steps) + ", expected " + std::to_string(steps));
   uint64_t count = 0; uint32_t pr = 0;
-  const bool trailer = read_trailer(r.f, len, &count, &pr);
+  const bool trailer = read_trailer(r, &count, &pr);
   uint64_t n = 0;
-  walk(r.f, trailer ? len - kTrailer : len, trailer ? count : UINT64_MAX, !trailer,
+  walk(r, trailer ? len - kTrailer : len, trailer ? count : UINT64_MAX, !trailer,
        [&](uint32_t seed, uint32_t, long) {
          if (seed >= 1 && seed <= num_runs) bitmap[(seed - 1) >> 3] |= (uint8_t)(1u << ((seed - 1) & 7));
          return true;
