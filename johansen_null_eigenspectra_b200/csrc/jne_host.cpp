@@ -113,13 +113,19 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
   // ---- one fused pass per distinct set of lacking models, double-buffered against the writers ----
   const size_t chunk = 1u << 16;      // ~20 ms of GPU work at dim 12, T 10 000: short tail, writers well ahead
   std::vector<double> buf[2];
-  std::vector<uint32_t> seeds;
+  // seeds by the set of models that lack them, one pass (ascending within a group)
+  std::vector<uint32_t> groups[32];
+  {
+    uint64_t counts[32] = {0};
+    for (uint64_t s = 0; s < num_runs; ++s) ++counts[need[s]];
+    for (uint32_t mask = 1; mask < 32; ++mask) groups[mask].reserve(counts[mask]);
+    for (uint64_t s = 0; s < num_runs; ++s)
+      if (need[s]) groups[need[s]].push_back((uint32_t)(s + 1));
+    std::vector<uint8_t>().swap(need);
+  }
   try {
     for (uint32_t mask = 1; mask < 32; ++mask) {
-      if ((mask & ~lacking) != 0) continue;
-      seeds.clear();
-      for (uint64_t s = 0; s < num_runs; ++s)
-        if (need[s] == mask) seeds.push_back((uint32_t)(s + 1));
+      const std::vector<uint32_t>& seeds = groups[mask];
       if (seeds.empty()) continue;
       const uint32_t width = (uint32_t)jne_multi_width(mask, dim);
       uint32_t off[5], pm[5];
