@@ -599,12 +599,14 @@ __device__ __forceinline__ void jne_gen8(uint32_t t, uint32_t t_end, uint32_t d,
     }
     float x[4];
     jne_normals4_keyed(keys, 8 * L + (g & 3), (t >> 2) + (g >> 2), x, xscale);
-    const bool low = g < 4;
+    // Lanes g >= 4 own no row in this slot: what they accumulate there (a path nobody reads: their operand in
+    // the mixed group is the received increment or the trend weight, and rows >= DP of the dump are ignored) is
+    // left unmasked -- zeroing it cost two FSEL per step after the widening.
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const float other = __shfl_xor_sync(0xffffffffu, x[s], 16);    // lane g ^ 4, same segment
-      z[L][s] = low ? x[s] : 0.0f;
-      z[L][4 + s] = low ? other : 0.0f;
+      z[L][s] = x[s];
+      z[L][4 + s] = other;
     }
   }
 }
