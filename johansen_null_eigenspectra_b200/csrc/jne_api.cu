@@ -233,7 +233,7 @@ template <int DP, bool RNG>
 cudaError_t launch_det(int det, const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm, double* o,
                        unsigned int* e, double* dbg, cudaStream_t st) {
   const bool multi = (prm.model_mask & (prm.model_mask - 1u)) != 0;   // more than one model: superset accumulation
-  if constexpr (JneGeo<DP>::B == 4) {
+  if constexpr (JneGeo<DP>::B == 4 || DP == 8) {
     if (prm.aux_tab != nullptr && (multi || det >= 1)) {   // trend moments through the MMA
       if (multi) return launch_one<DP, 2, RNG, true, true>(s, b, n, prm, o, e, dbg, st);
       if (det == 1) return launch_one<DP, 1, RNG, false, true>(s, b, n, prm, o, e, dbg, st);
@@ -286,7 +286,7 @@ template <int DP>
 uint64_t wave_det(const Device& dv, const JneRunParams& prm, bool aux) {
   const int det = (prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2);
   const bool multi = (prm.model_mask & (prm.model_mask - 1u)) != 0;
-  if constexpr (JneGeo<DP>::B == 4) {
+  if constexpr (JneGeo<DP>::B == 4 || DP == 8) {
     if (aux && det >= 1)
       return multi ? wave_one<DP, 2, true, true>(dv) : det == 1 ? wave_one<DP, 1, false, true>(dv) : wave_one<DP, 2, false, true>(dv);
   }
@@ -295,11 +295,11 @@ uint64_t wave_det(const Device& dv, const JneRunParams& prm, bool aux) {
 }
 uint64_t wave_runs(const jne_ctx* ctx, const Device& dv, const JneRunParams& prm);
 
-// The AUX kernels serve dim <= 4 and 9..12 (the MMA tile layouts with four F rows and four dB rows in one group)
-// when a selected model has a trend row and the weight table fits.
+// The AUX kernels serve dim <= 4 and 9..12 (the MMA tile layouts with four F rows and four dB rows in one group) and
+// dim 5, 6 (two padding rows in the 8-row F group) when a selected model has a trend row and the weight table fits.
 bool aux_wanted(const jne_ctx* ctx, const JneRunParams& prm) {
   return ctx->use_aux && ctx->kernel_family == 1 && prm.model >= 2 && prm.steps <= kAuxMaxSteps &&
-         (prm.dim <= 4 || (prm.dim >= 9 && prm.dim <= 12));
+         (prm.dim <= 6 || (prm.dim >= 9 && prm.dim <= 12));
 }
 // Device copy of make_aux_table(steps), built on first use; nullptr when it cannot be had (callers fall back).
 const double* aux_table_for(jne_ctx* ctx, Device& dv, uint32_t steps) {

@@ -366,12 +366,19 @@ __device__ __forceinline__ void jne_warp_stitch(const double* VV, const double* 
       sz += e;
       b0 += e;
     }
-    if (AUX && r < DP) {   // rows 8A+4+m of VV: sum over steps and segments of weight_m(step) * dB_r (jne_step)
-      const double* wr = VV + (8 * G::A + 4) * G::VV_LD + DP + r;
-      s1B += wr[0 * G::VV_LD];   // weight 0: sum_{i > s, same segment} w1_i  ->  sum w1_i c_i
-      s2B += wr[1 * G::VV_LD];   // weight 1: the same for w2
-      s2z = wr[2 * G::VV_LD];    // weight 2: w2_s
-      s1z = wr[3 * G::VV_LD];    // weight 3: w1_s
+    if (AUX && r < DP) {
+      if (G::B == 4) {   // rows 8A+4+m of VV: sum over steps and segments of weight_m(step) * dB_r (jne_step)
+        const double* wr = VV + (8 * G::A + 4) * G::VV_LD + DP + r;
+        s1B += wr[0 * G::VV_LD];   // weight 0: sum_{i > s, same segment} w1_i  ->  sum w1_i c_i
+        s2B += wr[1 * G::VV_LD];   // weight 1: the same for w2
+        s2z = wr[2 * G::VV_LD];    // weight 2: w2_s
+        s1z = wr[3 * G::VV_LD];    // weight 3: w1_s
+      } else {           // DP = 8, dim <= 6: rows 6, 7 of V carry w1, w2 themselves: products with c and with dB
+        s1B += VV[6 * G::VV_LD + r];
+        s2B += VV[7 * G::VV_LD + r];
+        s1z = VV[6 * G::VV_LD + DP + r];
+        s2z = VV[7 * G::VV_LD + DP + r];
+      }
     }
     tot[0 * 16 + r] = sB;  tot[1 * 16 + r] = s1B; tot[2 * 16 + r] = s2B;
     tot[3 * 16 + r] = sz;  tot[4 * 16 + r] = s1z; tot[5 * 16 + r] = s2z;
@@ -660,8 +667,11 @@ __device__ __forceinline__ void jne_step(uint32_t t, uint32_t t_end, int g, int 
   // group's dB half only produces dB x dB products nobody reads, so lanes g >= 4 put a trend weight of the step
   // there instead and the tensor pipe delivers sum_t weight_t dB_t' for all rows in the slots it wasted before
   // (rows 8 G::A + 4 + m of VV, m = weight index g - 4).  See make_aux_table (jne_api.cu) for the four weights.
-  double Vx = V[G::A < G::NCT ? G::A : 0];
-  if (AUX && DET >= 1) Vx = (g >= 4) ? auxv : Vx;
+  // AUX with DP = 8 (dim <= 6 only): rows 6 and 7 of F are padding, so lanes g = 6, 7 feed w1 and w2 of the step as
+  // the A operand of both tiles: rows 6, 7 of VV then hold sum w c' and sum w dB' directly.
+  constexpr int AUXG = (G::B == 4) ? G::A : 0;            // the operand group that carries the weights
+  double Vx = V[AUXG < G::NCT ? AUXG : 0];
+  if (AUX && DET >= 1) Vx = (g >= (G::B == 4 ? 4 : 6)) ? auxv : Vx;
   int ti = 0;
 #pragma unroll
   for (int a = 0; a < G::NRT; ++a)
@@ -670,7 +680,7 @@ __device__ __forceinline__ void jne_step(uint32_t t, uint32_t t_end, int g, int 
 #ifdef JNE_EXP_NOMMA   // experiment only: no tensor work
       L.acc[ti][0] += V[a]; L.acc[ti][1] += V[b];
 #else
-      jne_dmma(L.acc[ti][0], L.acc[ti][1], (AUX && a == G::A) ? Vx : V[a], V[b]);
+      jne_dmma(L.acc[ti][0], L.acc[ti][1], (AUX && a == AUXG) ? Vx : V[a], V[b]);
 #endif
       ++ti;
     }
@@ -821,7 +831,8 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
                double* __restrict__ dbg /* optional: per run S2 (16x16) then R (16x16) */) {
   using G = JneGeo<DP>;
   using ZT = typename JneZ<DP, SRC_RNG>::type;
-  constexpr bool AUX = AUXT && G::B == 4 && DET >= 1;   // trend moments through the MMA (jne_step)
+  // trend moments through the MMA (jne_step): DP = 4, 12 always; DP = 8 when the host guarantees dim <= 6
+  constexpr bool AUX = AUXT && (G::B == 4 || DP == 8) && DET >= 1;
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t run = (uint64_t)blockIdx.x * JNE_WARPS_PER_CTA + warp;
@@ -861,7 +872,9 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   uint32_t t = t_begin;
   const uint32_t t_full = t_begin + 8u * prm.full_blocks, t_stop = t_begin + prm.seg_len;
   // weight table: [local step][weight m][segment k]; lane (g, k) reads weight m = g & 3 (used when g >= 4)
-  const double* aux = AUX ? prm.aux_tab + (((g & 3) << 2) | k) : nullptr;
+  // (DP = 8: lane g = 6 reads weight 3 = w1, lane g = 7 weight 2 = w2)
+  const int aux_m = (G::B == 4) ? (g & 3) : (g == 7 ? 2 : 3);
+  const double* aux = AUX ? prm.aux_tab + ((aux_m << 2) | k) : nullptr;
   for (; t < t_full; t += 8) {
     jne_gen8<DP, SRC_RNG>(t, t_end, d, g, keys, rowscale, xscale, dBrun, z);
     jne_consume8<DP, DET, SRC_RNG, false, AUX>(t, t_end, g, src_lane, z, L, w2c, aux);

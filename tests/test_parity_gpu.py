@@ -151,11 +151,12 @@ def test_rng_path_pathwise_vs_oracle(engine, model):
 
 @pytest.mark.parametrize("model", [2, 3, 4])
 def test_trend_weight_kernels_vs_oracle(engine, model):
-    """The AUX kernels (dim <= 4 and 9..12: trend moments through the tensor pipe, table-driven weights) against the
-    oracle on the device normals, for every dim they serve, ragged step counts (masked tail blocks, empty segments),
+    """The AUX kernels (dim <= 6 and 9..12: trend moments through the tensor pipe, table-driven weights) against the
+    oracle on the device normals, for every dim they serve (and dim 7 as a scalar-sum neighbour), ragged step counts
+    (masked tail blocks, empty segments),
     and both sides of the table-size limit (T = 2^22 uses the table, 2^22 + 1 falls back to the scalar sums)."""
     # (T >= 2 dim + 6: with fewer steps than rows F F' is singular and the reference itself fails)
-    cases = [(d, T) for d in (1, 2, 3, 4, 9, 10, 11, 12) for T in (31, 33, 67, 250)]
+    cases = [(d, T) for d in (1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12) for T in (31, 33, 67, 250)] + [(5, 5000), (6, 1001)]
     cases += [(d, 14) for d in (1, 2, 3, 4)] + [(12, 2999), (4, 10000)]      # T = 14: two empty segments
     for dim, T in cases:
         seeds = np.array([7, 8], dtype=np.uint32)
