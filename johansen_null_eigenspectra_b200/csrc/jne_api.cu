@@ -61,7 +61,7 @@ struct Device {
 }  // namespace
 
 struct jne_ctx {
-  bool use_aux = true;        // trend moments through the MMA for dim <= 4 and 9..12 (env JNE_AUX=0: scalar FP64 sums)
+  bool use_aux = true;        // trend moments through the MMA for dim <= 6 and 9..12 (env JNE_AUX=0: scalar FP64 sums)
   std::mutex aux_mu;
   int kernel_family = 1;   // 1: tensor path, one warp per run start to end; 2: FMA-tiled path for 9 <= dim <= 12 (env JNE_KERNEL=v2);
                            // 3: tensor path with producer / consumer warps for dim <= 12 (env JNE_KERNEL=ws)

@@ -399,7 +399,7 @@ def test_warp_specialised_kernel_family():
     warps compute the very values the default family computes in place, so every record must be bit-identical to
     the default family with the same trend-moment arithmetic (JNE_AUX=0: scalar FP64 sums) -- for partial CTAs
     (fewer runs than consumer warps), several runs per consumer warp, ragged T, all models.  Against the default
-    family's AUX kernels (trend moments through the MMA, dim <= 4 and 9..12) the records agree to the gate-1
+    family's AUX kernels (trend moments through the MMA, dim <= 6 and 9..12) the records agree to the gate-1
     tolerance."""
     import os, subprocess, sys, textwrap
     code = textwrap.dedent('''
