@@ -147,6 +147,12 @@ int jne_percentiles_device(jne_ctx* ctx, const void* d_eigs, uint64_t n, uint32_
 int jne_simulate_percentiles(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, uint32_t first_seed,
                              uint64_t n, const double* qs, uint32_t n_q, double* trace_out, double* maxeig_out);
 
+/* The same for every model selected in model_mask from ONE fused pass over the seeds (rows f2 x f3: the CLI prints
+ * these statistics after each model of its loop, src/main.rs:117-126).  trace_out / maxeig_out: n_q doubles per
+ * selected model, models in ascending order. */
+int jne_simulate_percentiles_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps, uint32_t first_seed,
+                                   uint64_t n, const double* qs, uint32_t n_q, double* trace_out, double* maxeig_out);
+
 /* ---- orchestration helper (C++ mirror in csrc/jne_host.hpp) -------------------------------------- */
 
 /* run_model_simulation (src/data_storage/parallel_compute.rs:150-232) for one (model, dim, steps, num_runs) job:

@@ -52,6 +52,7 @@ def _load() -> C.CDLL:
         "jne_eigs_batch_debug": (C.c_int, [vp, u8, u32, u32, vp, u64, vp, vp]),
         "jne_percentiles_device": (C.c_int, [vp, vp, u64, u32, u32, vp, u32, vp, vp, vp]),
         "jne_simulate_percentiles": (C.c_int, [vp, u8, u32, u32, u32, u64, vp, u32, vp, vp]),
+        "jne_simulate_percentiles_multi": (C.c_int, [vp, u32, u32, u32, u32, u64, vp, u32, vp, vp]),
         "jne_run_model_simulation": (C.c_int, [vp, u8, u32, u32, u64, C.c_char_p, C.c_int, ip, C.c_int, C.POINTER(u64)]),
         "jne_fp64_peak_tflops": (C.c_int, [vp, C.c_int, dbl, C.POINTER(dbl)]),
         "jne_launch_count": (u64, [vp]),
@@ -303,6 +304,15 @@ class Engine:
         self._check(lib.jne_simulate_percentiles(self._ctx, _model_number(model), dim, steps, first_seed, num_runs,
                                                  qs.ctypes.data, qs.size, tr.ctypes.data, mx.ctypes.data))
         return tr, mx
+
+    def simulate_percentiles_multi(self, models, dim: int, steps: int, num_runs: int, percentiles, first_seed: int = 1):
+        """{model: (trace percentiles, max-eig percentiles)} for every model in `models` from one fused pass."""
+        models = sorted(_model_number(m) for m in models)
+        qs = np.ascontiguousarray(percentiles, dtype=np.float64)
+        tr = np.empty((len(models), qs.size)); mx = np.empty((len(models), qs.size))
+        self._check(lib.jne_simulate_percentiles_multi(self._ctx, self._mask(models), dim, steps, first_seed, num_runs,
+                                                       qs.ctypes.data, qs.size, tr.ctypes.data, mx.ctypes.data))
+        return {m: (tr[i], mx[i]) for i, m in enumerate(models)}
 
     def percentiles_device(self, d_eigs_ptr: int, n: int, p: int, stride: int, percentiles, stream_ptr: int = 0):
         qs = np.ascontiguousarray(percentiles, dtype=np.float64)

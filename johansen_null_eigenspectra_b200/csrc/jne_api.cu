@@ -1044,6 +1044,61 @@ int jne_simulate_percentiles(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t
   return rc;
 }
 
+int jne_simulate_percentiles_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps, uint32_t first_seed,
+                                   uint64_t n, const double* qs, uint32_t nq, double* trace_out, double* maxeig_out) {
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  join_worker(ctx);
+  if (model_mask == 0 || model_mask > 31u) return fail(ctx, JNE_ERR_INVALID_ARG, "model_mask must select models 0..4");
+  for (int m = 0; m < 5; ++m)
+    if ((model_mask >> m) & 1u) { int rc = validate(ctx, (uint8_t)m, dim, steps); if (rc) return rc; }
+  if (!qs || !trace_out || !maxeig_out || nq < 1) return fail(ctx, JNE_ERR_INVALID_ARG, "jne_simulate_percentiles_multi: bad arguments");
+  if ((uint64_t)first_seed + n > (1ull << 32)) return fail(ctx, JNE_ERR_INVALID_ARG, "seed range exceeds u32");
+  Device& dv = ctx->devs[0];
+  JNE_CUDA(ctx, cudaSetDevice(dv.id));
+  JneRunParams prm = make_params_mask(model_mask, dim, steps, false);
+  prm.jtab = jtab_for(dv, dim);
+  const int nm = __builtin_popcount(model_mask);
+  const uint64_t chunk = 1ull << 19, n1 = std::max<uint64_t>(n, 1);
+  double* d_agg = nullptr;     // per selected model: trace[n] + sort space[n] + max[n] + sort space[n]
+  uint32_t* d_seeds = nullptr;
+  double* d_eigs = nullptr;
+  JNE_CUDA(ctx, cudaMalloc(&d_agg, (size_t)nm * 4 * n1 * sizeof(double)));
+  JNE_CUDA(ctx, cudaMalloc(&d_seeds, chunk * sizeof(uint32_t)));
+  JNE_CUDA(ctx, cudaMalloc(&d_eigs, chunk * prm.out_stride * sizeof(double)));
+  auto body = [&]() -> int {
+    JNE_CUDA(ctx, cudaMemsetAsync(dv.d_err, 0, sizeof(unsigned int), dv.stream));
+    for (uint64_t off = 0; off < n; off += chunk) {
+      const uint64_t m = std::min(chunk, n - off);
+      jne_iota_kernel<<<(unsigned)((m + 255) / 256), 256, 0, dv.stream>>>(first_seed + (uint32_t)off, m, d_seeds);
+      JNE_CUDA(ctx, launch_run<true>(ctx, dv, d_seeds, nullptr, m, prm, d_eigs, dv.d_err, nullptr, dv.stream));
+      ctx->launches.fetch_add(2);
+      uint32_t col = 0;
+      int slot = 0;
+      for (int mod = 0; mod < 5; ++mod) {          // one Brownian path per seed serves every selected model
+        if (!((model_mask >> mod) & 1u)) continue;
+        const uint32_t p = (mod == 1 || mod == 3) ? dim + 1 : dim;
+        double* agg = d_agg + (size_t)slot * 4 * n1;
+        jne_aggregate_kernel<<<(unsigned)((m + 255) / 256), 256, 0, dv.stream>>>(d_eigs + col, m, p, prm.out_stride, agg + off, agg + 2 * n1 + off);
+        ctx->launches.fetch_add(1);
+        col += p; ++slot;
+      }
+      JNE_CUDA(ctx, cudaGetLastError());
+    }
+    JNE_CUDA(ctx, cudaMemcpyAsync(dv.h_err, dv.d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, dv.stream));
+    JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+    if (*dv.h_err) return fail(ctx, JNE_ERR_NONFINITE, "non-finite eigenvalues");
+    for (int slot = 0; slot < nm; ++slot) {
+      double* agg = d_agg + (size_t)slot * 4 * n1;
+      const int rc = percentiles_of(ctx, dv, agg, agg + 2 * n1, n, qs, nq, trace_out + (size_t)slot * nq, maxeig_out + (size_t)slot * nq, dv.stream);
+      if (rc) return rc;
+    }
+    return JNE_OK;
+  };
+  const int rc = body();
+  cudaFree(d_agg); cudaFree(d_seeds); cudaFree(d_eigs);
+  return rc;
+}
+
 int jne_fp64_peak_tflops(jne_ctx* ctx, int mode, double ms_target, double* tflops) {
   if (!ctx || !tflops) return JNE_ERR_INVALID_ARG;
   join_worker(ctx);

@@ -106,6 +106,16 @@ def test_streaming_percentiles(engine):
         d = torch.from_numpy(ev).cuda()
         tr2, mx2 = engine.percentiles_device(d.data_ptr(), n, ev.shape[1], ev.shape[1], qs, torch.cuda.current_stream().cuda_stream)
         assert np.array_equal(tr2, tr) and np.array_equal(mx2, mx)
+    # every model of a fused pass: identical to the per-model calls (rows f2 x f3)
+    qs2 = [0.5, 0.9, 0.95, 0.99]
+    both = engine.simulate_percentiles_multi(range(5), 5, 120, 20011, qs2)
+    for m in range(5):
+        tr1, mx1 = engine.simulate_percentiles(m, 5, 120, 20011, qs2)
+        assert np.array_equal(both[m][0], tr1) and np.array_equal(both[m][1], mx1)
+    part = engine.simulate_percentiles_multi([1, 4], 12, 64, 3000, qs2, first_seed=7)
+    for m in (1, 4):
+        tr1, mx1 = engine.simulate_percentiles(m, 12, 64, 3000, qs2, first_seed=7)
+        assert np.array_equal(part[m][0], tr1) and np.array_equal(part[m][1], mx1)
     # a different first seed selects a different sample (seeds 101..200 == the tail of 1..200)
     ev = engine.eigs_batch(2, 4, 150, np.arange(101, 201, dtype=np.uint32))
     tr, mx = engine.simulate_percentiles(2, 4, 150, 100, [0.5], first_seed=101)
