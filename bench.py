@@ -289,11 +289,14 @@ def main():
     #      resume scan, GPU batches, batched EIGENVALS_V6 encode + write of five files, trailers ----
     dat_value = None
     dat_bytes = 0
+    dat_error = None
     if rank == 0 and not args.no_dat:
         import shutil, tempfile
         from johansen_null_eigenspectra_b200 import dat as jdat
         n_dat = R * max(1, args.steps)
-        tmpdir = tempfile.mkdtemp(prefix="jne_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        need_bytes = n_dat * (width * 8 + 5 * 6) * 2          # five files plus head-room
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > need_bytes else None
+        tmpdir = tempfile.mkdtemp(prefix="jne_bench_", dir=base)
         try:
             names = {m: os.path.join(tmpdir, f"eigenvalues_model{m}_dim{dim}_steps{T}.dat") for m in MODELS}
             d0 = time.perf_counter()
@@ -302,6 +305,8 @@ def main():
             assert all(st[m]["total_in_file"] == n_dat for m in MODELS)
             dat_bytes = sum(os.path.getsize(f) for f in names.values())
             dat_value = len(MODELS) * n_dat / dat_s
+        except Exception as exc:                                # a full scratch disk must not take the bench line down
+            dat_error = f"{type(exc).__name__}: {exc}"
         finally:
             shutil.rmtree(tmpdir, ignore_errors=True)
     h2d = 4 * R
@@ -362,11 +367,13 @@ def main():
             "gpu_launches": int(gpu_launches),
             "clocks": clocks.summary(),
         }
+        if dat_error is not None:
+            line["e2e_dat"] = {"value": None, "unit": "runs/s", "error": dat_error}
         if dat_value is not None:
             line["e2e_dat"] = {
                 "value": dat_value, "unit": "runs/s", "file_bytes": dat_bytes,
                 "note": f"rank 0: run_models_simulation of {R * max(1, args.steps)} seeds x 5 models into five EIGENVALS_V6 files "
-                        "(tmpfs), resume scan + GPU + batched encode/write + trailers inside",
+                        "(tmpfs when it has room, else the temp dir), resume scan + GPU + batched encode/write + trailers inside",
             }
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
