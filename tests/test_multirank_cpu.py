@@ -50,3 +50,23 @@ def test_two_rank_sharding_and_max_timing():
     assert tmax == 2.0                                   # max over ranks, not rank 0's own time
     assert bounds[0][:2] == (0, 501) and bounds[1][:2] == (501, 1001)
     assert bounds[0][2:] == (1, 50) and bounds[1][2:] == (51, 100)   # disjoint seed ranges, union 1..100
+
+
+def test_reference_arm_runs_without_gpu():
+    """bench.py --impl reference times the CPU port of the reference path (oracle/jne_oracle.c) and needs no GPU:
+    one JSON line with the contract's keys; under torchrun only rank 0 prints."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-runs", "32"],
+                       cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "runs/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "runs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and "dim 12" in d["config"]["workload"]
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-runs", "32"],
+                       cwd=root, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
