@@ -238,9 +238,9 @@ def test_mhm_critical_values_gpu(engine):
 
 
 def test_trace_critical_values_all_dims(engine):
-    """The product's purpose end to end: the 95 % quantile of the trace statistic from the fused pass at the metric's
-    horizon (T = 10 000), models 0-4, dim 1..12, against the published asymptotic critical values of MacKinnon, Haug &
-    Michelis (1999) (cases I-V, as printed by standard econometrics packages).  200 000 runs per cell: Monte Carlo
+    """The product's purpose end to end: the 95 % quantiles of the trace and maximum-eigenvalue statistics from the fused
+    pass at the metric's horizon (T = 10 000), models 0-4, dim 1..12, against the published asymptotic critical values of
+    MacKinnon, Haug & Michelis (1999) (cases I-V, as printed by standard econometrics packages).  200 000 runs per cell: Monte Carlo
     error ~0.15 %, finite-T bias up to -0.2 % (profiles/r1_validation_trace_quantiles.txt has the 10^6-run table:
     every cell within 0.19 %); window 0.7 %."""
     import torch
@@ -251,6 +251,13 @@ def test_trace_critical_values_all_dims(engine):
         2: [3.841466, 15.49471, 29.79707, 47.85613, 69.81889, 95.75366, 125.6154, 159.5297, 197.3709, 239.2354, 285.1425, 334.9837],
         3: [12.51798, 25.87211, 42.91525, 63.87610, 88.80380, 117.7082, 150.5585, 187.4701, 228.2979, 273.1889, 322.0692, 374.9076],
         4: [3.841466, 18.39771, 35.01090, 55.24578, 79.34145, 107.3466, 139.2753, 175.1715, 215.1232, 259.0294, 306.8944, 358.7184],
+    }
+    mhm95_max = {
+        0: [4.129906, 11.22480, 17.79730, 24.15921, 30.43961, 36.63019, 42.77219, 48.87720, 54.96577, 61.03407, 67.07555, 73.09094],
+        1: [9.164546, 15.89210, 22.29962, 28.58808, 34.80587, 40.95680, 47.07897, 53.18784, 59.24000, 65.30016, 71.33542, 77.38180],
+        2: [3.841466, 14.26460, 21.13162, 27.58434, 33.87687, 40.07757, 46.23142, 52.36261, 58.43354, 64.50472, 70.53513, 76.57843],
+        3: [12.51798, 19.38704, 25.82321, 32.11832, 38.33101, 44.49720, 50.59985, 56.70519, 62.75215, 68.81206, 74.83748, 80.87025],
+        4: [3.841466, 17.14769, 24.25202, 30.81507, 37.16359, 43.41977, 49.58633, 55.72819, 61.80550, 67.90393, 73.94036, 79.97193],
     }
     n, T = 200_000, 10_000
     st = torch.cuda.current_stream()
@@ -263,8 +270,10 @@ def test_trace_critical_values_all_dims(engine):
         off = 0
         for m in range(5):
             q = float(torch.quantile(out[:, off:off + widths[m]].sum(dim=1), 0.95))
+            qmax = float(torch.quantile(out[:, off], 0.95))           # rows are descending: first entry = maximum
             off += widths[m]
             assert abs(q / mhm95[m][dim - 1] - 1.0) < 0.007, (m, dim, q, mhm95[m][dim - 1])
+            assert abs(qmax / mhm95_max[m][dim - 1] - 1.0) < 0.007, (m, dim, qmax, mhm95_max[m][dim - 1])
 
 
 def test_full_size_properties(engine):
