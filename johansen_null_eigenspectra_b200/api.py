@@ -206,15 +206,18 @@ class Engine:
             mask |= 1 << _model_number(m)
         return mask
 
-    def eigs_batch_multi(self, models, dim: int, steps: int, seeds) -> dict:
-        """One pass over each seed's Brownian path for all `models`; {model: (n, p) float64}."""
+    def eigs_batch_multi(self, models, dim: int, steps: int, seeds, out: Optional[np.ndarray] = None) -> dict:
+        """One pass over each seed's Brownian path for all `models`; {model: (n, p) float64} (views of one (n, width)
+        array; pass `out` to reuse a caller-owned buffer)."""
         seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
         models = sorted({_model_number(m) for m in models})
         mask = self._mask(models)
         width = lib.jne_multi_width(mask, dim)
         if width < 0:
             raise JneError(width, "invalid model mask / dim")
-        out = np.empty((seeds.size, width), dtype=np.float64)
+        if out is None:
+            out = np.empty((seeds.size, width), dtype=np.float64)
+        assert out.shape == (seeds.size, width) and out.dtype == np.float64 and out.flags.c_contiguous
         self._check(lib.jne_eigs_batch_multi(self._ctx, mask, dim, steps, seeds.ctypes.data, seeds.size,
                                              out.ctypes.data))
         res, off = {}, 0
