@@ -81,6 +81,7 @@ int jne_eigs_batch_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32
 int jne_eigs_batch_multi_device(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps,
                                 const void* d_seeds, uint64_t n, void* d_out, void* stream);
 int jne_multi_width(uint32_t model_mask, uint32_t dim);   /* sum of jne_num_eigs over the selected models */
+int jne_ctx_device_count(const jne_ctx* ctx);             /* devices this context shards its batches over */
 
 /* Asynchronous pair: jne_submit enqueues the batch (seeds are copied before it returns; `out`
  * must stay valid until jne_wait) and returns a ticket > 0, or a negative status.  jne_wait

@@ -48,6 +48,10 @@ int jne_dat_append_batch(jne_dat_writer* w, const uint32_t* seeds, const double*
  * multi-model batch (jne_eigs_batch_multi) without a de-interleaving copy.  stride >= p. */
 int jne_dat_append_batch_strided(jne_dat_writer* w, const uint32_t* seeds, const double* eigs, uint64_t n, uint32_t p,
                                  uint64_t stride);
+/* The same with the records encoded by `threads` host threads (contiguous ranges, written in order): one core encodes
+ * about 10^7 records/s, a multi-GPU context produces several times that per file.  Same bytes as the serial call. */
+int jne_dat_append_batch_strided_mt(jne_dat_writer* w, const uint32_t* seeds, const double* eigs, uint64_t n, uint32_t p,
+                                    uint64_t stride, int threads);
 
 /* Flush buffered records to the OS (the reference flushes every 10 000 records, config.rs:5). */
 int jne_dat_flush(jne_dat_writer* w);

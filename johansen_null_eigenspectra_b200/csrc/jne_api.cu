@@ -712,6 +712,8 @@ int jne_eigs_batch_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32
   return eigs_batch_sync(ctx, model_mask, dim, steps, seeds, n, out);
 }
 
+int jne_ctx_device_count(const jne_ctx* ctx) { return ctx ? (int)ctx->devs.size() : JNE_ERR_INVALID_ARG; }
+
 int jne_multi_width(uint32_t model_mask, uint32_t dim) {
   if (model_mask == 0 || model_mask > 31u || dim < 1 || dim > 255) return JNE_ERR_INVALID_ARG;
   return (int)mask_width(model_mask, dim);

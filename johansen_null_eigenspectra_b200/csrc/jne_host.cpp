@@ -111,7 +111,10 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
     if (rc != JNE_OK) { const std::string msg = jne_dat_last_error(); abandon_all(); throw Error(rc, msg); }
   }
   // ---- one fused pass per distinct set of lacking models, double-buffered against the writers ----
-  const size_t chunk = 1u << 16;      // ~20 ms of GPU work at dim 12, T 10 000: short tail, writers well ahead
+  // ~20 ms of GPU work per device at dim 12, T 10 000: short tail, writers well ahead
+  const int n_dev = std::max(1, jne_ctx_device_count(gpu.ctx()));
+  const size_t chunk_max = (size_t)(1u << 16) * (size_t)n_dev;
+  const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
   std::vector<double> buf[2];
   // seeds by the set of models that lack them, one pass (ascending within a group)
   std::vector<uint32_t> groups[32];
@@ -127,6 +130,8 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
     for (uint32_t mask = 1; mask < 32; ++mask) {
       const std::vector<uint32_t>& seeds = groups[mask];
       if (seeds.empty()) continue;
+      // at least four chunks per group, so that the writers overlap the devices in small jobs as well
+      const size_t chunk = std::min(chunk_max, std::max<size_t>(1u << 16, (seeds.size() + 3) / 4));
       const uint32_t width = (uint32_t)jne_multi_width(mask, dim);
       uint32_t off[5], pm[5];
       { uint32_t o = 0; for (int m = 0; m < 5; ++m) { pm[m] = (uint32_t)Model((uint8_t)m).num_eigs(dim); off[m] = o; if ((mask >> m) & 1u) o += pm[m]; } }
@@ -148,7 +153,9 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
           for (int m = 0; m < 5; ++m) {
             if (!((mask >> m) & 1u)) continue;
             th[m] = std::thread([&, m]() {
-              rcs[m] = jne_dat_append_batch_strided(w[m], seeds.data() + prev_a, rows + off[m], prev_n, pm[m], width);
+              // encoders per file: what the host has beyond one thread per file, as far as the devices need it
+              const int enc = std::max(1, std::min({4, n_dev, hw / (2 * __builtin_popcount(mask))}));
+              rcs[m] = jne_dat_append_batch_strided_mt(w[m], seeds.data() + prev_a, rows + off[m], prev_n, pm[m], width, enc);
               if (rcs[m] != JNE_OK) errs[m] = jne_dat_last_error();
             });
           }

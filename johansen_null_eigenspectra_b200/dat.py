@@ -53,6 +53,8 @@ lib.jne_run_model_simulation.argtypes = [_vp, C.c_uint8, C.c_uint32, C.c_uint32,
 lib.jne_run_models_simulation.restype = C.c_int
 lib.jne_run_models_simulation.argtypes = [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_char_p), C.c_int,
                                           C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_uint64)]
+lib.jne_dat_append_batch_strided_mt.restype = C.c_int
+lib.jne_dat_append_batch_strided_mt.argtypes = [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int]
 lib.jne_dat_append_batch_strided.restype = C.c_int
 lib.jne_dat_append_batch_strided.argtypes = [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint64]
 
@@ -103,13 +105,14 @@ class AppendOnlyWriter:
         assert eigs.shape[0] == seeds.size
         _check(lib.jne_dat_append_batch(self._w, seeds.ctypes.data, eigs.ctypes.data, seeds.size, eigs.shape[1]))
 
-    def append_batch_strided(self, seeds, rows, offset: int, p: int) -> None:
-        """Append columns [offset, offset + p) of the C-contiguous rows of a fused multi-model batch."""
+    def append_batch_strided(self, seeds, rows, offset: int, p: int, threads: int = 1) -> None:
+        """Append columns [offset, offset + p) of the C-contiguous rows of a fused multi-model batch
+        (threads > 1: records encoded by that many host threads, same bytes)."""
         seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
         rows = np.ascontiguousarray(rows, dtype=np.float64)
         assert rows.ndim == 2 and rows.shape[0] == seeds.size and offset + p <= rows.shape[1]
-        _check(lib.jne_dat_append_batch_strided(self._w, seeds.ctypes.data, rows.ctypes.data + 8 * offset, seeds.size, p,
-                                                rows.shape[1]))
+        _check(lib.jne_dat_append_batch_strided_mt(self._w, seeds.ctypes.data, rows.ctypes.data + 8 * offset, seeds.size, p,
+                                                   rows.shape[1], int(threads)))
 
     def append_eigenvalues(self, seed: int, eigenvalues) -> None:   # the reference's per-record call
         self.append_batch([seed], np.asarray(eigenvalues, dtype=np.float64)[None, :])

@@ -175,6 +175,15 @@ def test_strided_append_matches_contiguous(tmp_path):
         w = dat.AppendOnlyWriter(a, model, 12, 50); w.append_batch_strided(seeds, rows, off, p); w.finish()
         w = dat.AppendOnlyWriter(b, model, 12, 50); w.append_batch(seeds, rows[:, off:off + p].copy()); w.finish()
         assert a.read_bytes() == b.read_bytes()
+    # encoded by several threads: same bytes
+    big_n = 50_000
+    big = rng.standard_normal((big_n, width)); big_seeds = rng.permutation(np.arange(1, big_n + 1)).astype(np.uint32)
+    for threads in (1, 3, 8):
+        f = tmp_path / f"mt{threads}.dat"
+        w = dat.AppendOnlyWriter(f, 1, 12, 50); w.append_batch_strided(big_seeds, big, 12, 13, threads=threads); w.finish()
+    assert (tmp_path / "mt1.dat").read_bytes() == (tmp_path / "mt3.dat").read_bytes() == (tmp_path / "mt8.dat").read_bytes()
+    s2, e2, *_ = dat.read_append_file(tmp_path / "mt8.dat")
+    assert np.array_equal(s2, big_seeds) and np.array_equal(e2, big[:, 12:25])
     w = dat.AppendOnlyWriter(tmp_path / "c.dat", 0, 2, 5)
     rc = dat.lib.jne_dat_append_batch_strided(w._w, seeds.ctypes.data, rows.ctypes.data, 10, 3, 2)
     assert rc < 0 and b"stride" in dat.lib.jne_dat_last_error()

@@ -3,10 +3,12 @@ import os, shutil, sys, tempfile, time
 sys.path.insert(0, ".")
 import johansen_null_eigenspectra_b200 as jne
 from johansen_null_eigenspectra_b200 import dat
-eng = jne.Engine([0])
+import torch
+eng = jne.Engine(list(range(torch.cuda.device_count())))
+print("devices:", torch.cuda.device_count())
 base = "/dev/shm" if os.path.isdir("/dev/shm") else None
 print("tmpfs free GB:", shutil.disk_usage(base or "/tmp").free / 1e9)
-for n in (133200, 666000, 2000000):
+for n in (666000, 2000000, 8000000):
     d = tempfile.mkdtemp(prefix="jne_job_", dir=base)
     try:
         names = {m: os.path.join(d, f"eigenvalues_model{m}_dim12_steps10000.dat") for m in range(5)}
