@@ -34,7 +34,9 @@ typedef enum jne_status {
   JNE_ERR_NONFINITE = -3,    /* a run produced a NaN/Inf eigenvalue; the reference panics at
                                 src/johansen_statistics.rs:45 (partial_cmp().unwrap()) */
   JNE_ERR_UNSUPPORTED = -4,  /* dim > JNE_MAX_DIM */
-  JNE_ERR_IO = -5            /* .dat writer / reader failures (jne_dat_* functions) */
+  JNE_ERR_IO = -5,           /* .dat writer / reader failures (jne_dat_* functions) */
+  JNE_ERR_INTERNAL = -6      /* host-side failure inside the library (out of memory, a thread could not be started):
+                                caught at the boundary, never thrown across it */
 } jne_status;
 
 #define JNE_MAX_DIM 15

@@ -361,9 +361,18 @@ def calculate_eigenvalues_parallel(dim: int, steps: int, seeds: Iterable[int], m
         chunk = seeds[a:a + batch]
         out = np.empty((chunk.size, p), dtype=np.float64)
         ticket = eng.submit(model, dim, steps, chunk, out)
-        if prev is not None:
-            for s, row in zip(prev[0].tolist(), prev[1]):
-                sender(s, row.tolist())
+        try:
+            if prev is not None:
+                for s, row in zip(prev[0].tolist(), prev[1]):
+                    sender(s, row.tolist())
+        except BaseException:
+            # the worker still writes into `out`: join it before the array can be collected, and leave the engine
+            # without a pending ticket
+            try:
+                eng.wait(ticket)
+            except JneError:
+                pass
+            raise
         eng.wait(ticket)
         prev = (chunk, out)
     if prev is not None:

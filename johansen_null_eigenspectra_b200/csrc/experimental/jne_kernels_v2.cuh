@@ -14,7 +14,7 @@
 // jne_kernels.cuh) and jne_solve_kernel runs the per-model assembly + Cholesky/Jacobi solve at full occupancy.
 // The random stream is the same function of (seed, row, step) as everywhere else.
 #pragma once
-#include "jne_kernels.cuh"
+#include "../jne_kernels.cuh"
 
 #define JNE_MOM_DOUBLES (2 * 256 + 6 * 16)   // MBB[16][16], MBZ[16][16], tot[6][16]
 #ifndef JNE_V2_WARPS

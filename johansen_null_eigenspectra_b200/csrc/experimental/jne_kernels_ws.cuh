@@ -17,7 +17,7 @@
 // stream every IMAD.WIDE of a producer waits for about one DMMA slot, whichever warp issues it.  Not the default
 // (JNE_KERNEL=ws selects it).
 #pragma once
-#include "jne_kernels.cuh"
+#include "../jne_kernels.cuh"
 
 #ifndef JNE_WS_CONS
 #define JNE_WS_CONS 20        // consumer warps per CTA: 5 per SM sub-partition

@@ -10,6 +10,7 @@
 #include <memory>
 #include <map>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -18,16 +19,23 @@
 
 #include "../../include/jne.h"
 #include "jne_kernels.cuh"
-#include "jne_kernels_v2.cuh"
-#include "jne_kernels_ws.cuh"
+#include "jne_kernels_lane.cuh"
+#ifdef JNE_EXPERIMENTAL_FAMILIES   // measured-slower formulations kept for regression experiments (build.py --experimental)
+#include "experimental/jne_kernels_v2.cuh"
+#include "experimental/jne_kernels_ws.cuh"
+#endif
 
 #define JNE_VERSION_STR "jne-b200 0.1.0 (sm_100a)"
 
 namespace {
 
-constexpr uint64_t kChunkRuns = 1ull << 15;   // capacity of a staging slot, in runs
-constexpr uint64_t kChunkTarget = 1ull << 13; // runs per launch on the host-buffer path (D2H of chunk i overlaps the kernel of chunk i+1)
+constexpr uint64_t kSlotSeeds = 1ull << 17;   // capacity of a staging slot, in runs (seed buffer) ...
 constexpr uint64_t kMaxWidth = 5 * 16;        // doubles per run: all five models at dim 15
+constexpr uint64_t kSlotDoubles = (1ull << 15) * kMaxWidth;   // ... and in eigenvalues (21 MB): 2^15 runs at the widest row,
+                                                               // 2^17 runs up to 20 doubles per run
+constexpr uint64_t kChunkTarget = 1ull << 13; // runs per launch on the host-buffer path (D2H of chunk i overlaps the kernel of chunk i+1)
+
+inline uint64_t slot_runs(uint32_t width) { return std::min<uint64_t>(kSlotSeeds, kSlotDoubles / std::max<uint32_t>(width, 1)); }
 
 std::mutex g_init_err_mu;
 std::string g_init_err;
@@ -50,8 +58,8 @@ struct Device {
   unsigned int* d_err = nullptr;
   unsigned int* h_err = nullptr;  // pinned
   uint32_t* d_jtab = nullptr;   // 8 Jacobi step tables (ne = 2, 4, .., 16), kTabWords words each
-  double* d_mom[2] = {nullptr, nullptr};   // v2 path: per-run moments between jne_moments12_kernel and jne_solve_kernel,
-  uint64_t mom_runs[2] = {0, 0};           // one buffer per concurrently used stream (capacity in runs)
+  double* d_mom[2] = {nullptr, nullptr};   // lane family: per-run moments between the moments and the solve kernel,
+  size_t mom_doubles[2] = {0, 0};          // one buffer per concurrently used stream (capacity in doubles)
   int sm_count = 0;
   std::map<uint32_t, double*> aux_tabs;   // trend-weight tables of the AUX kernels, by steps (make_aux_table)
   double* d_scratch = nullptr;    // increments / pencil inputs, grown on demand
@@ -63,8 +71,10 @@ struct Device {
 struct jne_ctx {
   bool use_aux = true;        // trend moments through the MMA for dim <= 6 and 9..12 (env JNE_AUX=0: scalar FP64 sums)
   std::mutex aux_mu;
-  int kernel_family = 1;   // 1: tensor path, one warp per run start to end; 2: FMA-tiled path for 9 <= dim <= 12 (env JNE_KERNEL=v2);
-                           // 3: tensor path with producer / consumer warps for dim <= 12 (env JNE_KERNEL=ws)
+  int kernel_family = 1;   // 1: production dispatch (lane family for dim <= 6, tensor family above);
+                           // experimental builds only (JNE_EXPERIMENTAL_FAMILIES): 2 = FMA-tiled path for 9 <= dim <= 12
+                           // (env JNE_KERNEL=v2), 3 = producer / consumer warps for dim <= 12 (env JNE_KERNEL=ws)
+  bool use_lane = true;    // env JNE_LANE=0: tensor family for every dim (regression tooling)
   std::vector<Device> devs;
   std::string err;
   std::mutex err_mu;
@@ -248,6 +258,7 @@ cudaError_t launch_det(int det, const uint32_t* s, const double* b, uint64_t n, 
   }
 }
 
+#ifdef JNE_EXPERIMENTAL_FAMILIES
 // warp-specialised persistent kernel (jne_kernels_ws.cuh): one CTA per SM, RNG path, dim <= 12
 template <int DP, int DET, bool MULTI>
 cudaError_t launch_ws_one(const Device& dv, const uint32_t* d_seeds, uint64_t n, const JneRunParams& prm, double* d_out,
@@ -271,6 +282,8 @@ cudaError_t launch_ws(const Device& dv, const uint32_t* s, uint64_t n, const Jne
     default: return launch_ws_one<DP, 2, false>(dv, s, n, prm, o, e, st);
   }
 }
+
+#endif  // JNE_EXPERIMENTAL_FAMILIES
 
 // Runs in one full wave of the kernel launch_run would pick for prm (resident CTAs per SM x SMs x runs per CTA):
 // the host-buffer path sizes its chunks in whole waves so that a chunk does not end on a mostly empty wave.
@@ -321,8 +334,116 @@ const double* aux_table_for(jne_ctx* ctx, Device& dv, uint32_t steps) {
   return d;
 }
 
-constexpr uint64_t kMomChunk = 1ull << 18;   // runs per v2 moments/solve pair (1.27 GB of moments)
+// ---- lane family (jne_kernels_lane.cuh): dim <= 6, one thread per run + one warp per run for the solve ----
+constexpr uint64_t kMomChunk = 1ull << 18;   // upper bound on the runs per moments / solve pair (195 MB of moments at dim 6)
 
+bool lane_wanted(const jne_ctx* ctx, const JneRunParams& prm) {
+  return ctx->use_lane && ctx->kernel_family == 1 && prm.dim <= JNE_LANE_MAX_DIM;
+}
+int lane_det(const JneRunParams& prm) {
+  const bool multi = (prm.model_mask & (prm.model_mask - 1u)) != 0;
+  return multi ? 2 : ((prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2));
+}
+
+template <int D, bool RNG>
+cudaError_t launch_lane_moments(int det, const uint32_t* s, const double* b, uint64_t m, uint32_t steps, double* mom, cudaStream_t st) {
+  constexpr int TH = JneLaneGeo<D>::THREADS;
+  const unsigned grid = (unsigned)((m + TH - 1) / TH);
+  if constexpr (RNG) {
+    switch (det) {
+      case 0: jne_lane_moments_kernel<D, 0, true><<<grid, TH, 0, st>>>(s, b, m, steps, mom); break;
+      case 1: jne_lane_moments_kernel<D, 1, true><<<grid, TH, 0, st>>>(s, b, m, steps, mom); break;
+      default: jne_lane_moments_kernel<D, 2, true><<<grid, TH, 0, st>>>(s, b, m, steps, mom); break;
+    }
+  } else {   // caller increments (parity gate 1): one instantiation, the superset of the trend sums
+    jne_lane_moments_kernel<D, 2, false><<<grid, TH, 0, st>>>(s, b, m, steps, mom);
+  }
+  return cudaGetLastError();
+}
+template <bool RNG>
+cudaError_t launch_lane_moments_dim(uint32_t dim, int det, const uint32_t* s, const double* b, uint64_t m, uint32_t steps,
+                                    double* mom, cudaStream_t st) {
+  switch (dim) {
+    case 1: return launch_lane_moments<1, RNG>(det, s, b, m, steps, mom, st);
+    case 2: return launch_lane_moments<2, RNG>(det, s, b, m, steps, mom, st);
+    case 3: return launch_lane_moments<3, RNG>(det, s, b, m, steps, mom, st);
+    case 4: return launch_lane_moments<4, RNG>(det, s, b, m, steps, mom, st);
+    case 5: return launch_lane_moments<5, RNG>(det, s, b, m, steps, mom, st);
+    default: return launch_lane_moments<6, RNG>(det, s, b, m, steps, mom, st);
+  }
+}
+template <int DP, bool MULTI>
+cudaError_t launch_lane_solve(const double* mom, uint64_t m, const JneRunParams& prm, double* o, unsigned int* e, double* dbg,
+                              cudaStream_t st) {
+  auto kern = jne_lane_solve_kernel<DP, MULTI>;
+  cudaError_t rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jne_lane_solve_smem<DP, MULTI>());
+  if (rc != cudaSuccess) return rc;
+  const unsigned grid = (unsigned)((m + JNE_WARPS_PER_CTA - 1) / JNE_WARPS_PER_CTA);
+  kern<<<grid, 32 * JNE_WARPS_PER_CTA, jne_lane_solve_smem<DP, MULTI>(), st>>>(mom, m, prm, o, e, dbg);
+  return cudaGetLastError();
+}
+
+// Runs resident at once in the lane moments kernel (0 if the query fails).
+template <int D> uint64_t lane_wave_one(const Device& dv, int det) {
+  int nb = 0;
+  constexpr int TH = JneLaneGeo<D>::THREADS;
+  cudaError_t rc = det == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, jne_lane_moments_kernel<D, 0, true>, TH, 0)
+                 : det == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, jne_lane_moments_kernel<D, 1, true>, TH, 0)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, jne_lane_moments_kernel<D, 2, true>, TH, 0);
+  if (rc != cudaSuccess) { cudaGetLastError(); return 0; }
+  return (uint64_t)nb * dv.sm_count * TH;
+}
+uint64_t lane_wave(const Device& dv, const JneRunParams& prm) {
+  const int det = lane_det(prm);
+  switch (prm.dim) {
+    case 1: return lane_wave_one<1>(dv, det);
+    case 2: return lane_wave_one<2>(dv, det);
+    case 3: return lane_wave_one<3>(dv, det);
+    case 4: return lane_wave_one<4>(dv, det);
+    case 5: return lane_wave_one<5>(dv, det);
+    default: return lane_wave_one<6>(dv, det);
+  }
+}
+
+// moments kernel + solve kernel per chunk of runs (whole waves of the moments kernel), both on stream st
+template <bool RNG>
+cudaError_t launch_lane(jne_ctx* ctx, Device& dv, const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm,
+                        double* o, unsigned int* e, double* dbg, cudaStream_t st, int ms) {
+  const size_t per_run = (size_t)jne_lane_mom_size((int)prm.dim);
+  uint64_t chunk = kMomChunk;
+  const uint64_t wave = lane_wave(dv, prm);
+  if (wave > 0 && wave <= kMomChunk) chunk = (kMomChunk / wave) * wave;
+  const size_t need = (size_t)std::min<uint64_t>(n, chunk) * per_run;
+  if (dv.mom_doubles[ms] < need) {
+    if (dv.d_mom[ms]) {
+      cudaError_t f = cudaFree(dv.d_mom[ms]);   // (synchronises the device: earlier launches reading it are done)
+      dv.d_mom[ms] = nullptr; dv.mom_doubles[ms] = 0;
+      if (f != cudaSuccess) return f;
+    }
+    cudaError_t a = cudaMalloc(&dv.d_mom[ms], need * sizeof(double));
+    if (a != cudaSuccess) return a;
+    dv.mom_doubles[ms] = need;
+  }
+  double* d_mom = dv.d_mom[ms];
+  const bool multi = (prm.model_mask & (prm.model_mask - 1u)) != 0;
+  const int det = lane_det(prm);
+  for (uint64_t off = 0; off < n; off += chunk) {
+    const uint64_t m = std::min(chunk, n - off);
+    const uint32_t* sp = s ? s + off : nullptr;
+    const double* bp = b ? b + off * (uint64_t)prm.dim * prm.steps : nullptr;
+    cudaError_t rc = launch_lane_moments_dim<RNG>(prm.dim, det, sp, bp, m, prm.steps, d_mom, st);
+    if (rc != cudaSuccess) return rc;
+    double* op = o + off * prm.out_stride;
+    double* dp = dbg ? dbg + off * 512 : nullptr;
+    if (prm.dim <= 4) rc = multi ? launch_lane_solve<4, true>(d_mom, m, prm, op, e, dp, st) : launch_lane_solve<4, false>(d_mom, m, prm, op, e, dp, st);
+    else rc = multi ? launch_lane_solve<8, true>(d_mom, m, prm, op, e, dp, st) : launch_lane_solve<8, false>(d_mom, m, prm, op, e, dp, st);
+    if (rc != cudaSuccess) return rc;
+    ctx->launches.fetch_add(1);   // the solve kernel; the caller counts the moments kernel
+  }
+  return cudaSuccess;
+}
+
+#ifdef JNE_EXPERIMENTAL_FAMILIES
 template <int DET, bool RNG>
 cudaError_t launch_v2_det(const uint32_t* s, const double* b, uint64_t m, const JneRunParams& prm, double* mom, cudaStream_t st) {
   constexpr unsigned runs_per_cta = 8 * JNE_V2_WARPS;
@@ -335,12 +456,12 @@ cudaError_t launch_v2_det(const uint32_t* s, const double* b, uint64_t m, const 
 template <bool RNG>
 cudaError_t launch_v2(jne_ctx* ctx, Device& dv, const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm,
                       double* o, unsigned int* e, double* dbg, cudaStream_t st, int ms) {
-  const uint64_t need = std::min<uint64_t>(n, kMomChunk);
-  if (dv.mom_runs[ms] < need) {
-    if (dv.d_mom[ms]) { cudaError_t f = cudaFree(dv.d_mom[ms]); dv.d_mom[ms] = nullptr; dv.mom_runs[ms] = 0; if (f != cudaSuccess) return f; }
-    cudaError_t a = cudaMalloc(&dv.d_mom[ms], need * JNE_MOM_DOUBLES * sizeof(double));
+  const size_t need = (size_t)std::min<uint64_t>(n, kMomChunk) * JNE_MOM_DOUBLES;
+  if (dv.mom_doubles[ms] < need) {
+    if (dv.d_mom[ms]) { cudaError_t f = cudaFree(dv.d_mom[ms]); dv.d_mom[ms] = nullptr; dv.mom_doubles[ms] = 0; if (f != cudaSuccess) return f; }
+    cudaError_t a = cudaMalloc(&dv.d_mom[ms], need * sizeof(double));
     if (a != cudaSuccess) return a;
-    dv.mom_runs[ms] = need;
+    dv.mom_doubles[ms] = need;
   }
   double* d_mom = dv.d_mom[ms];
   const bool multi = (prm.model_mask & (prm.model_mask - 1u)) != 0;
@@ -370,16 +491,20 @@ cudaError_t launch_v2(jne_ctx* ctx, Device& dv, const uint32_t* s, const double*
   }
   return cudaSuccess;
 }
+#endif  // JNE_EXPERIMENTAL_FAMILIES
 
 template <bool RNG>
 cudaError_t launch_run(jne_ctx* ctx, Device& dv, const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm,
                        double* o, unsigned int* e, double* dbg, cudaStream_t st, int mom_slot = 0) {
+#ifdef JNE_EXPERIMENTAL_FAMILIES
   if (ctx->kernel_family == 2 && prm.dim >= 9 && prm.dim <= 12) return launch_v2<RNG>(ctx, dv, s, b, n, prm, o, e, dbg, st, mom_slot);
   if (RNG && ctx->kernel_family == 3 && prm.dim <= 12 && dbg == nullptr) {
     if (prm.dim <= 4) return launch_ws<4>(dv, s, n, prm, o, e, st);
     if (prm.dim <= 8) return launch_ws<8>(dv, s, n, prm, o, e, st);
     return launch_ws<12>(dv, s, n, prm, o, e, st);
   }
+#endif
+  if (lane_wanted(ctx, prm)) return launch_lane<RNG>(ctx, dv, s, b, n, prm, o, e, dbg, st, mom_slot);
   const int det = (prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2);
   JneRunParams q = prm;
   q.aux_tab = aux_wanted(ctx, prm) ? aux_table_for(ctx, dv, prm.steps) : nullptr;
@@ -390,7 +515,8 @@ cudaError_t launch_run(jne_ctx* ctx, Device& dv, const uint32_t* s, const double
 }
 
 uint64_t wave_runs(const jne_ctx* ctx, const Device& dv, const JneRunParams& prm) {
-  if (ctx->kernel_family != 1) return 0;     // the other families have their own geometry: keep the fixed chunk
+  if (ctx->kernel_family != 1) return 0;     // the experimental families have their own geometry: keep the fixed chunk
+  if (lane_wanted(ctx, prm)) return lane_wave(dv, prm);
   const bool aux = aux_wanted(ctx, prm);
   uint64_t w = prm.dim <= 4 ? wave_det<4>(dv, prm, aux) : prm.dim <= 8 ? wave_det<8>(dv, prm, aux)
              : prm.dim <= 12 ? wave_det<12>(dv, prm, aux) : wave_det<16>(dv, prm, aux);
@@ -423,15 +549,17 @@ int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32
     JneRunParams prm = prm_in;
     prm.jtab = jtab_for(dv, prm.dim);
     *dv.h_err = 0;
+    for (auto& s : dv.slot) s.busy = false;   // nothing of an earlier (possibly failed) call is ever drained into this one
     JNE_CUDA(ctx, cudaMemsetAsync(dv.d_err, 0, sizeof(unsigned int), dv.stream));
     JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
     uint64_t done = 0;
     int which = 0;
     // Chunks are whole waves (a launch does not end on a mostly idle wave) and small (what stays exposed at the end
     // of a call is the last chunk's D2H and the hand-over of the last two chunks to the caller's array).
-    uint64_t chunk = kChunkTarget;
+    const uint64_t cap = slot_runs(prm.out_stride);
+    uint64_t chunk = std::min(kChunkTarget, cap);
     const uint64_t wave = wave_runs(ctx, dv, prm);
-    if (wave > 0 && wave <= kChunkRuns) chunk = std::max<uint64_t>(1, kChunkTarget / wave) * wave;
+    if (wave > 0 && wave <= cap) chunk = std::max<uint64_t>(1, kChunkTarget / wave) * wave;
     while (done < n) {
       Slot& s = dv.slot[which];
       int rc = drain(ctx, s, prm.p, out);
@@ -464,12 +592,18 @@ int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32
   };
   // ctx->err is shared between device threads: serialise through a local copy
   int rc = body();
-  if (rc && err_out) { std::lock_guard<std::mutex> lk(ctx->err_mu); *err_out = ctx->err; }
+  if (rc) {
+    // error exit: let whatever is still in flight on the slots' streams finish (it targets the library's own staging
+    // buffers), and forget it -- a later call must not copy stale rows into its caller's array
+    for (auto& s : dv.slot) { if (s.stream) cudaStreamSynchronize(s.stream); s.busy = false; }
+    cudaGetLastError();
+    if (err_out) { std::lock_guard<std::mutex> lk(ctx->err_mu); *err_out = ctx->err; }
+  }
   return rc;
 }
 
-int eigs_batch_sync(jne_ctx* ctx, uint32_t mask, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
-                    double* out) {
+int eigs_batch_sync_impl(jne_ctx* ctx, uint32_t mask, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
+                         double* out) {
   const JneRunParams prm = make_params_mask(mask, dim, steps, false);
   const size_t nd = ctx->devs.size();
   if (n == 0) return JNE_OK;
@@ -479,17 +613,39 @@ int eigs_batch_sync(jne_ctx* ctx, uint32_t mask, uint32_t dim, uint32_t steps, c
   std::vector<int> rc(nd, JNE_OK);
   std::vector<std::string> errs(nd);
   const uint64_t per = (n + nd - 1) / nd;
-  for (size_t i = 0; i < nd; ++i) {
-    const uint64_t a = std::min<uint64_t>(i * per, n), b = std::min<uint64_t>(a + per, n);
-    if (a == b) continue;
-    th.emplace_back([&, i, a, b]() {
-      rc[i] = run_share(ctx, ctx->devs[i], prm, seeds + a, b - a, out + a * prm.p, &errs[i]);
-    });
+  try {
+    for (size_t i = 0; i < nd; ++i) {
+      const uint64_t a = std::min<uint64_t>(i * per, n), b = std::min<uint64_t>(a + per, n);
+      if (a == b) continue;
+      th.emplace_back([&, i, a, b]() {
+        rc[i] = run_share(ctx, ctx->devs[i], prm, seeds + a, b - a, out + a * prm.p, &errs[i]);
+      });
+    }
+  } catch (...) {            // a thread could not be started: the ones that run still use rc / errs / out
+    for (auto& t : th) t.join();
+    throw;
   }
   for (auto& t : th) t.join();
   for (size_t i = 0; i < nd; ++i)
-    if (rc[i]) { ctx->err = errs[i]; return rc[i]; }
+    if (rc[i]) { std::lock_guard<std::mutex> lk(ctx->err_mu); ctx->err = errs[i]; return rc[i]; }
   return JNE_OK;
+}
+
+// Nothing may cross the C ABI: host-side failures (std::bad_alloc, std::system_error from std::thread ...) become
+// JNE_ERR_INTERNAL with the message in jne_last_error.
+template <class F> auto guarded(jne_ctx* ctx, F&& f) -> decltype(f()) {
+  try {
+    return f();
+  } catch (const std::exception& e) {
+    return (decltype(f()))fail(ctx, JNE_ERR_INTERNAL, std::string("host-side failure: ") + e.what());
+  } catch (...) {
+    return (decltype(f()))fail(ctx, JNE_ERR_INTERNAL, "host-side failure: unknown exception");
+  }
+}
+
+int eigs_batch_sync(jne_ctx* ctx, uint32_t mask, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
+                    double* out) {
+  return guarded(ctx, [&]() { return eigs_batch_sync_impl(ctx, mask, dim, steps, seeds, n, out); });
 }
 
 void join_worker(jne_ctx* ctx) {
@@ -646,10 +802,14 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
   }
   if (n_devices < 0) return fail(nullptr, JNE_ERR_INVALID_ARG, "n_devices < 0");
   if (n_devices == 0) n_devices = visible;
-  jne_ctx* ctx = new jne_ctx();
+  jne_ctx* ctx = new (std::nothrow) jne_ctx();
+  if (!ctx) return fail(nullptr, JNE_ERR_INTERNAL, "out of host memory");
+#ifdef JNE_EXPERIMENTAL_FAMILIES
   if (const char* kf = std::getenv("JNE_KERNEL")) ctx->kernel_family = (std::strcmp(kf, "v2") == 0) ? 2 : (std::strcmp(kf, "ws") == 0) ? 3 : 1;
+#endif
+  if (const char* ln = std::getenv("JNE_LANE")) ctx->use_lane = std::strcmp(ln, "0") != 0;
   if (const char* ax = std::getenv("JNE_AUX")) ctx->use_aux = std::strcmp(ax, "0") != 0;
-  ctx->devs.resize(n_devices);
+  try { ctx->devs.resize(n_devices); } catch (...) { delete ctx; return fail(nullptr, JNE_ERR_INTERNAL, "out of host memory"); }
   for (int i = 0; i < n_devices; ++i) {
     Device& dv = ctx->devs[i];
     dv.id = device_ids ? device_ids[i] : i;
@@ -667,10 +827,10 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
       dv.sm_count = prop.multiProcessorCount;
       JNE_CUDA(nullptr, cudaStreamCreateWithFlags(&dv.stream, cudaStreamNonBlocking));
       for (auto& s : dv.slot) {
-        JNE_CUDA(nullptr, cudaMalloc(&s.d_seeds, kChunkRuns * sizeof(uint32_t)));
-        JNE_CUDA(nullptr, cudaMalloc(&s.d_out, kChunkRuns * kMaxWidth * sizeof(double)));
-        JNE_CUDA(nullptr, cudaMallocHost(&s.h_seeds, kChunkRuns * sizeof(uint32_t)));
-        JNE_CUDA(nullptr, cudaMallocHost(&s.h_out, kChunkRuns * kMaxWidth * sizeof(double)));
+        JNE_CUDA(nullptr, cudaMalloc(&s.d_seeds, kSlotSeeds * sizeof(uint32_t)));
+        JNE_CUDA(nullptr, cudaMalloc(&s.d_out, kSlotDoubles * sizeof(double)));
+        JNE_CUDA(nullptr, cudaMallocHost(&s.h_seeds, kSlotSeeds * sizeof(uint32_t)));
+        JNE_CUDA(nullptr, cudaMallocHost(&s.h_out, kSlotDoubles * sizeof(double)));
         JNE_CUDA(nullptr, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         JNE_CUDA(nullptr, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
       }
@@ -749,12 +909,14 @@ int64_t jne_submit(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, co
   if (rc) return rc;
   if (n && (!seeds || !out)) return fail(ctx, JNE_ERR_INVALID_ARG, "seeds/out is NULL");
   join_worker(ctx);
-  auto copy = std::make_shared<std::vector<uint32_t>>(seeds, seeds + n);
-  ctx->pending_ticket = ctx->next_ticket++;
-  ctx->worker = std::thread([ctx, model, dim, steps, copy, n, out]() {
-    ctx->pending_status = eigs_batch_sync(ctx, 1u << model, dim, steps, copy->data(), n, out);
+  return guarded(ctx, [&]() -> int64_t {
+    auto copy = std::make_shared<std::vector<uint32_t>>(seeds, seeds + n);
+    ctx->worker = std::thread([ctx, model, dim, steps, copy, n, out]() {
+      ctx->pending_status = eigs_batch_sync(ctx, 1u << model, dim, steps, copy->data(), n, out);
+    });
+    ctx->pending_ticket = ctx->next_ticket++;     // only once the worker exists
+    return ctx->pending_ticket;
   });
-  return ctx->pending_ticket;
 }
 
 int64_t jne_submit_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
@@ -766,12 +928,14 @@ int64_t jne_submit_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32
     if ((model_mask >> m) & 1u) { int rc = validate(ctx, (uint8_t)m, dim, steps); if (rc) return rc; }
   if (n && (!seeds || !out)) return fail(ctx, JNE_ERR_INVALID_ARG, "seeds/out is NULL");
   join_worker(ctx);
-  auto copy = std::make_shared<std::vector<uint32_t>>(seeds, seeds + n);
-  ctx->pending_ticket = ctx->next_ticket++;
-  ctx->worker = std::thread([ctx, model_mask, dim, steps, copy, n, out]() {
-    ctx->pending_status = eigs_batch_sync(ctx, model_mask, dim, steps, copy->data(), n, out);
+  return guarded(ctx, [&]() -> int64_t {
+    auto copy = std::make_shared<std::vector<uint32_t>>(seeds, seeds + n);
+    ctx->worker = std::thread([ctx, model_mask, dim, steps, copy, n, out]() {
+      ctx->pending_status = eigs_batch_sync(ctx, model_mask, dim, steps, copy->data(), n, out);
+    });
+    ctx->pending_ticket = ctx->next_ticket++;     // only once the worker exists
+    return ctx->pending_ticket;
   });
-  return ctx->pending_ticket;
 }
 
 int jne_wait(jne_ctx* ctx, int64_t ticket) {
@@ -829,7 +993,7 @@ static int single_device_run(jne_ctx* ctx, const JneRunParams& prm_in, const uin
   const bool rng = dB == nullptr;
   const uint64_t per_run_in = rng ? 0 : (uint64_t)prm.dim * prm.steps;
   // bound the scratch: <= 1 GiB of increments, <= 2^18 runs per launch
-  uint64_t chunk = kChunkRuns;
+  uint64_t chunk = 1ull << 15;
   if (!rng) chunk = std::max<uint64_t>(1, std::min<uint64_t>(chunk, (1ull << 27) / std::max<uint64_t>(1, per_run_in)));
   if (mats) chunk = std::min<uint64_t>(chunk, 1ull << 14);
   const size_t in_bytes = rng ? chunk * sizeof(uint32_t) : chunk * per_run_in * sizeof(double);

@@ -10,6 +10,22 @@
 
 namespace jne {
 
+namespace {
+// An outstanding jne_submit ticket writes into a caller buffer from the context's worker thread.  If anything throws
+// while it is in flight (a full disk in the writer, a failing sender), the buffer must outlive the worker and the
+// context must not be left with a pending ticket: the guard is declared AFTER the buffers, so unwinding joins the
+// worker (jne_wait) before they are freed.
+struct TicketGuard {
+  jne_ctx* ctx;
+  int64_t ticket = 0;
+  explicit TicketGuard(jne_ctx* c) : ctx(c) {}
+  ~TicketGuard() { if (ticket > 0) jne_wait(ctx, ticket); }
+  int wait() { const int64_t t = ticket; ticket = 0; return t > 0 ? jne_wait(ctx, t) : JNE_OK; }
+  TicketGuard(const TicketGuard&) = delete;
+  TicketGuard& operator=(const TicketGuard&) = delete;
+};
+}  // namespace
+
 SimulationStats run_model_simulation(const Engine& gpu, Model model, uint32_t dim, uint32_t steps, uint64_t num_runs,
                                      const std::string& filename, bool quiet) {
   SimulationStats st;
@@ -33,6 +49,9 @@ SimulationStats run_model_simulation(const Engine& gpu, Model model, uint32_t di
     st.total_in_file = completed;
     return st;
   }
+  if (!quiet && completed)   // a resumed file continues with THIS library's stream (Philox), whoever wrote the head of it
+    printf("Resuming %s: %llu of %llu runs present, %zu to compute\n", filename.c_str(), (unsigned long long)completed,
+           (unsigned long long)num_runs, remaining.size());
   jne_dat_writer* w = nullptr;
   uint64_t existing = 0;
   rc = jne_dat_open(filename.c_str(), model.number, (uint8_t)dim, steps, &existing, &w);
@@ -41,16 +60,17 @@ SimulationStats run_model_simulation(const Engine& gpu, Model model, uint32_t di
   // double-buffered: the GPU computes chunk i+1 while chunk i is encoded and written
   const size_t chunk = 1u << 20;
   std::vector<double> buf[2];
+  TicketGuard inflight(gpu.ctx());     // after buf: joined before the buffers die on any exit path
   size_t prev_a = 0, prev_n = 0;
   int which = 0;
   try {
     for (size_t a = 0;; a += chunk) {
       const size_t n = a < remaining.size() ? std::min(chunk, remaining.size() - a) : 0;
-      int64_t ticket = 0;
       if (n) {
         buf[which].resize(n * p);
-        ticket = jne_submit(gpu.ctx(), model.number, dim, steps, remaining.data() + a, n, buf[which].data());
+        const int64_t ticket = jne_submit(gpu.ctx(), model.number, dim, steps, remaining.data() + a, n, buf[which].data());
         gpu.check(ticket);
+        inflight.ticket = ticket;
       }
       if (prev_n) {
         rc = jne_dat_append_batch(w, remaining.data() + prev_a, buf[which ^ 1].data(), prev_n, (uint32_t)p);
@@ -58,11 +78,12 @@ SimulationStats run_model_simulation(const Engine& gpu, Model model, uint32_t di
         st.computed += prev_n;
         if (!quiet) printf("Simulation progress: %llu/%llu\n", (unsigned long long)(completed + st.computed), (unsigned long long)num_runs);
       }
-      if (n) gpu.check(jne_wait(gpu.ctx(), ticket));
+      if (n) gpu.check(inflight.wait());
       prev_a = a; prev_n = n; which ^= 1;
       if (!n) break;
     }
   } catch (...) {
+    inflight.wait();        // the worker still writes into buf: join it before anything is torn down
     jne_dat_abandon(w);     // leave a trailer-less, resumable file behind, like an interrupted reference run
     throw;
   }
@@ -116,6 +137,7 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
   const size_t chunk_max = (size_t)(1u << 16) * (size_t)n_dev;
   const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
   std::vector<double> buf[2];
+  TicketGuard inflight(gpu.ctx());     // after buf: joined before the buffers die on any exit path
   // seeds by the set of models that lack them, one pass (ascending within a group)
   std::vector<uint32_t> groups[32];
   {
@@ -139,25 +161,30 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
       int which = 0;
       for (size_t a = 0;; a += chunk) {
         const size_t n = a < seeds.size() ? std::min(chunk, seeds.size() - a) : 0;
-        int64_t ticket = 0;
         if (n) {
           buf[which].resize(n * width);
-          ticket = jne_submit_multi(gpu.ctx(), mask, dim, steps, seeds.data() + a, n, buf[which].data());
+          const int64_t ticket = jne_submit_multi(gpu.ctx(), mask, dim, steps, seeds.data() + a, n, buf[which].data());
           gpu.check(ticket);
+          inflight.ticket = ticket;
         }
         if (prev_n) {                                  // one writer thread per file, as many files as models in the mask
           std::thread th[5];
           int rcs[5] = {0, 0, 0, 0, 0};
           std::string errs[5];
           const double* rows = buf[which ^ 1].data();
-          for (int m = 0; m < 5; ++m) {
-            if (!((mask >> m) & 1u)) continue;
-            th[m] = std::thread([&, m]() {
-              // encoders per file: what the host has beyond one thread per file, as far as the devices need it
-              const int enc = std::max(1, std::min({4, n_dev, hw / (2 * __builtin_popcount(mask))}));
-              rcs[m] = jne_dat_append_batch_strided_mt(w[m], seeds.data() + prev_a, rows + off[m], prev_n, pm[m], width, enc);
-              if (rcs[m] != JNE_OK) errs[m] = jne_dat_last_error();
-            });
+          try {
+            for (int m = 0; m < 5; ++m) {
+              if (!((mask >> m) & 1u)) continue;
+              th[m] = std::thread([&, m]() {
+                // encoders per file: what the host has beyond one thread per file, as far as the devices need it
+                const int enc = std::max(1, std::min({4, n_dev, hw / (2 * __builtin_popcount(mask))}));
+                rcs[m] = jne_dat_append_batch_strided_mt(w[m], seeds.data() + prev_a, rows + off[m], prev_n, pm[m], width, enc);
+                if (rcs[m] != JNE_OK) errs[m] = jne_dat_last_error();
+              });
+            }
+          } catch (...) {                              // std::thread could not start: join the ones that did, then unwind
+            for (auto& t : th) if (t.joinable()) t.join();
+            throw;
           }
           for (auto& t : th) if (t.joinable()) t.join();
           for (int m = 0; m < 5; ++m) {
@@ -167,12 +194,13 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
           if (!quiet) printf("Simulation progress (models mask 0x%x): %llu/%llu seeds\n", mask,
                              (unsigned long long)(prev_a + prev_n), (unsigned long long)seeds.size());
         }
-        if (n) gpu.check(jne_wait(gpu.ctx(), ticket));
+        if (n) gpu.check(inflight.wait());
         prev_a = a; prev_n = n; which ^= 1;
         if (!n) break;
       }
     }
   } catch (...) {
+    inflight.wait();      // the worker still writes into buf: join it before anything is torn down
     abandon_all();        // trailer-less, resumable files, like an interrupted reference run
     throw;
   }
@@ -210,6 +238,12 @@ int jne_run_models_simulation(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, u
   } catch (const jne::Error& e) {
     fprintf(stderr, "jne_run_models_simulation: %s\n", e.what());
     return e.status;
+  } catch (const std::exception& e) {   // bad_alloc, system_error (thread creation) ...: nothing may cross the C ABI
+    fprintf(stderr, "jne_run_models_simulation: %s\n", e.what());
+    return JNE_ERR_INTERNAL;
+  } catch (...) {
+    fprintf(stderr, "jne_run_models_simulation: unknown exception\n");
+    return JNE_ERR_INTERNAL;
   }
 }
 
@@ -228,6 +262,12 @@ int jne_run_model_simulation(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t
   } catch (const jne::Error& e) {
     fprintf(stderr, "jne_run_model_simulation: %s\n", e.what());
     return e.status;
+  } catch (const std::exception& e) {
+    fprintf(stderr, "jne_run_model_simulation: %s\n", e.what());
+    return JNE_ERR_INTERNAL;
+  } catch (...) {
+    fprintf(stderr, "jne_run_model_simulation: unknown exception\n");
+    return JNE_ERR_INTERNAL;
   }
 }
 

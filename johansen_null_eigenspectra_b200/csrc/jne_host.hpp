@@ -78,18 +78,24 @@ inline void calculate_eigenvalues_parallel(const Engine& gpu, uint32_t dim, uint
                                            Model model, const Sender& sender, bool /*quiet*/, size_t chunk = 1u << 20) {
   const int p = model.num_eigs(dim);
   std::vector<double> buf[2];
+  // declared after buf: if `sender` throws while a ticket is in flight, unwinding joins the worker (jne_wait) before
+  // the buffer it writes into is freed, and the context is left without a pending ticket
+  struct Inflight {
+    jne_ctx* ctx; int64_t ticket;
+    ~Inflight() { if (ticket > 0) jne_wait(ctx, ticket); }
+  } inflight{gpu.ctx(), 0};
   size_t prev_a = 0, prev_n = 0;
   int which = 0;
   for (size_t a = 0; a < seeds.size() || prev_n; a += chunk) {
     const size_t n = a < seeds.size() ? std::min(chunk, seeds.size() - a) : 0;
-    int64_t ticket = 0;
     if (n) {
       buf[which].resize(n * p);
-      ticket = jne_submit(gpu.ctx(), model.number, dim, steps, seeds.data() + a, n, buf[which].data());
+      const int64_t ticket = jne_submit(gpu.ctx(), model.number, dim, steps, seeds.data() + a, n, buf[which].data());
       gpu.check(ticket);
+      inflight.ticket = ticket;
     }
     for (size_t i = 0; i < prev_n; ++i) sender(seeds[prev_a + i], buf[which ^ 1].data() + i * p, p);
-    if (n) gpu.check(jne_wait(gpu.ctx(), ticket));
+    if (n) { const int64_t t = inflight.ticket; inflight.ticket = 0; gpu.check(jne_wait(gpu.ctx(), t)); }
     prev_a = a; prev_n = n; which ^= 1;
     if (!n) break;
   }

@@ -575,7 +575,7 @@ __device__ __forceinline__ bool jne_warp_models(double* __restrict__ wsm, const 
 // theirs to lane g - 4 with four FP32 shuffles: 3 calls per lane instead of 4.  DP = 4 likewise: 1 instead of 2.
 // The value of element (row, step) is unchanged: it depends on (seed, row, step) only.
 // ---------------------------------------------------------------------------------------------
-template <int DP, bool SRC_RNG> struct JneZ { using type = float; };
+template <int DP, bool SRC_RNG> struct JneZ { using type = jne_zt; };
 template <int DP> struct JneZ<DP, false> { using type = double; };
 
 template <int DP, bool SRC_RNG>
@@ -604,14 +604,14 @@ __device__ __forceinline__ void jne_gen8(uint32_t t, uint32_t t_end, uint32_t d,
       jne_normals4_keyed(keys, 8 * j + g, t >> 2, &z[j][0], rowscale[j]);
       jne_normals4_keyed(keys, 8 * j + g, (t >> 2) + 1, &z[j][4], rowscale[j]);
     }
-    float x[4];
+    jne_zt x[4];
     jne_normals4_keyed(keys, 8 * L + (g & 3), (t >> 2) + (g >> 2), x, xscale);
     // Lanes g >= 4 own no row in this slot: what they accumulate there (a path nobody reads: their operand in
     // the mixed group is the received increment or the trend weight, and rows >= DP of the dump are ignored) is
     // left unmasked -- zeroing it cost two FSEL per step after the widening.
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-      const float other = __shfl_xor_sync(0xffffffffu, x[s], 16);    // lane g ^ 4, same segment
+      const jne_zt other = __shfl_xor_sync(0xffffffffu, x[s], 16);    // lane g ^ 4, same segment
       z[L][s] = x[s];
       z[L][4 + s] = other;
     }
@@ -943,7 +943,7 @@ __global__ void jne_normal_matrix_kernel(uint32_t seed, uint32_t d, uint32_t T, 
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (uint64_t)nb * d) return;
   const uint32_t row = idx % d, tb = idx / d;
-  float z[4];
+  jne_zt z[4];
   jne_normals4(seed, row, tb, z);
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
@@ -960,7 +960,7 @@ __global__ void jne_brownian_kernel(uint32_t seed, uint32_t d, uint32_t T, doubl
   double acc = 0.0;
   out[row] = acc;
   for (uint32_t tb = 0; tb < (T + 3) / 4; ++tb) {
-    float z[4];
+    jne_zt z[4];
     jne_normals4(seed, row, tb, z);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {

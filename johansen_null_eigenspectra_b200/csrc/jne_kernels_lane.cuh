@@ -1,0 +1,222 @@
+// Lane family: one THREAD per run, register-resident FP64 moments (sm_100a).  Serves dim <= 6.
+//
+// Why a second family.  On the tensor path (jne_kernels.cuh) a warp owns one run and feeds V = [F ; dB] to
+// mma.sync.m8n8k4.f64 tiles; the tile layouts are sized for 4, 8 and 12 rows, so dim 1 pays for dim 4 and
+// dim 5 for dim 8 -- both in padded products and in Philox blocks generated for rows that do not exist
+// (profiles/r1_bench_all_configs.jsonl: 10.5 M seeds/s for every dim 1..4, 7.2 M for dim 5 and 6).  The reference's
+// cost is proportional to the products it needs (src/matrix_utils.rs:67-85: p x d per step), and below about
+// seven rows all of a run's moments fit one thread's registers:
+//     sum c c' (upper triangle)   D (D + 1) / 2        sum c dB'   D^2        sum c, sum w1 c, sum w2 c   3 D
+// = 81 doubles at D = 6.  So here a lane owns a whole run: it generates exactly the D rows the run has (one Philox
+// call per row and four steps), keeps the path in registers, and every product is an FP64 FMA on two registers:
+// no padded products, no operand exchange, no time segments (the sums run left to right over the T steps, as the
+// reference's do), D known at compile time.  The moments go to global memory in a compact layout
+// (JneLaneMom<D>) and jne_lane_solve_kernel -- one warp per run, the epilogue of the tensor path unchanged
+// (jne_warp_models: assembly per model, elimination, Jacobi) -- turns them into eigenvalues.
+//
+//   K1  jne_normals4_keyed        (jne_rng.cuh)  replaces gen_normal_matrix        src/rng_matrix.rs:11-37
+//   K2  jne_lane_moments_kernel                  replaces brownian_motion_matrix   src/rng_matrix.rs:57-141,
+//                                                dmatrix_cumsum RowWise            src/matrix_utils.rs:51-63,
+//                                                construct_f_matrix                src/johansen_statistics.rs:102-197,
+//                                                2 x sum_of_outer_products         src/matrix_utils.rs:67-85
+//   K3  jne_lane_solve_kernel                    replaces GeneralizedEigen::new + |alpha|/beta + sort
+//                                                                                  src/johansen_statistics.rs:35-46
+// The random stream is the same function of (seed, row, step) as everywhere else.
+#pragma once
+#include "jne_kernels.cuh"
+
+#define JNE_LANE_MAX_DIM 6
+// Launch geometry: 128 threads per CTA (one warp per SM sub-partition) and the resident CTAs per SM the register
+// budget is sized for.  Registers are allocated per sub-partition (16 384 each): 6 / 5 / 4 / 3 / 2 resident warps
+// leave 85 / 102 / 128 / 168 / 255 registers per thread.
+#ifndef JNE_LANE_MINB5
+#define JNE_LANE_MINB5 3      // dim 5: 168 registers (the five-model kernel spills ten doubles); 2 = 255 registers
+#endif
+template <int D> struct JneLaneGeo {
+  static constexpr int THREADS = 128;
+  static constexpr int MINB = D <= 2 ? 6 : D == 3 ? 5 : D == 4 ? 4 : D == 5 ? JNE_LANE_MINB5 : 2;
+};
+
+// Per-run moments in global memory (doubles):
+//   bb [D (D + 1) / 2]  sum c_i c_j, i <= j, row-major upper triangle        (c = path BEFORE the step = F rows)
+//   bz [D][D]           sum c_i dB_j
+//   tot[6][D]           0 sum c, 1 sum w1 c, 2 sum w2 c, 3 sum dB, 4 sum w1 dB, 5 sum w2 dB
+// with w1_t = 2 t + 1 - T and w2_t = 3 w1_t^2 - (T^2 - 1): the integer forms of the reference's trend regressors
+// (t + 1) / T - 1/2 and the residual of ((t + 1) / T)^2 on [1, (t + 1) / T] (src/johansen_statistics.rs:127-135,170-194).
+template <int D> struct JneLaneMom {
+  static constexpr int NBB = D * (D + 1) / 2;
+  static constexpr int OFF_BZ = NBB, OFF_TOT = NBB + D * D, SZ = OFF_TOT + 6 * D;
+};
+__host__ __device__ constexpr int jne_lane_mom_size(int d) { return d * (d + 1) / 2 + d * d + 6 * d; }
+
+// DET: 0 = models 0, 1 (sum c only), 1 = models 2, 3 (+ w1 moments), 2 = model 4 / several models (+ w2 moments).
+template <int D, int DET> struct JneLaneState {
+  double c[D], bb[JneLaneMom<D>::NBB], bz[D * D], s0[D], s1[D], s2[D];
+  double w1, w2, w2c;
+};
+
+// One step: the products of the path before the step with itself and with the step's increments, the trend sums,
+// then B_t = B_{t-1} + dB_t (src/matrix_utils.rs:51-63).
+template <int D, int DET, bool SRC_RNG>
+__device__ __forceinline__ void jne_lane_step(JneLaneState<D, DET>& S, const double (&zin)[D]) {
+  double dz[D], cn[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    cn[i] = S.c[i] + zin[i];
+    dz[i] = SRC_RNG ? zin[i] : cn[i] - S.c[i];   // caller increments: dB re-derived by subtraction (src/johansen_statistics.rs:80-82)
+  }
+  int idx = 0;
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = i; j < D; ++j) { S.bb[idx] = fma(S.c[i], S.c[j], S.bb[idx]); ++idx; }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) S.bz[i * D + j] = fma(S.c[i], dz[j], S.bz[i * D + j]);
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    S.s0[i] += S.c[i];
+    if (DET >= 1) S.s1[i] = fma(S.w1, S.c[i], S.s1[i]);
+    if (DET >= 2) S.s2[i] = fma(S.w2, S.c[i], S.s2[i]);
+    S.c[i] = cn[i];
+  }
+  if (DET >= 1) S.w1 += 2.0;
+  if (DET >= 2) S.w2 = fma(3.0 * S.w1, S.w1, S.w2c);
+}
+
+template <int D, int DET, bool SRC_RNG>
+__global__ void __launch_bounds__(JneLaneGeo<D>::THREADS, JneLaneGeo<D>::MINB)
+jne_lane_moments_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB, uint64_t n, uint32_t T,
+                        double* __restrict__ mom) {
+  using M = JneLaneMom<D>;
+  const uint64_t run_raw = (uint64_t)blockIdx.x * JneLaneGeo<D>::THREADS + threadIdx.x;
+  const bool live = run_raw < n;
+  const uint64_t run = live ? run_raw : n - 1;         // idle lanes shadow the last run (no divergence in the loop)
+  // round keys of Philox word 0; the empty asm makes each one opaque, so that ptxas keeps them in registers instead
+  // of re-adding "seed + r * W0" inside the time loop (jne_make_keys does the same through shared memory)
+  jne_keys keys;
+  {
+    const uint32_t seed = SRC_RNG ? seeds[run] : 0u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      keys.k[r] = seed + (uint32_t)r * 0x9E3779B9u;
+      asm volatile("" : "+r"(keys.k[r]));
+    }
+  }
+  const double* dBrun = SRC_RNG ? nullptr : dB + run * (uint64_t)D * T;
+
+  JneLaneState<D, DET> S;
+#pragma unroll
+  for (int i = 0; i < D; ++i) { S.c[i] = S.s0[i] = S.s1[i] = S.s2[i] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < M::NBB; ++i) S.bb[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < D * D; ++i) S.bz[i] = 0.0;
+  const double Td = (double)T;
+  const double w1_first = 1.0 - Td;
+  const double w2c = -(Td * Td - 1.0);
+  S.w1 = w1_first;
+  S.w2c = w2c;
+  S.w2 = fma(3.0 * w1_first, w1_first, w2c);
+
+  // four steps per Philox call and row; the ragged tail (T mod 4 steps) is uniform over the grid: T is a launch parameter
+  const uint32_t nfull = T >> 2, tail = T & 3u;
+  auto load_block = [&](uint32_t tb, uint32_t ns, double (&z)[4][D]) {
+    if constexpr (SRC_RNG) {
+#pragma unroll
+      for (int r = 0; r < D; ++r) {
+        jne_zt zf[4];
+        jne_normals4_keyed(keys, (uint32_t)r, tb, zf);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) z[s][r] = (double)zf[s];
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int r = 0; r < D; ++r) z[s][r] = (uint32_t)s < ns ? dBrun[(uint64_t)(4u * tb + s) * D + r] : 0.0;
+    }
+  };
+  for (uint32_t tb = 0; tb < nfull; ++tb) {
+    double z[4][D];
+    load_block(tb, 4u, z);
+    jne_lane_step<D, DET, SRC_RNG>(S, z[0]);
+    jne_lane_step<D, DET, SRC_RNG>(S, z[1]);
+    jne_lane_step<D, DET, SRC_RNG>(S, z[2]);
+    jne_lane_step<D, DET, SRC_RNG>(S, z[3]);
+  }
+  if (tail != 0u) {
+    double z[4][D];
+    load_block(nfull, tail, z);
+#pragma unroll 1
+    for (uint32_t s = 0; s < tail; ++s) {
+      double zz[D];
+#pragma unroll
+      for (int r = 0; r < D; ++r) zz[r] = s == 0u ? z[0][r] : s == 1u ? z[1][r] : z[2][r];
+      jne_lane_step<D, DET, SRC_RNG>(S, zz);
+    }
+  }
+  if (!live) return;
+
+  double* m = mom + run * (uint64_t)M::SZ;
+#pragma unroll
+  for (int i = 0; i < M::NBB; ++i) m[i] = S.bb[i];
+#pragma unroll
+  for (int i = 0; i < D * D; ++i) m[M::OFF_BZ + i] = S.bz[i];
+  // the increment moments by summation by parts (dB_t = c_{t+1} - c_t, c_0 = 0, w1_t - w1_{t-1} = 2,
+  // w2_t - w2_{t-1} = 12 w1_t - 12):  sum w1 dB = w1_last c_T - 2 sum c,  sum w2 dB = w2_last c_T - 12 sum w1 c + 12 sum c
+  const double w1_last = w1_first + 2.0 * (Td - 1.0);
+  const double w2_last = fma(3.0 * w1_last, w1_last, w2c);
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double* t = m + M::OFF_TOT + i;
+    t[0 * D] = S.s0[i];
+    t[1 * D] = S.s1[i];
+    t[2 * D] = S.s2[i];
+    t[3 * D] = S.c[i];
+    t[4 * D] = fma(w1_last, S.c[i], -2.0 * S.s0[i]);
+    t[5 * D] = fma(w2_last, S.c[i], 12.0 * (S.s0[i] - S.s1[i]));
+  }
+}
+
+// One warp per run: the moments of jne_lane_moments_kernel in the stitched layout of jne_warp_stitch, then the
+// epilogue of the tensor path (per-model assembly with demeaning / detrending as Schur complements, elimination,
+// Jacobi, sort).  DP = 4 (dim <= 4) or 8 sizes the work matrices.
+template <int DP, bool MULTI>
+__global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA)
+jne_lane_solve_kernel(const double* __restrict__ mom, uint64_t n, JneRunParams prm, double* __restrict__ out,
+                      unsigned int* __restrict__ err_count, double* __restrict__ dbg) {
+  using G = JneGeo<DP>;
+  using E = JneEpi<DP, MULTI ? 5 : 1>;
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t run = (uint64_t)blockIdx.x * JNE_WARPS_PER_CTA + warp;
+  if (run >= n) return;
+  double* wsm = smem + (size_t)warp * E::END;
+  double* tot = wsm;
+  double* MBB = tot + G::TOT_SZ;
+  double* MBZ = MBB + G::STITCH_HALF;
+  const int d = prm.dim;
+  const int nbb = d * (d + 1) / 2;
+  const double* M = mom + run * (uint64_t)jne_lane_mom_size(d);
+  for (int e = lane; e < G::STITCH_HALF; e += 32) {
+    const int i = e >> 4, j = e & 15;
+    const bool in = i < d && j < d;
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    MBB[e] = in ? M[lo * d - ((lo * (lo - 1)) >> 1) + (hi - lo)] : 0.0;
+    MBZ[e] = in ? M[nbb + i * d + j] : 0.0;
+  }
+  for (int e = lane; e < 96; e += 32) {
+    const int k = e >> 4, i = e & 15;
+    tot[e] = i < d ? M[nbb + d * d + k * d + i] : 0.0;
+  }
+  __syncwarp();
+  const bool ok = jne_warp_models<DP, MULTI ? 5 : 1>(wsm, prm, out + run * prm.out_stride,
+                                                     dbg != nullptr ? dbg + run * 512 : nullptr);
+  if (!ok && lane == 0) atomicAdd(err_count, 1u);
+}
+
+template <int DP, bool MULTI> constexpr size_t jne_lane_solve_smem() {
+  return (size_t)JNE_WARPS_PER_CTA * sizeof(double) * JneEpi<DP, MULTI ? 5 : 1>::END;
+}

@@ -15,6 +15,18 @@
 #include <cstdint>
 
 #define JNE_KEY1 0x4A4E4531u  // "JNE1"
+// Philox rounds.  10 is the Random123 / cuRAND default and what this library ships; 7 is the smallest count the
+// Random123 paper reports as Crush-resistant -- available as a build-time ablation only (profiles/: the lever table).
+#ifndef JNE_PHILOX_ROUNDS
+#define JNE_PHILOX_ROUNDS 10
+#endif
+// Type of a generated normal before it is widened for the FP64 accumulation: float in the product (FP32 + MUFU
+// transform), double in the validation build (-DJNE_RNG_F64, see jne_box_muller_f64).
+#ifdef JNE_RNG_F64
+typedef double jne_zt;
+#else
+typedef float jne_zt;
+#endif
 
 struct jne_u4 { uint32_t x, y, z, w; };
 
@@ -27,7 +39,7 @@ __device__ __forceinline__ jne_u4 jne_philox4x32_10(uint32_t c0, uint32_t c1, ui
                                                     uint32_t k0, uint32_t k1) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < JNE_PHILOX_ROUNDS; ++r) {
     const uint64_t p0 = (uint64_t)M0 * c0;
     const uint64_t p1 = (uint64_t)M1 * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ (k0 + (uint32_t)r * W0);
@@ -55,11 +67,11 @@ __device__ __forceinline__ jne_keys jne_make_keys(uint32_t seed, volatile uint32
   __syncwarp();
   return ks;
 }
-__device__ __forceinline__ jne_u4 jne_philox4x32_10_keyed(uint32_t c0, uint32_t c1, const jne_keys& ks) {
+__device__ __forceinline__ jne_u4 jne_philox4x32_10_keyed(uint32_t c0, uint32_t c1, const jne_keys& ks, uint32_t c2 = 0u) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W1 = 0xBB67AE85u;
-  uint32_t c2 = 0u, c3 = 0u;
+  uint32_t c3 = 0u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < JNE_PHILOX_ROUNDS; ++r) {
     uint32_t h0, l0, h1, l1;
     jne_mulhilo(M0, c0, h0, l0);
     jne_mulhilo(M1, c2, h1, l1);
@@ -87,14 +99,43 @@ __device__ __forceinline__ void jne_box_muller(uint32_t wa, uint32_t wb, float& 
   z1 = r * __sinf(th);
 }
 
+// VALIDATION STREAM (-DJNE_RNG_F64, never in libjne.so): the same counters, keys and word assignment, but the radius
+// uniform and the angle carry 64 bits -- the product's 32-bit word on top, the matching word of a second Philox block
+// (counter word 2 = 1) below -- and the transform runs in FP64 (log, sqrt, sincospi).  u = (x + 1/2) 2^-64, so the
+// radius reaches 9.5 instead of 6.76 and the tail is not quantised at 2^-32.  Element (row, step) of this stream differs
+// from the product's by the MUFU / FP32 rounding (~1e-6) and the low-order refinement only, which makes the A/B of
+// tools/validate_gate2.py a PAIRED comparison of the statistics, run by run.
+__device__ __forceinline__ void jne_box_muller_f64(uint32_t wa, uint32_t wa_lo, uint32_t wb, uint32_t wb_lo, double& z0,
+                                                   double& z1, double scale) {
+  const uint64_t xa = ((uint64_t)wa << 32) | wa_lo;
+  const long long xb = (long long)(((uint64_t)wb << 32) | wb_lo);
+  const double u = fma((double)xa, 0x1p-64, 0x1p-65);           // (0, 1]; log(1) = 0 gives radius 0
+  const double r = sqrt(-2.0 * log(u)) * scale;
+  double sn, cs;
+  sincospi((double)xb * 0x1p-63, &sn, &cs);                     // angle = 2 pi xb 2^-64 in [-pi, pi)
+  z0 = r * cs;
+  z1 = r * sn;
+}
+
 // The four normals of (row, time block tb = t >> 2) for one seed.
-__device__ __forceinline__ void jne_normals4(uint32_t seed, uint32_t row, uint32_t tb, float z[4]) {
+__device__ __forceinline__ void jne_normals4(uint32_t seed, uint32_t row, uint32_t tb, jne_zt z[4]) {
   const jne_u4 w = jne_philox4x32_10(tb, row, 0u, 0u, seed, JNE_KEY1);
+#ifdef JNE_RNG_F64
+  const jne_u4 v = jne_philox4x32_10(tb, row, 1u, 0u, seed, JNE_KEY1);
+  jne_box_muller_f64(w.x, v.x, w.y, v.y, z[0], z[1], 1.0);
+  jne_box_muller_f64(w.z, v.z, w.w, v.w, z[2], z[3], 1.0);
+#else
   jne_box_muller(w.x, w.y, z[0], z[1]);
   jne_box_muller(w.z, w.w, z[2], z[3]);
+#endif
 }
-__device__ __forceinline__ void jne_normals4_keyed(const jne_keys& ks, uint32_t row, uint32_t tb, float* z,
+__device__ __forceinline__ void jne_normals4_keyed(const jne_keys& ks, uint32_t row, uint32_t tb, jne_zt* z,
                                                    float scale = 1.0f) {
+#ifdef JNE_RNG_F64
+  const jne_u4 w = jne_philox4x32_10_keyed(tb, row, ks), v = jne_philox4x32_10_keyed(tb, row, ks, 1u);
+  jne_box_muller_f64(w.x, v.x, w.y, v.y, z[0], z[1], (double)scale);
+  jne_box_muller_f64(w.z, v.z, w.w, v.w, z[2], z[3], (double)scale);
+#else
 #ifdef JNE_EXP_NORNG   // experiment only: no Philox / Box-Muller (NOT a valid stream)
   z[0] = scale * 0.5f; z[1] = -scale * (float)(row + 1) * 0.25f; z[2] = scale * 0.125f * (tb & 3); z[3] = -scale;
   return;
@@ -107,4 +148,5 @@ __device__ __forceinline__ void jne_normals4_keyed(const jne_keys& ks, uint32_t 
   const jne_u4 w = jne_philox4x32_10_keyed(tb, row, ks);
   jne_box_muller(w.x, w.y, z[0], z[1], scale);
   jne_box_muller(w.z, w.w, z[2], z[3], scale);
+#endif
 }

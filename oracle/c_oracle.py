@@ -29,6 +29,8 @@ def load() -> C.CDLL:
     lib.jne_oracle_fast_from_increments.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.jne_oracle_fast_batch.restype = C.c_int
     lib.jne_oracle_fast_batch.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    lib.jne_oracle_fast_multi_stats.restype = C.c_int
+    lib.jne_oracle_fast_multi_stats.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
     lib.jne_oracle_gen_normal_matrix.restype = None
     lib.jne_oracle_gen_normal_matrix.argtypes = [C.c_size_t, C.c_size_t, C.c_uint64, C.c_size_t, C.c_void_p]
     return lib
@@ -90,4 +92,15 @@ def fast_batch(lib, model: int, dim: int, steps: int, seeds, threads: int) -> np
     rc = lib.jne_oracle_fast_batch(model, dim, steps, seeds.ctypes.data, seeds.size, threads, out.ctypes.data)
     if rc:
         raise FloatingPointError(f"oracle fast rc={rc}")
+    return out
+
+
+def fast_multi_stats(lib, dim: int, steps: int, seeds, threads: int) -> np.ndarray:
+    """(n, 5, 2): per seed and model the trace and the largest eigenvalue, all five models from ONE f64-ziggurat path
+    per seed (the gate-(2) CPU sampler)."""
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+    out = np.empty((seeds.size, 5, 2))
+    rc = lib.jne_oracle_fast_multi_stats(dim, steps, seeds.ctypes.data, seeds.size, threads, out.ctypes.data)
+    if rc:
+        raise FloatingPointError(f"oracle fast multi rc={rc}")
     return out

@@ -374,3 +374,43 @@ int jne_oracle_fast_batch(int model, int d, size_t T, const uint32_t* seeds, siz
   free(th); free(jobs);
   return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Gate-(2) sampler (tools/gate2_cpu_samples.py): for every seed ONE Brownian path from f64 ziggurat normals
+ * (xoshiro256++ seeded by the seed, like jne_oracle_fast_batch), the raw moments once, then all five models;
+ * per seed and model the two statistics the reference's analysers report (src/simulation_analyzers.rs:25-40):
+ * trace = sum of the eigenvalues, max = the largest.  out: n x 10 doubles, [model][trace, max].
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct { int d, nthreads, tid, rc; size_t T, n; const uint32_t* seeds; double* out; } sjob_t;
+static void* stats_worker(void* arg) {
+  sjob_t* j = (sjob_t*)arg;
+  double ev[17];
+  for (size_t i = j->tid; i < j->n; i += j->nthreads) {
+    xo_t rng; xo_seed(&rng, (uint64_t)j->seeds[i]);
+    mom_t m;
+    fast_accumulate(&m, j->d, j->T, NULL, &rng);
+    for (int model = 0; model < 5; ++model) {
+      const int p = (model == 1 || model == 3) ? j->d + 1 : j->d;
+      const int rc = fast_solve(&m, j->d, (double)j->T, model, 1.0, ev);
+      if (rc) j->rc = rc;
+      double tr = 0.0, mx = -1.7976931348623157e308;
+      for (int k = 0; k < p; ++k) { tr += ev[k]; if (ev[k] > mx) mx = ev[k]; }
+      j->out[i * 10 + 2 * model] = tr;
+      j->out[i * 10 + 2 * model + 1] = mx;
+    }
+  }
+  return NULL;
+}
+int jne_oracle_fast_multi_stats(int d, size_t T, const uint32_t* seeds, size_t n, int nthreads, double* out) {
+  if (d > 16) return -1;
+  pthread_once(&zig_once, zig_init);
+  scipy_openblas_set_num_threads(1);
+  if (nthreads < 1) nthreads = 1;
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+  sjob_t* jobs = (sjob_t*)malloc(sizeof(sjob_t) * nthreads);
+  for (int t = 0; t < nthreads; ++t) { jobs[t] = (sjob_t){d, nthreads, t, 0, T, n, seeds, out}; pthread_create(&th[t], NULL, stats_worker, &jobs[t]); }
+  int rc = 0;
+  for (int t = 0; t < nthreads; ++t) { pthread_join(th[t], NULL); if (jobs[t].rc) rc = jobs[t].rc; }
+  free(th); free(jobs);
+  return rc;
+}

@@ -361,8 +361,18 @@ def test_increment_scale_covariance(engine):
             assert_close(got / scale / scale, ref, f"model {model} scale {scale}")
 
 
+def _experimental_library():
+    """The measured-slower kernel families live in csrc/experimental/ and are compiled only into the variant library
+    (python -m johansen_null_eigenspectra_b200.build --experimental); libjne.so does not contain them."""
+    from johansen_null_eigenspectra_b200 import build as jbuild
+    path = jbuild.VARIANTS["experimental"][1]
+    if not path.exists():
+        pytest.skip("libjne_experimental.so not built (build.py --experimental)")
+    return str(path)
+
+
 def test_fma_tiled_kernel_family():
-    """JNE_KERNEL=v2 selects the register-tiled FMA family (csrc/jne_kernels_v2.cuh) for 9 <= dim <= 12.  It consumes
+    """JNE_KERNEL=v2 selects the register-tiled FMA family (csrc/experimental/jne_kernels_v2.cuh) for 9 <= dim <= 12.  It consumes
     the same random stream, so it must agree with the oracle fed the device normals (gate-1 tolerance), with the
     increments entry, and -- to rounding, not bits: the summation order differs -- with the default tensor family."""
     import os, subprocess, sys, textwrap
@@ -392,9 +402,10 @@ def test_fma_tiled_kernel_family():
     ''')
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = {}
+    explib = _experimental_library()
     for fam in ("v2", "v1"):
         path = f"/tmp/jne_family_{fam}.npy"
-        env = dict(os.environ, JNE_KERNEL=fam)
+        env = dict(os.environ, JNE_KERNEL=fam, JNE_LIBRARY=explib)
         r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=env, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stderr[-2000:]
         worst = float(r.stdout.split("WORST")[1])
@@ -404,7 +415,7 @@ def test_fma_tiled_kernel_family():
 
 
 def test_warp_specialised_kernel_family():
-    """JNE_KERNEL=ws selects the producer / consumer family (csrc/jne_kernels_ws.cuh) for dim <= 12.  Its generator
+    """JNE_KERNEL=ws selects the producer / consumer family (csrc/experimental/jne_kernels_ws.cuh) for dim <= 12.  Its generator
     warps compute the very values the default family computes in place, so every record must be bit-identical to
     the default family with the same trend-moment arithmetic (JNE_AUX=0: scalar FP64 sums) -- for partial CTAs
     (fewer runs than consumer warps), several runs per consumer warp, ragged T, all models.  Against the default
@@ -429,9 +440,10 @@ def test_warp_specialised_kernel_family():
     ''')
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
+    explib = _experimental_library()
     for fam, kern, aux in (("ws", "ws", "0"), ("v1", "v1", "0"), ("v1aux", "v1", "1")):
         path = f"/tmp/jne_family_{fam}.npz"
-        env = dict(os.environ, JNE_KERNEL=kern, JNE_AUX=aux)
+        env = dict(os.environ, JNE_KERNEL=kern, JNE_AUX=aux, JNE_LANE="0", JNE_LIBRARY=explib)   # tensor family for every dim
         r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         res[fam] = np.load(path)
@@ -441,6 +453,43 @@ def test_warp_specialised_kernel_family():
         a, b = res["v1aux"][k], res["v1"][k]
         tol = 1e-9 * np.abs(b) + 1e-12 * b.max(axis=1, keepdims=True)
         assert np.all(np.abs(a - b) <= tol), k
+
+
+def test_lane_family_vs_tensor_family():
+    """dim <= 6 runs on the lane family (csrc/jne_kernels_lane.cuh: one thread per run, FP64 FMA on registers, the sums
+    left to right); JNE_LANE=0 sends the same dims through the tensor family (one warp per run, DMMA tiles, four time
+    segments).  Both consume the same random stream, so their records agree to rounding -- well inside the gate-1
+    tolerance -- for every model, ragged T, single-model and fused entry points."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import sys, numpy as np
+        sys.path.insert(0, ".")
+        import johansen_null_eigenspectra_b200 as jne
+        eng = jne.Engine([0])
+        out = {}
+        for dim, T, n in [(1, 9, 70), (2, 1000, 300), (3, 37, 50), (4, 10000, 40), (5, 5000, 200), (6, 103, 3000)]:
+            seeds = np.arange(11, 11 + n, dtype=np.uint32)
+            res = eng.eigs_batch_multi(range(5), dim, T, seeds)
+            for m in range(5):
+                out[f"{dim}_{T}_{m}"] = res[m]
+                assert np.array_equal(res[m], eng.eigs_batch(m, dim, T, seeds))
+        np.savez(sys.argv[1], **out)
+    ''')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, lane in (("lane", "1"), ("tensor", "0")):
+        path = f"/tmp/jne_lane_{tag}.npz"
+        r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=dict(os.environ, JNE_LANE=lane),
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[tag] = np.load(path)
+    differ = False
+    for k in res["lane"].files:
+        a, b = res["lane"][k], res["tensor"][k]
+        tol = 1e-10 * np.abs(b) + 1e-13 * b.max(axis=1, keepdims=True)      # a tenth of the gate-1 tolerance
+        assert np.all(np.abs(a - b) <= tol), (k, float(np.max(np.abs(a - b) / tol)))
+        differ |= not np.array_equal(a, b)
+    assert differ, "JNE_LANE=0 did not select a different kernel family"
 
 
 def test_host_path_chunking_is_invisible(engine):

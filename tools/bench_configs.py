@@ -34,12 +34,13 @@ def report(name, models, dim, T, n, note=""):
                       "fp64_peak_tflops": peak, "note": note}), flush=True)
 
 
+# dim <= 6 runs one THREAD per run (lane family): a launch needs ~10^6 seeds to fill several waves of the GPU
 report("c1 model 0 dim 2 T 1000 (100 000 runs)", [0], 2, 1000, 100000)
-report("c2 dim 5 T 5000 models 0-4 (fused pass)", range(5), 5, 5000, 1 << 18)
+report("c2 dim 5 T 5000 models 0-4 (fused pass)", range(5), 5, 5000, 1 << 20)
 for m in range(5):
-    report(f"c2 dim 5 T 5000 model {m} alone", [m], 5, 5000, 1 << 18)
+    report(f"c2 dim 5 T 5000 model {m} alone", [m], 5, 5000, 1 << 20)
 for d in range(1, 13):
-    report(f"c3 sweep dim {d} T 10000 models 0-4 (fused pass)", range(5), d, 10000, 1 << 17)
+    report(f"c3 sweep dim {d} T 10000 models 0-4 (fused pass)", range(5), d, 10000, 1 << 20 if d <= 6 else 1 << 17)
 for m in range(5):
     report(f"c4 dim 12 T 10000 model {m} alone", [m], 12, 10000, 1 << 17)
 report("c4 dim 12 T 10000 models 0-4 (fused pass)", range(5), 12, 10000, 1 << 17)
