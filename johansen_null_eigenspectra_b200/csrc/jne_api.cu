@@ -75,6 +75,7 @@ struct jne_ctx {
                            // experimental builds only (JNE_EXPERIMENTAL_FAMILIES): 2 = FMA-tiled path for 9 <= dim <= 12
                            // (env JNE_KERNEL=v2), 3 = producer / consumer warps for dim <= 12 (env JNE_KERNEL=ws)
   bool use_lane = true;    // env JNE_LANE=0: tensor family for every dim (regression tooling)
+  bool lane_thread_solve = true;   // env JNE_LANE_SOLVE=warp: the lane family's moments through the warp-per-run epilogue
   std::vector<Device> devs;
   std::string err;
   std::mutex err_mu;
@@ -383,6 +384,22 @@ cudaError_t launch_lane_solve(const double* mom, uint64_t m, const JneRunParams&
   return cudaGetLastError();
 }
 
+template <int D>
+cudaError_t launch_lane_tsolve(const double* mom, uint64_t m, const JneRunParams& prm, double* o, unsigned int* e, cudaStream_t st) {
+  jne_lane_tsolve_kernel<D><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(mom, m, prm.model_mask, prm.T, prm.factor, prm.out_stride, o, e);
+  return cudaGetLastError();
+}
+cudaError_t launch_lane_tsolve_dim(const double* mom, uint64_t m, const JneRunParams& prm, double* o, unsigned int* e, cudaStream_t st) {
+  switch (prm.dim) {
+    case 1: return launch_lane_tsolve<1>(mom, m, prm, o, e, st);
+    case 2: return launch_lane_tsolve<2>(mom, m, prm, o, e, st);
+    case 3: return launch_lane_tsolve<3>(mom, m, prm, o, e, st);
+    case 4: return launch_lane_tsolve<4>(mom, m, prm, o, e, st);
+    case 5: return launch_lane_tsolve<5>(mom, m, prm, o, e, st);
+    default: return launch_lane_tsolve<6>(mom, m, prm, o, e, st);
+  }
+}
+
 // Runs resident at once in the lane moments kernel (0 if the query fails).
 template <int D> uint64_t lane_wave_one(const Device& dv, int det) {
   int nb = 0;
@@ -435,7 +452,10 @@ cudaError_t launch_lane(jne_ctx* ctx, Device& dv, const uint32_t* s, const doubl
     if (rc != cudaSuccess) return rc;
     double* op = o + off * prm.out_stride;
     double* dp = dbg ? dbg + off * 512 : nullptr;
-    if (prm.dim <= 4) rc = multi ? launch_lane_solve<4, true>(d_mom, m, prm, op, e, dp, st) : launch_lane_solve<4, false>(d_mom, m, prm, op, e, dp, st);
+    // solve: one thread per run; the warp-per-run epilogue of the tensor family only when the caller wants the
+    // assembled matrices back (jne_eigs_batch_debug) or asks for it (JNE_LANE_SOLVE=warp, regression tooling)
+    if (dp == nullptr && ctx->lane_thread_solve) rc = launch_lane_tsolve_dim(d_mom, m, prm, op, e, st);
+    else if (prm.dim <= 4) rc = multi ? launch_lane_solve<4, true>(d_mom, m, prm, op, e, dp, st) : launch_lane_solve<4, false>(d_mom, m, prm, op, e, dp, st);
     else rc = multi ? launch_lane_solve<8, true>(d_mom, m, prm, op, e, dp, st) : launch_lane_solve<8, false>(d_mom, m, prm, op, e, dp, st);
     if (rc != cudaSuccess) return rc;
     ctx->launches.fetch_add(1);   // the solve kernel; the caller counts the moments kernel
@@ -808,6 +828,7 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
   if (const char* kf = std::getenv("JNE_KERNEL")) ctx->kernel_family = (std::strcmp(kf, "v2") == 0) ? 2 : (std::strcmp(kf, "ws") == 0) ? 3 : 1;
 #endif
   if (const char* ln = std::getenv("JNE_LANE")) ctx->use_lane = std::strcmp(ln, "0") != 0;
+  if (const char* ls = std::getenv("JNE_LANE_SOLVE")) ctx->lane_thread_solve = std::strcmp(ls, "warp") != 0;
   if (const char* ax = std::getenv("JNE_AUX")) ctx->use_aux = std::strcmp(ax, "0") != 0;
   try { ctx->devs.resize(n_devices); } catch (...) { delete ctx; return fail(nullptr, JNE_ERR_INTERNAL, "out of host memory"); }
   for (int i = 0; i < n_devices; ++i) {

@@ -30,7 +30,10 @@
 // budget is sized for.  Registers are allocated per sub-partition (16 384 each): 6 / 5 / 4 / 3 / 2 resident warps
 // leave 85 / 102 / 128 / 168 / 255 registers per thread.
 #ifndef JNE_LANE_MINB5
-#define JNE_LANE_MINB5 3      // dim 5: 168 registers (the five-model kernel spills ten doubles); 2 = 255 registers
+#define JNE_LANE_MINB5 2      // dim 5: 255 registers, 2 resident CTAs per SM; 3 = 168 registers (measured equal without
+#endif                        // the software pipeline, whose second block of normals needs the room)
+#ifndef JNE_LANE_PIPELINE
+#define JNE_LANE_PIPELINE 1   // 0: generate a block, then consume it (regression / ablation)
 #endif
 template <int D> struct JneLaneGeo {
   static constexpr int THREADS = 128;
@@ -120,41 +123,75 @@ jne_lane_moments_kernel(const uint32_t* __restrict__ seeds, const double* __rest
   S.w2c = w2c;
   S.w2 = fma(3.0 * w1_first, w1_first, w2c);
 
-  // four steps per Philox call and row; the ragged tail (T mod 4 steps) is uniform over the grid: T is a launch parameter
+  // Four steps per Philox call and row.  The ragged tail (T mod 4 steps) is uniform over the grid: T is a launch
+  // parameter.
   const uint32_t nfull = T >> 2, tail = T & 3u;
-  auto load_block = [&](uint32_t tb, uint32_t ns, double (&z)[4][D]) {
-    if constexpr (SRC_RNG) {
+  if constexpr (SRC_RNG && JNE_LANE_PIPELINE) {
+    // Software pipeline: the normals of block b + 1 are generated BETWEEN the steps of block b (rows spread over the
+    // four steps), so that every stretch of the instruction stream carries both a Philox / MUFU dependency chain and a
+    // batch of independent FP64 FMAs.  With two or three resident warps per sub-partition the generator's latency
+    // is otherwise exposed (ncu: 55 % issue-slot use, FP64 and XU pipes 45 / 42 % busy, `wait` the top stall).
+    jne_zt zc[D][4], zn[D][4];
 #pragma unroll
-      for (int r = 0; r < D; ++r) {
-        jne_zt zf[4];
-        jne_normals4_keyed(keys, (uint32_t)r, tb, zf);
+    for (int r = 0; r < D; ++r) jne_normals4_keyed(keys, (uint32_t)r, 0u, zc[r]);
+    for (uint32_t tb = 0; tb < nfull; ++tb) {
 #pragma unroll
-        for (int s = 0; s < 4; ++s) z[s][r] = (double)zf[s];
+      for (int s = 0; s < 4; ++s) {
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+          if (r * 4 / D == s) jne_normals4_keyed(keys, (uint32_t)r, tb + 1u, zn[r]);
+        double zz[D];
+#pragma unroll
+        for (int r = 0; r < D; ++r) zz[r] = (double)zc[r][s];
+        jne_lane_step<D, DET, SRC_RNG>(S, zz);
       }
-    } else {
 #pragma unroll
-      for (int s = 0; s < 4; ++s)
+      for (int r = 0; r < D; ++r)
 #pragma unroll
-        for (int r = 0; r < D; ++r) z[s][r] = (uint32_t)s < ns ? dBrun[(uint64_t)(4u * tb + s) * D + r] : 0.0;
+        for (int s = 0; s < 4; ++s) zc[r][s] = zn[r][s];
     }
-  };
-  for (uint32_t tb = 0; tb < nfull; ++tb) {
-    double z[4][D];
-    load_block(tb, 4u, z);
-    jne_lane_step<D, DET, SRC_RNG>(S, z[0]);
-    jne_lane_step<D, DET, SRC_RNG>(S, z[1]);
-    jne_lane_step<D, DET, SRC_RNG>(S, z[2]);
-    jne_lane_step<D, DET, SRC_RNG>(S, z[3]);
-  }
-  if (tail != 0u) {
-    double z[4][D];
-    load_block(nfull, tail, z);
 #pragma unroll 1
-    for (uint32_t s = 0; s < tail; ++s) {
+    for (uint32_t s = 0; s < tail; ++s) {            // zc holds block nfull
       double zz[D];
 #pragma unroll
-      for (int r = 0; r < D; ++r) zz[r] = s == 0u ? z[0][r] : s == 1u ? z[1][r] : z[2][r];
+      for (int r = 0; r < D; ++r) zz[r] = (double)(s == 0u ? zc[r][0] : s == 1u ? zc[r][1] : zc[r][2]);
       jne_lane_step<D, DET, SRC_RNG>(S, zz);
+    }
+  } else {
+    auto load_block = [&](uint32_t tb, uint32_t ns, double (&z)[4][D]) {
+      if constexpr (SRC_RNG) {
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+          jne_zt zf[4];
+          jne_normals4_keyed(keys, (uint32_t)r, tb, zf);
+#pragma unroll
+          for (int s = 0; s < 4; ++s) z[s][r] = (double)zf[s];
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+          for (int r = 0; r < D; ++r) z[s][r] = (uint32_t)s < ns ? dBrun[(uint64_t)(4u * tb + s) * D + r] : 0.0;
+      }
+    };
+    for (uint32_t tb = 0; tb < nfull; ++tb) {
+      double z[4][D];
+      load_block(tb, 4u, z);
+      jne_lane_step<D, DET, SRC_RNG>(S, z[0]);
+      jne_lane_step<D, DET, SRC_RNG>(S, z[1]);
+      jne_lane_step<D, DET, SRC_RNG>(S, z[2]);
+      jne_lane_step<D, DET, SRC_RNG>(S, z[3]);
+    }
+    if (tail != 0u) {
+      double z[4][D];
+      load_block(nfull, tail, z);
+#pragma unroll 1
+      for (uint32_t s = 0; s < tail; ++s) {
+        double zz[D];
+#pragma unroll
+        for (int r = 0; r < D; ++r) zz[r] = s == 0u ? z[0][r] : s == 1u ? z[1][r] : z[2][r];
+        jne_lane_step<D, DET, SRC_RNG>(S, zz);
+      }
     }
   }
   if (!live) return;
@@ -219,4 +256,197 @@ jne_lane_solve_kernel(const double* __restrict__ mom, uint64_t n, JneRunParams p
 
 template <int DP, bool MULTI> constexpr size_t jne_lane_solve_smem() {
   return (size_t)JNE_WARPS_PER_CTA * sizeof(double) * JneEpi<DP, MULTI ? 5 : 1>::END;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 for the lane family: one THREAD per run (dim <= 6), everything in registers.
+//
+// The warp-per-run epilogue of the tensor path costs ~7 000 warp instructions per run at dim 5 whatever the size of the
+// problem (ncu: issue-bound, 17 % of the c2 step next to the lane moments kernel); a 6 x 6 problem does not need 32
+// lanes.  Here a thread assembles S2 = sum F F' and R = S1' = sum F dB' of one model from the run's moments exactly as
+// jne_warp_assemble does (demeaning / detrending as Schur complements, src/johansen_statistics.rs:102-197), reduces the
+// pencil (S1'S1, S2) to the d x d Gram matrix G = R' S2^-1 R by a Cholesky factorisation and a forward substitution,
+// and diagonalises G by cyclic Jacobi -- all loops unrolled over the compile-time D, every array in registers.
+// Replaces GeneralizedEigen::new (LAPACK dggev) + |alpha| / beta + sort, src/johansen_statistics.rs:35-46.
+// Every model is computed on its own, so a block of a fused launch is bit-identical to the single-model launch.
+// Models whose F has D rows are embedded in the (D + 1)-row problem by a decoupled unit row (one code path).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ bool jne_thread_model(const double* __restrict__ M, int model, double T, double factor,
+                                                 double* __restrict__ out) {
+  constexpr int P = D + 1, NBB = D * (D + 1) / 2;
+  const double* bb = M;
+  const double* bz = M + NBB;
+  const double* tot = M + NBB + D * D;
+  double SB[D], S1B[D], S2B[D], Sz[D], S1z[D], S2z[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    SB[i] = tot[0 * D + i]; S1B[i] = tot[1 * D + i]; S2B[i] = tot[2 * D + i];
+    Sz[i] = tot[3 * D + i]; S1z[i] = tot[4 * D + i]; S2z[i] = tot[5 * D + i];
+  }
+  const double invT = 1.0 / T;
+  const double nu = T * (T * T - 1.0) / 3.0;               // sum w1^2
+  const double inv_nu = 1.0 / nu;                          // inf at T = 1 (model 4 needs T >= 3)
+  const bool demean = model >= 2, detrend = model == 4;
+  const bool trim = model == 2 || model == 4;              // F keeps D - 1 Brownian rows; the deterministic row is row D - 1
+  const bool extra = model == 1 || model == 3;             // F has D + 1 rows; the deterministic row is row D
+
+  double S2[P][P], R[P][D];                                // S2: lower triangle (i >= j)
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      double v = bb[j * D - ((j * (j - 1)) >> 1) + (i - j)];
+      if (demean) v -= SB[i] * SB[j] * invT;               // src/johansen_statistics.rs:120-125,145-150,186-194
+      if (detrend) v -= S1B[i] * S1B[j] * inv_nu;          // residual on [1, tau]   :186-194
+      S2[i][j] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double v = bz[i * D + j];
+      if (demean) v -= SB[i] * Sz[j] * invT;
+      if (detrend) v -= S1B[i] * S1z[j] * inv_nu;
+      R[i][j] = v;
+    }
+  }
+  // deterministic row: constant (model 1, :108-113), trend (i+1)/T - 1/2 = (w1+1)/(2T) carried as (w1+1)/T (models 2, 3,
+  // :127-135,152-160; NOT demeaned), residual of tau^2 on [1, tau] = w2 / (12 T^2) carried as w2 / T^2 (model 4, :170-194).
+  // Row scalings of F do not change the pencil's eigenvalues.
+  double s2v[D], rv[D], dg;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    s2v[j] = model == 1 ? SB[j] : model == 4 ? S2B[j] * invT * invT : S1B[j] * invT;
+    rv[j] = model == 1 ? Sz[j] : model == 4 ? S2z[j] * invT * invT : (S1z[j] + Sz[j]) * invT;
+  }
+  dg = model == 1 ? T : model == 4 ? 0.8 * T * (T * T - 1.0) * (T * T - 4.0) * invT * invT * invT * invT
+                                   : (nu + T) * invT * invT;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    if (trim) {
+      if (j < D - 1) S2[D - 1][j] = s2v[j]; else S2[D - 1][D - 1] = dg;
+      R[D - 1][j] = rv[j];
+    }
+    S2[D][j] = extra ? s2v[j] : 0.0;
+    R[D][j] = extra ? rv[j] : 0.0;
+  }
+  S2[D][D] = extra ? dg : 1.0;
+
+  // Cholesky S2 = L L' (left-looking; pivots through a wide-range rsqrt so that caller increments of any scale work,
+  // NaN for a non-positive pivot -> flagged below), W = L^-1 R, G = W' W.
+  double W[P][D];
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    double dj = S2[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) dj = fma(-S2[j][k], S2[j][k], dj);
+    const double inv = jne_rsqrt_wide(dj);
+#pragma unroll
+    for (int i = j + 1; i < P; ++i) {
+      double v = S2[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v = fma(-S2[i][k], S2[j][k], v);
+      S2[i][j] = v * inv;
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      double v = R[j][c];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v = fma(-S2[j][k], W[k][c], v);
+      W[j][c] = v * inv;
+    }
+  }
+  double G[D][D];                                          // upper triangle (a <= b)
+  double tr = 0.0;
+#pragma unroll
+  for (int a = 0; a < D; ++a)
+#pragma unroll
+    for (int b = a; b < D; ++b) {
+      double v = 0.0;
+#pragma unroll
+      for (int j = 0; j < P; ++j) v = fma(W[j][a], W[j][b], v);
+      G[a][b] = v;
+      if (a == b) tr += v;
+    }
+  const double inv_tr = 1.0 / tr;                          // unit trace: the rotation thresholds below are absolute
+#pragma unroll
+  for (int a = 0; a < D; ++a)
+#pragma unroll
+    for (int b = a; b < D; ++b) G[a][b] *= inv_tr;
+
+  // Cyclic Jacobi, rotation (p, q) applied as the exact similarity J' G J for the (c, s) actually used: tan(theta) comes
+  // from FP32 arithmetic (it only steers convergence), (c, s) is normalised in FP64.  Same skip rule as jne_warp_jacobi.
+  if (D > 1) {
+    const double tol = 8.8817841970012523e-16;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+      bool rotated = false;
+#pragma unroll
+      for (int p = 0; p < D - 1; ++p)
+#pragma unroll
+        for (int q = p + 1; q < D; ++q) {
+          const double app = G[p][p], aqq = G[q][q], apq = G[p][q];
+          const double diff = aqq - app;
+          if (fabs(apq) > tol && apq * apq > 1e-14 * fabs(diff) * fmin(app, aqq)) {
+            float th, hy, tf;
+            asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(th) : "f"((float)diff), "f"(2.0f * (float)apq));
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(hy) : "f"(fmaf(th, th, 1.0f)));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tf) : "f"(fabsf(th) + hy));
+            const double t = (double)copysignf(tf, th);
+            const double c = jne_rsqrt(fma(t, t, 1.0)), s = t * c;
+            rotated = true;
+            const double cc = c * c, ss = s * s, cs2 = 2.0 * c * s;
+            G[p][p] = fma(cc, app, fma(-cs2, apq, ss * aqq));
+            G[q][q] = fma(ss, app, fma(cs2, apq, cc * aqq));
+            G[p][q] = fma(c * s, app - aqq, (cc - ss) * apq);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+              if (k == p || k == q) continue;
+              double& gkp = k < p ? G[k][p] : G[p][k];
+              double& gkq = k < q ? G[k][q] : G[q][k];
+              const double x = gkp, y = gkq;
+              gkp = fma(c, x, -s * y);
+              gkq = fma(s, x, c * y);
+            }
+          }
+        }
+      if (!rotated) break;
+    }
+  }
+  // lambda_i = factor * trace * |g_ii| (src/johansen_statistics.rs:40-44: |alpha| / beta), sorted descending (:45) by
+  // rank counting; models 1 and 3 carry one extra eigenvalue that is exactly 0 here (rank-D pencil).
+  double ev[P];
+  const double scale = factor * tr;
+  bool finite = true;
+#pragma unroll
+  for (int k = 0; k < D; ++k) { ev[k] = fabs(G[k][k]) * scale; finite &= isfinite(ev[k]); }
+  ev[D] = 0.0 * scale;                                     // 0 * NaN keeps a failure visible
+  const int np = extra ? P : D;
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    if (k < np) {
+      int rank = 0;
+#pragma unroll
+      for (int j = 0; j < P; ++j)
+        if (j < np) rank += (ev[j] > ev[k]) || (ev[j] == ev[k] && j < k);
+      out[finite ? rank : k] = ev[k];                      // NaN compares false everywhere: keep the slots distinct
+    }
+  }
+  return finite;
+}
+
+template <int D>
+__global__ void __launch_bounds__(128)
+jne_lane_tsolve_kernel(const double* __restrict__ mom, uint64_t n, uint32_t model_mask, double T, double factor,
+                       uint32_t out_stride, double* __restrict__ out, unsigned int* __restrict__ err_count) {
+  const uint64_t run = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+  if (run >= n) return;
+  const double* M = mom + run * (uint64_t)JneLaneMom<D>::SZ;
+  double* o = out + run * out_stride;
+  bool ok = true;
+#pragma unroll 1
+  for (int model = 0; model < 5; ++model) {
+    if (!((model_mask >> model) & 1u)) continue;
+    ok &= jne_thread_model<D>(M, model, T, factor, o);
+    o += (model == 1 || model == 3) ? D + 1 : D;
+  }
+  if (!ok) atomicAdd(err_count, 1u);
 }

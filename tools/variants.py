@@ -12,7 +12,8 @@ VARIANTS = {
     "philox7": ["-DJNE_PHILOX_ROUNDS=7"],          # Random123's smallest Crush-resistant round count (default 10)
     "nobm": ["-DJNE_EXP_NOBM"],                    # Philox only, no normal transform (NOT a valid stream)
     "norng": ["-DJNE_EXP_NORNG"],                  # no generator at all (NOT a valid stream)
-    "lane5_minb2": ["-DJNE_LANE_MINB5=2"],         # dim 5 lane kernel: 255 registers, 2 resident CTAs per SM
+    "lane_nopipe": ["-DJNE_LANE_PIPELINE=0"],      # lane family without the software pipeline (generate a block, then consume it)
+    "lane_nopipe_minb3": ["-DJNE_LANE_PIPELINE=0", "-DJNE_LANE_MINB5=3"],   # ... and dim 5 at 168 registers / 3 CTAs per SM
 }
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-pthread"]
 
