@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--cpu-runs", type=int, default=0, help="CPU sample: runs per model (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dat", action="store_true", help="skip the end-to-end figure that includes the .dat files")
+    ap.add_argument("--sustain-s", type=float, default=10.0, help="length of the sustained window (0 = skip)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c2 figures and the in-process multi-device figure")
     return ap.parse_args()
 
 
@@ -273,6 +275,26 @@ def main():
     total_runs = len(MODELS) * R * args.steps * world
     value = total_runs / (ms_max * 1e-3)
 
+    # ---- sustained window: the same device-resident step back to back for >= --sustain-s seconds, clocks sampled
+    #      (shows whether the short timed region above survives power management) ----
+    sustained = None
+    if args.sustain_s > 0:
+        n_sus = max(1, int(np.ceil(args.sustain_s / (ms / args.steps * 1e-3))))
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as sus_clocks:
+            s0.record(stream)
+            for _ in range(n_sus):
+                device_step(False)
+            s1.record(stream)
+            barrier()
+        ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sustained = {"value": len(MODELS) * R * n_sus * world / (float(ts.item()) * 1e-3), "unit": "runs/s", "steps": n_sus,
+                     "seconds": float(ts.item()) * 1e-3, "clocks": sus_clocks.summary()}
+        eng.check_async()
+
     # ---- e2e: host buffers through the public API (H2D seeds + D2H eigenvalues inside) ----
     eng.eigs_batch_multi(MODELS, dim, T, seeds_np[: min(R, 4096)])
     barrier()
@@ -309,6 +331,55 @@ def main():
             dat_error = f"{type(exc).__name__}: {exc}"
         finally:
             shutil.rmtree(tmpdir, ignore_errors=True)
+    # ---- rank 0 extras: BASELINE config c2 (dim 5, T 5 000) on this GPU, and ONE in-process context over every
+    #      visible GPU with host buffers (what the reference-side FFI shim creates: jne_init(NULL, 0)) ----
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        def timed(models, dim2, T2, n2, reps=3):
+            ds = torch.arange(1, n2 + 1, dtype=torch.int32, device="cuda")
+            do = torch.empty((n2, sum(jne.num_eigs(m, dim2) for m in models)), dtype=torch.float64, device="cuda")
+            best = 1e30
+            for _ in range(reps + 1):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                if len(models) == 1:
+                    eng.eigs_batch_device(models[0], dim2, T2, ds.data_ptr(), n2, do.data_ptr(), stream.cuda_stream)
+                else:
+                    eng.eigs_batch_multi_device(models, dim2, T2, ds.data_ptr(), n2, do.data_ptr(), stream.cuda_stream)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            eng.check_async()
+            return best
+        n2 = 1 << 20
+        c2 = {"workload": f"README example (BASELINE configs[1]): dim 5, T 5000, {n2} seeds per launch, device-resident, best of 3"}
+        t = timed(MODELS, 5, 5000, n2)
+        c2["fused_runs_per_s"] = len(MODELS) * n2 / (t * 1e-3)
+        pm = {m: timed([m], 5, 5000, n2) for m in MODELS}
+        c2["per_model_runs_per_s"] = {str(m): n2 / (pm[m] * 1e-3) for m in MODELS}
+        c2["per_model_frac_of_fp64_peak"] = {str(m): jne.flops_per_run(m, 5, 5000) * n2 / (pm[m] * 1e-3) / 1e12 / peak for m in MODELS}
+        extras["c2"] = c2
+    if world > 1:
+        dist.barrier()          # the other ranks idle while rank 0 drives every GPU from one process
+    if rank == 0 and not args.no_extras:
+        try:
+            nvis = torch.cuda.device_count()
+            eng_all = jne.Engine(None)
+            seeds_all = np.arange(1, R * nvis + 1, dtype=np.uint32)
+            buf_all = np.empty((seeds_all.size, width), dtype=np.float64)
+            eng_all.eigs_batch_multi(MODELS, dim, T, seeds_all[: 4096 * nvis])
+            i0 = time.perf_counter()
+            reps_ip = max(1, min(args.steps, 5))
+            for _ in range(reps_ip):
+                eng_all.eigs_batch_multi(MODELS, dim, T, seeds_all, out=buf_all)
+            ip_s = time.perf_counter() - i0
+            extras["e2e_inprocess"] = {"value": len(MODELS) * seeds_all.size * reps_ip / ip_s, "unit": "runs/s", "devices": nvis,
+                                       "note": "one jne context over every visible GPU (jne_init(NULL, 0)), host buffers, seed-sharded inside the library"}
+            eng_all.close()
+        except Exception as exc:
+            extras["e2e_inprocess"] = {"value": None, "error": f"{type(exc).__name__}: {exc}"}
+    if world > 1:
+        dist.barrier()
     h2d = 4 * R
     d2h = 8 * R * width
     tp = torch.tensor([pm_ms], dtype=torch.float64, device="cuda")
@@ -323,13 +394,20 @@ def main():
         pm_dur_ms = sum(float(np.mean(kern_ms[m])) for m in MODELS)
         per_model = {str(m): round(jne.flops_per_run(m, dim, T) * R / (float(np.mean(kern_ms[m])) * 1e-3) / 1e12, 3)
                      for m in MODELS}
-        traffic = None
-        tfile = ROOT / "profiles" / "traffic_bytes_per_launch.json"
+        # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture of this very
+        # launch shape (tools/ncu_target.py --n R; tools/ncu_traffic.py writes the file).  Only quoted when the capture
+        # was taken at the same seeds-per-launch and configuration; never extrapolated.
+        traffic, traffic_src = None, None
+        tfile = ROOT / "profiles" / "r2_traffic_fused_d12.json"
         if tfile.exists():
             try:
-                traffic = json.loads(tfile.read_text()).get("dram_bytes_per_run") * R   # per launch of R seeds
+                tj = json.loads(tfile.read_text())
+                if tj.get("seeds_in_launch") == R and tj.get("dim") == dim and tj.get("steps") == T:
+                    traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                    traffic_src = f"profiles/{tfile.name} ({tj.get('report')})"
             except Exception:
                 traffic = None
+        contraction_flops_run = 2.0 * T * (dim * (dim + 1) / 2 + dim * dim)
         line = {
             "metric": METRIC, "value": value, "unit": "runs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -344,7 +422,12 @@ def main():
                 # the FP64 tensor pipe (DMMA.8x8x4; scalar DFMA shares the same datapath and the same cap)
                 "bound": "tensor", "precision": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak,
-                "traffic": traffic,
+                "frac_definition": "fused pass, its own flop count (incl. the five trend moments per row)",
+                "frac_contraction_only": contraction_flops_run * R / (dur_ms * 1e-3) / 1e12 / peak,
+                "frac_per_model_s8d": model_flops_step / (pm_dur_ms * 1e-3) / 1e12 / peak,
+                "frac_per_model_s8d_definition": "SURVEY section 8(d): F_alg = 2T[p(p+1)/2 + p d] per run, five per-model launches "
+                                                 "(per_model_path); the fused pass serves the same runs with 4.1x fewer flops",
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured in this run: register-resident DFMA / DMMA m8n8k4 chains (jne_fp64_peak_tflops); "
                                "MEASURED_PEAKS.json holds no FP64 figure",
                 "peak_dfma": peak_dfma, "peak_dmma": peak_dmma, "peak_nominal": NOMINAL_FP64_TFLOPS,
@@ -367,6 +450,9 @@ def main():
             "gpu_launches": int(gpu_launches),
             "clocks": clocks.summary(),
         }
+        if sustained is not None:
+            line["sustained"] = sustained
+        line.update(extras)
         if dat_error is not None:
             line["e2e_dat"] = {"value": None, "unit": "runs/s", "error": dat_error}
         if dat_value is not None:

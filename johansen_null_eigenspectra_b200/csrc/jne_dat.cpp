@@ -101,7 +101,7 @@ long walk(const Reader& r, long data_end, uint64_t limit, bool scan, F&& on_reco
     uint32_t seed;
     const int used = read_uleb(r, pos, &seed);
     if (used <= 0) { if (!scan && err) *err = "Incomplete ULEB128 encoding"; break; }
-    if (pos + used >= r.len) break;
+    if (pos + used >= data_end) break;                 // the count byte must lie inside the record area
     const int cnt = r.p[pos + used];
     const long payload = pos + used + 1;
     if (cnt == 0) {
@@ -208,7 +208,7 @@ int jne_dat_read(const char* path, uint32_t* seeds, double* eigs, uint64_t capac
   const bool trailer = read_trailer(r, &count, &pr);
   std::string err;
   bool mismatch = false;
-  uint64_t n = 0;
+  uint64_t n = 0, walked = 0;
   const uint64_t limit = trailer ? (count < capacity ? count : capacity) : capacity;
   walk(r, trailer ? len - kTrailer : len, limit, !trailer,
        [&](uint32_t seed, uint32_t c, long payload) {
@@ -217,8 +217,13 @@ int jne_dat_read(const char* path, uint32_t* seeds, double* eigs, uint64_t capac
          memcpy(eigs + n * p, r.p + payload, 8 * (size_t)p);      // little-endian host assumed (x86-64 / aarch64)
          ++n;
          return true;
-       }, &count, &err);
+       }, &walked, &err);
   if (mismatch) return fail(err);
+  // Fast path (reader.rs:107-160): every one of the trailer's `count` records must be there -- a zero count, a bad
+  // ULEB128 or a record cut short is InvalidData / UnexpectedEof in the reference, not a short read.
+  if (trailer && n < limit)
+    return fail(!err.empty() ? err : "unexpected end of file: the trailer promises " + std::to_string(count) +
+                                     " records, " + std::to_string(n) + " are readable");
   if (n_read) *n_read = n;
   return JNE_OK;
 }
@@ -249,8 +254,20 @@ int jne_dat_open(const char* path, uint8_t model, uint8_t dim, uint32_t steps, u
                                  [&](uint32_t, uint32_t c, long) { if (!first) first = c; return true; }, &have, nullptr);
       per_run = first;
       r.close_map();
-      // drop the trailer (writer.rs:181-203) and any torn tail so that appended records stay parseable
-      if (truncate(path, good_end) != 0) return fail(std::string("truncate failed: ") + strerror(errno));
+      if (trailer && (have != count || good_end != len - kTrailer)) {
+        // A FINISHED file whose records do not add up to its trailer is damaged.  The reference's progress check
+        // treats it as "no progress" (progress.rs:51) and its writer then appends behind the damaged bytes
+        // (writer.rs:150-158), which leaves an unreadable file.  Here nothing is thrown away silently: the damaged
+        // file is set aside as <path>.damaged and the job restarts on a fresh file, as the progress check implies.
+        const std::string aside = std::string(path) + ".damaged";
+        fprintf(stderr, "WARNING: %s: trailer promises %llu records, %llu readable; kept as %s, starting a fresh file\n", path,
+                (unsigned long long)count, (unsigned long long)have, aside.c_str());
+        if (rename(path, aside.c_str()) != 0) return fail(std::string("cannot set the damaged file aside: ") + strerror(errno));
+        fresh = true; have = 0; per_run = 0;
+      } else if (truncate(path, good_end) != 0) {
+        // drop the trailer (writer.rs:181-203) and, in an interrupted file, the torn tail so that appended records stay parseable
+        return fail(std::string("truncate failed: ") + strerror(errno));
+      }
     }
   }
   jne_dat_writer* w = new jne_dat_writer();
@@ -381,12 +398,18 @@ int jne_dat_completed_bitmap(const char* path, uint8_t model, uint8_t dim, uint3
   uint64_t count = 0; uint32_t pr = 0;
   const bool trailer = read_trailer(r, &count, &pr);
   uint64_t n = 0;
-  walk(r, trailer ? len - kTrailer : len, trailer ? count : UINT64_MAX, !trailer,
+  const long good_end = walk(r, trailer ? len - kTrailer : len, trailer ? count : UINT64_MAX, !trailer,
        [&](uint32_t seed, uint32_t, long) {
          if (seed >= 1 && seed <= num_runs) bitmap[(seed - 1) >> 3] |= (uint8_t)(1u << ((seed - 1) & 7));
          return true;
        }, &n, nullptr);
-  if (completed) *completed = n;
+  if (trailer && (n != count || good_end != len - kTrailer)) {
+    // the reference's fast read fails on such a file (reader.rs:107-160) and check_append_progress then reports
+    // no progress at all (progress.rs:51): restart
+    memset(bitmap, 0, (num_runs + 7) / 8);
+    n = 0;
+  }
+  if (completed) *completed = n;      // ALL records of the file, also seeds beyond num_runs (progress.rs:47)
   return JNE_OK;
 }
 

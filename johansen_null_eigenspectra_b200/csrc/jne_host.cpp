@@ -43,9 +43,13 @@ SimulationStats run_model_simulation(const Engine& gpu, Model model, uint32_t di
     completed = 0;
   }
   st.completed_before = completed;
+  if (completed >= num_runs) {                          // the reference counts ALL records of the file, also seeds beyond
+    st.total_in_file = completed;                       // num_runs, and skips the job (:182-188)
+    return st;
+  }
   std::vector<uint32_t> remaining(jne_dat_remaining_seeds(bitmap.data(), num_runs, nullptr, 0));
   jne_dat_remaining_seeds(bitmap.data(), num_runs, remaining.data(), remaining.size());
-  if (remaining.empty()) {                              // already complete (:182-198)
+  if (remaining.empty()) {                              // already complete (:190-198)
     st.total_in_file = completed;
     return st;
   }
@@ -116,6 +120,7 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
       }
       stats[m].completed_before = completed;
       stats[m].total_in_file = completed;
+      if (completed >= num_runs) continue;               // parallel_compute.rs:182-188: enough records, whatever their seeds
       for (uint64_t s = 0; s < num_runs; ++s)
         if (!((bitmap[s >> 3] >> (s & 7)) & 1u)) need[s] |= (uint8_t)(1u << m);
     }

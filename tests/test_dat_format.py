@@ -188,3 +188,46 @@ def test_strided_append_matches_contiguous(tmp_path):
     rc = dat.lib.jne_dat_append_batch_strided(w._w, seeds.ctypes.data, rows.ctypes.data, 10, 3, 2)
     assert rc < 0 and b"stride" in dat.lib.jne_dat_last_error()
     w.finish()
+
+
+def test_damaged_finished_file(tmp_path):
+    """A FINISHED file (trailer present) whose records do not add up to the trailer.  The reference's fast read fails on
+    it (reader.rs:107-160: InvalidData / UnexpectedEof), its progress check then reports no progress (progress.rs:51),
+    and its writer appends behind the damaged bytes (writer.rs:150-158).  Here: the read is an error, the progress check
+    says restart, and the writer sets the damaged file aside as <name>.damaged instead of truncating or appending."""
+    path = tmp_path / "dmg.dat"
+    w = dat.AppendOnlyWriter(path, 0, 2, 50)
+    w.append_batch(np.arange(1, 11), np.arange(20, dtype=np.float64).reshape(10, 2))
+    w.finish()
+    raw = path.read_bytes()
+    rec = 1 + 1 + 16
+    assert len(raw) == 18 + 10 * rec + 17
+    # (a) the count byte of record 4 zeroed: "Invalid eigenvalue count: cannot be zero" in the reference
+    bad = bytearray(raw); bad[18 + 3 * rec + 1] = 0
+    path.write_bytes(bytes(bad))
+    with pytest.raises(JneError, match="Invalid eigenvalue count"):
+        dat.read_append_file(path)
+    done, rem = dat.check_append_progress(path, 0, 2, 50, 10)
+    assert done == 0 and list(rem) == list(range(1, 11))               # restart, as check_append_progress does
+    # (b) three records cut out of the middle, trailer kept: the trailer promises 10, 7 are there
+    path.write_bytes(raw[:18 + 4 * rec] + raw[18 + 7 * rec:])
+    with pytest.raises(JneError, match="unexpected end of file|Incomplete ULEB128"):
+        dat.read_append_file(path)
+    assert dat.check_append_progress(path, 0, 2, 50, 10)[0] == 0
+    w = dat.AppendOnlyWriter(path, 0, 2, 50)                            # nothing is dropped silently ...
+    assert w.existing_records == 0
+    w.append_batch([1], [[1.0, 2.0]])
+    w.finish()
+    aside = tmp_path / "dmg.dat.damaged"
+    assert aside.exists() and aside.read_bytes() == raw[:18 + 4 * rec] + raw[18 + 7 * rec:]   # ... the damaged bytes are kept
+    seeds, eigs, *_ = dat.read_append_file(path)
+    assert list(seeds) == [1] and eigs.tolist() == [[1.0, 2.0]]
+    # an INTERRUPTED file (no trailer) with a torn tail is still resumed in place (reader.rs:157-216)
+    torn = tmp_path / "torn.dat"
+    torn.write_bytes(raw[:18 + 6 * rec + 5])
+    done, rem = dat.check_append_progress(torn, 0, 2, 50, 10)
+    assert done == 6 and list(rem) == [7, 8, 9, 10]
+    w = dat.AppendOnlyWriter(torn, 0, 2, 50)
+    assert w.existing_records == 6
+    w.finish()
+    assert os.path.getsize(torn) == 18 + 6 * rec + 17 and not (tmp_path / "torn.dat.damaged").exists()
