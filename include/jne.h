@@ -139,14 +139,17 @@ int jne_eigs_batch_debug(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t ste
 /* ---- streaming statistics ------------------------------------------- */
 
 /* Percentiles of the trace (sum of a record's eigenvalues) and of the max-eigenvalue over n records resident on
- * device 0 (row i at d_eigs + i*stride, p values) -- calculate_trace_percentiles / calculate_maxeig_percentiles,
+ * device 0 of the context (row i at d_eigs + i*stride, p values) -- calculate_trace_percentiles / calculate_maxeig_percentiles,
  * src/simulation_analyzers.rs:42-81, which today re-read and sort the whole .dat file on the host.  qs: n_q
  * fractions in [0,1]; value at rank q (n-1) with linear interpolation (:4-18).  qs / outputs are HOST arrays. */
 int jne_percentiles_device(jne_ctx* ctx, const void* d_eigs, uint64_t n, uint32_t p, uint32_t stride,
                            const double* qs, uint32_t n_q, double* trace_out, double* maxeig_out, void* stream);
 
-/* Simulate seeds first_seed .. first_seed+n-1 on device 0 and return only those percentiles: eigenvalues never
- * leave the GPU (seeds are generated on the device, records are reduced to (trace, max) as they are produced). */
+/* Simulate seeds first_seed .. first_seed+n-1 on EVERY device of the context (contiguous shares) and return only those
+ * percentiles: eigenvalues never leave the GPUs (seeds are generated on the device, records are reduced to (trace, max)
+ * as they are produced, the order statistics are found by an exact digit-by-digit selection whose per-device
+ * histograms are the only data merged on the host -- no sort, no collective).  The result does not depend on the
+ * number of devices.  At most 16 percentiles per call. */
 int jne_simulate_percentiles(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, uint32_t first_seed,
                              uint64_t n, const double* qs, uint32_t n_q, double* trace_out, double* maxeig_out);
 

@@ -15,8 +15,6 @@
 #include <thread>
 #include <vector>
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include "../../include/jne.h"
 #include "jne_kernels.cuh"
 #include "jne_kernels_lane.cuh"
@@ -711,18 +709,39 @@ __global__ void jne_aggregate_kernel(const double* __restrict__ eigs, uint64_t n
   maxeig[i] = mx;
 }
 
-// get_percentile_value of src/simulation_analyzers.rs:4-18: rank = q (n-1), linear interpolation.
-__global__ void jne_percentile_kernel(const double* __restrict__ sorted, uint64_t n, const double* __restrict__ qs,
-                                      uint32_t nq, double* __restrict__ out) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nq) return;
-  if (n == 0) { out[k] = __longlong_as_double(0x7ff8000000000000ll); return; }
-  const double rank = qs[k] * (double)(n - 1);
-  const uint64_t lo = (uint64_t)floor(rank), hi = (uint64_t)ceil(rank);
-  if (lo == hi) { out[k] = sorted[lo]; return; }
-  const double w = rank - (double)lo;
-  // two products and one sum, each rounded (no FMA contraction): bit-identical to the reference's expression
-  out[k] = __dadd_rn(__dmul_rn(sorted[lo], 1.0 - w), __dmul_rn(sorted[hi], w));
+// ---- exact order statistics without a sort (row f3) ----
+// Doubles map to 64-bit keys whose unsigned order is the doubles' order.  The k-th smallest key of a sample that is
+// spread over several arrays (one per device) is found digit by digit: four passes of 16 bits, each a histogram of
+// the next digit over the keys that match the prefixes found so far.  Several ranks are resolved together (one
+// histogram row per distinct prefix).  Nothing but histograms leaves a device; the result does not depend on how the
+// sample is partitioned.
+__device__ __forceinline__ uint64_t jne_order_key(double x) {
+  const uint64_t b = (uint64_t)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+constexpr int kSelMaxGroups = 32;
+struct JneSelPrefixes { uint64_t prefix[kSelMaxGroups]; int n; };
+// hist[g][digit] += 1 for every key whose bits above the digit equal prefix[g] (pass 0: one group, every key)
+__global__ void __launch_bounds__(256)
+jne_select_hist_kernel(const double* __restrict__ vals, uint64_t n, int shift, JneSelPrefixes pf, unsigned int* __restrict__ hist) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += stride) {   // whole warps stay together
+    const uint64_t i = base + threadIdx.x;
+    int slot = -1;
+    if (i < n) {
+      const uint64_t key = jne_order_key(vals[i]);
+      const uint64_t hi = shift >= 48 ? 0ull : key >> (shift + 16);
+      int g = -1;
+      for (int k = 0; k < pf.n; ++k) if (pf.prefix[k] == hi) g = k;
+      if (g >= 0) slot = (g << 16) | (int)((key >> shift) & 0xffffull);
+    }
+    // warp-aggregated: one atomic per distinct (group, digit) in the warp (the leading digits of a sample are few)
+    const unsigned active = __ballot_sync(0xffffffffu, slot >= 0);
+    if (slot >= 0) {
+      const unsigned peers = __match_any_sync(active, slot);
+      if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(hist + slot, (unsigned int)__popc(peers));
+    }
+  }
 }
 
 __global__ void jne_iota_kernel(uint32_t first, uint64_t n, uint32_t* __restrict__ out) {
@@ -1145,34 +1164,204 @@ int jne_pencil_eigs_batch(jne_ctx* ctx, uint32_t p, uint32_t d, const double* S1
   return JNE_OK;
 }
 
-// Sort the two aggregate arrays and interpolate the requested percentiles; d_trace / d_max hold n doubles each and
-// are followed by n more doubles each of sort space.  Results land in the host arrays.
-static int percentiles_of(jne_ctx* ctx, Device& dv, double* d_trace, double* d_max, uint64_t n, const double* qs,
-                          uint32_t nq, double* trace_out, double* maxeig_out, cudaStream_t st) {
-  size_t tmp_bytes = 0;
-  JNE_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_trace, d_trace + n, (int64_t)n, 0, 64, st));
-  void* d_tmp = nullptr;
-  double* d_q = nullptr;
-  JNE_CUDA(ctx, cudaMalloc(&d_tmp, tmp_bytes + 64));
-  JNE_CUDA(ctx, cudaMalloc(&d_q, 3 * (size_t)nq * sizeof(double)));
+}  // extern "C"
+
+namespace {
+
+// One statistic of one model: its values as they lie on the context's devices (n[i] doubles at vals[i] on device i).
+struct SelSample { std::vector<const double*> vals; std::vector<uint64_t> n; };
+
+// x_(k) for every k in ranks (0-based, any order, duplicates allowed) of the union of the sample's arrays.
+int select_ranks(jne_ctx* ctx, const std::vector<int>& dev_index, const SelSample& smp, const std::vector<uint64_t>& ranks,
+                 std::vector<double>* out) {
+  const size_t nr = ranks.size(), nd = smp.vals.size();
+  std::vector<uint64_t> prefix(nr, 0), within(ranks);
+  std::vector<unsigned int*> d_hist(nd, nullptr);
+  std::vector<unsigned int> h_hist, h_part;
   auto body = [&]() -> int {
-    JNE_CUDA(ctx, cudaMemcpyAsync(d_q, qs, nq * sizeof(double), cudaMemcpyHostToDevice, st));
-    JNE_CUDA(ctx, cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_trace, d_trace + n, (int64_t)n, 0, 64, st));
-    jne_percentile_kernel<<<(nq + 63) / 64, 64, 0, st>>>(d_trace + n, n, d_q, nq, d_q + nq);
-    JNE_CUDA(ctx, cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_max, d_max + n, (int64_t)n, 0, 64, st));
-    jne_percentile_kernel<<<(nq + 63) / 64, 64, 0, st>>>(d_max + n, n, d_q, nq, d_q + 2 * nq);
-    JNE_CUDA(ctx, cudaGetLastError());
-    ctx->launches.fetch_add(2);
-    JNE_CUDA(ctx, cudaMemcpyAsync(trace_out, d_q + nq, nq * sizeof(double), cudaMemcpyDeviceToHost, st));
-    JNE_CUDA(ctx, cudaMemcpyAsync(maxeig_out, d_q + 2 * nq, nq * sizeof(double), cudaMemcpyDeviceToHost, st));
-    JNE_CUDA(ctx, cudaStreamSynchronize(st));
+    for (size_t i = 0; i < nd; ++i) {
+      JNE_CUDA(ctx, cudaSetDevice(ctx->devs[dev_index[i]].id));
+      JNE_CUDA(ctx, cudaMalloc(&d_hist[i], (size_t)kSelMaxGroups * 65536 * sizeof(unsigned int)));
+    }
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 48 - 16 * pass;
+      JneSelPrefixes pf{};
+      std::vector<int> group(nr);
+      for (size_t r = 0; r < nr; ++r) {                  // distinct prefixes among the ranks still being resolved
+        int g = -1;
+        for (int k = 0; k < pf.n; ++k) if (pf.prefix[k] == prefix[r]) g = k;
+        if (g < 0) {
+          if (pf.n == kSelMaxGroups) return fail(ctx, JNE_ERR_INVALID_ARG, "too many distinct percentiles in one call (at most 16)");
+          g = pf.n; pf.prefix[pf.n++] = prefix[r];
+        }
+        group[r] = g;
+      }
+      const size_t words = (size_t)pf.n * 65536;
+      h_hist.assign(words, 0u);
+      h_part.resize(words);
+      for (size_t i = 0; i < nd; ++i) {
+        if (smp.n[i] == 0) continue;
+        Device& dv = ctx->devs[dev_index[i]];
+        JNE_CUDA(ctx, cudaSetDevice(dv.id));
+        JNE_CUDA(ctx, cudaMemsetAsync(d_hist[i], 0, words * sizeof(unsigned int), dv.stream));
+        const unsigned grid = (unsigned)std::min<uint64_t>((smp.n[i] + 255) / 256, (uint64_t)dv.sm_count * 16);
+        jne_select_hist_kernel<<<grid, 256, 0, dv.stream>>>(smp.vals[i], smp.n[i], shift, pf, d_hist[i]);
+        JNE_CUDA(ctx, cudaGetLastError());
+        ctx->launches.fetch_add(1);
+      }
+      for (size_t i = 0; i < nd; ++i) {                  // merge: the only data that leaves a device
+        if (smp.n[i] == 0) continue;
+        Device& dv = ctx->devs[dev_index[i]];
+        JNE_CUDA(ctx, cudaSetDevice(dv.id));
+        JNE_CUDA(ctx, cudaMemcpyAsync(h_part.data(), d_hist[i], words * sizeof(unsigned int), cudaMemcpyDeviceToHost, dv.stream));
+        JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+        for (size_t w = 0; w < words; ++w) h_hist[w] += h_part[w];
+      }
+      for (size_t r = 0; r < nr; ++r) {
+        const unsigned int* h = h_hist.data() + (size_t)group[r] * 65536;
+        uint64_t cum = 0;
+        int digit = 0;
+        for (; digit < 65536; ++digit) {
+          if (within[r] < cum + h[digit]) break;
+          cum += h[digit];
+        }
+        if (digit == 65536) return fail(ctx, JNE_ERR_INVALID_ARG, "rank outside the sample");
+        within[r] -= cum;
+        prefix[r] = (prefix[r] << 16) | (uint64_t)digit;
+      }
+    }
+    out->resize(nr);
+    for (size_t r = 0; r < nr; ++r) {
+      const uint64_t key = prefix[r];
+      const uint64_t bits = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
+      std::memcpy(&(*out)[r], &bits, 8);
+    }
     return JNE_OK;
   };
   const int rc = body();
-  cudaFree(d_tmp);
-  cudaFree(d_q);
+  for (size_t i = 0; i < nd; ++i)
+    if (d_hist[i]) { cudaSetDevice(ctx->devs[dev_index[i]].id); cudaFree(d_hist[i]); }
   return rc;
 }
+
+// get_percentile_value of src/simulation_analyzers.rs:4-18 for every q: rank = q (n - 1), linear interpolation between
+// the two neighbouring order statistics; two products and one sum, each rounded (no FMA contraction), as the reference.
+int percentiles_of_sample(jne_ctx* ctx, const std::vector<int>& dev_index, const SelSample& smp, const double* qs, uint32_t nq,
+                          double* out) {
+  uint64_t n = 0;
+  for (uint64_t m : smp.n) n += m;
+  if (n == 0) { for (uint32_t k = 0; k < nq; ++k) out[k] = std::nan(""); return JNE_OK; }
+  std::vector<uint64_t> ranks;
+  for (uint32_t k = 0; k < nq; ++k) {
+    const double rank = qs[k] * (double)(n - 1);
+    if (!(rank >= 0.0) || rank > (double)(n - 1)) return fail(ctx, JNE_ERR_INVALID_ARG, "percentile outside [0, 1]");
+    ranks.push_back((uint64_t)std::floor(rank));
+    ranks.push_back((uint64_t)std::ceil(rank));
+  }
+  std::vector<double> x;
+  const int rc = select_ranks(ctx, dev_index, smp, ranks, &x);
+  if (rc) return rc;
+  for (uint32_t k = 0; k < nq; ++k) {
+    const double rank = qs[k] * (double)(n - 1);
+    const uint64_t lo = ranks[2 * k], hi = ranks[2 * k + 1];
+    if (lo == hi) { out[k] = x[2 * k]; continue; }
+    const double w = rank - (double)lo;
+    volatile double a = x[2 * k] * (1.0 - w), b = x[2 * k + 1] * w;   // volatile: two roundings, then the sum
+    out[k] = a + b;
+  }
+  return JNE_OK;
+}
+
+// Simulates seeds first_seed .. first_seed + n - 1 for every model of the mask on ALL devices of the context (contiguous
+// shares, one host thread per device) and keeps, per model, trace and max-eig of every run on the device that computed
+// it; then the percentiles by exact distributed selection.
+int simulate_percentiles_impl(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps, uint32_t first_seed, uint64_t n,
+                              const double* qs, uint32_t nq, double* trace_out, double* maxeig_out) {
+  const size_t nd = ctx->devs.size();
+  const int nm = __builtin_popcount(model_mask);
+  const JneRunParams prm0 = make_params_mask(model_mask, dim, steps, false);
+  std::vector<double*> d_agg(nd, nullptr);                 // per device: [model slot][trace | max][share]
+  std::vector<uint64_t> share(nd, 0), start(nd, 0);
+  const uint64_t per = (n + nd - 1) / nd;
+  for (size_t i = 0; i < nd; ++i) { start[i] = std::min<uint64_t>(i * per, n); share[i] = std::min<uint64_t>(start[i] + per, n) - start[i]; }
+  std::vector<int> rcs(nd, JNE_OK);
+  std::vector<std::string> errs(nd);
+  auto device_part = [&](size_t i) -> int {
+    Device& dv = ctx->devs[i];
+    const uint64_t ni = share[i];
+    if (ni == 0) return JNE_OK;
+    JNE_CUDA(ctx, cudaSetDevice(dv.id));
+    JneRunParams prm = prm0;
+    prm.jtab = jtab_for(dv, dim);
+    const uint64_t chunk = 1ull << 19;
+    uint32_t* d_seeds = nullptr;
+    double* d_eigs = nullptr;
+    JNE_CUDA(ctx, cudaMalloc(&d_agg[i], (size_t)nm * 2 * ni * sizeof(double)));
+    JNE_CUDA(ctx, cudaMalloc(&d_seeds, chunk * sizeof(uint32_t)));
+    if (cudaMalloc(&d_eigs, chunk * prm.out_stride * sizeof(double)) != cudaSuccess) { cudaFree(d_seeds); return fail(ctx, JNE_ERR_CUDA, "out of device memory"); }
+    auto body = [&]() -> int {
+      JNE_CUDA(ctx, cudaMemsetAsync(dv.d_err, 0, sizeof(unsigned int), dv.stream));
+      for (uint64_t off = 0; off < ni; off += chunk) {
+        const uint64_t m = std::min(chunk, ni - off);
+        jne_iota_kernel<<<(unsigned)((m + 255) / 256), 256, 0, dv.stream>>>(first_seed + (uint32_t)(start[i] + off), m, d_seeds);
+        JNE_CUDA(ctx, launch_run<true>(ctx, dv, d_seeds, nullptr, m, prm, d_eigs, dv.d_err, nullptr, dv.stream));
+        ctx->launches.fetch_add(2);
+        uint32_t col = 0;
+        int slot = 0;
+        for (int mod = 0; mod < 5; ++mod) {              // one Brownian path per seed serves every selected model
+          if (!((model_mask >> mod) & 1u)) continue;
+          const uint32_t p = (mod == 1 || mod == 3) ? dim + 1 : dim;
+          double* agg = d_agg[i] + (size_t)slot * 2 * ni;
+          jne_aggregate_kernel<<<(unsigned)((m + 255) / 256), 256, 0, dv.stream>>>(d_eigs + col, m, p, prm.out_stride, agg + off, agg + ni + off);
+          ctx->launches.fetch_add(1);
+          col += p; ++slot;
+        }
+        JNE_CUDA(ctx, cudaGetLastError());
+      }
+      JNE_CUDA(ctx, cudaMemcpyAsync(dv.h_err, dv.d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, dv.stream));
+      JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+      if (*dv.h_err) return fail(ctx, JNE_ERR_NONFINITE, "non-finite eigenvalues");
+      return JNE_OK;
+    };
+    const int rc = body();
+    cudaFree(d_seeds); cudaFree(d_eigs);
+    return rc;
+  };
+  if (nd == 1) {
+    rcs[0] = device_part(0);
+  } else {
+    std::vector<std::thread> th;
+    try {
+      for (size_t i = 0; i < nd; ++i)
+        th.emplace_back([&, i]() { rcs[i] = device_part(i); if (rcs[i]) { std::lock_guard<std::mutex> lk(ctx->err_mu); errs[i] = ctx->err; } });
+    } catch (...) { for (auto& t : th) t.join(); throw; }
+    for (auto& t : th) t.join();
+  }
+  int rc = JNE_OK;
+  for (size_t i = 0; i < nd; ++i)
+    if (rcs[i] && !rc) { rc = rcs[i]; if (nd > 1) { std::lock_guard<std::mutex> lk(ctx->err_mu); ctx->err = errs[i]; } }
+  if (!rc) {
+    std::vector<int> dev_index(nd);
+    for (size_t i = 0; i < nd; ++i) dev_index[i] = (int)i;
+    for (int slot = 0; slot < nm && !rc; ++slot) {
+      SelSample tr, mx;
+      for (size_t i = 0; i < nd; ++i) {
+        const double* agg = d_agg[i] ? d_agg[i] + (size_t)slot * 2 * share[i] : nullptr;
+        tr.vals.push_back(agg); tr.n.push_back(share[i]);
+        mx.vals.push_back(agg ? agg + share[i] : nullptr); mx.n.push_back(share[i]);
+      }
+      rc = percentiles_of_sample(ctx, dev_index, tr, qs, nq, trace_out + (size_t)slot * nq);
+      if (!rc) rc = percentiles_of_sample(ctx, dev_index, mx, qs, nq, maxeig_out + (size_t)slot * nq);
+    }
+  }
+  for (size_t i = 0; i < nd; ++i)
+    if (d_agg[i]) { cudaSetDevice(ctx->devs[i].id); cudaFree(d_agg[i]); }
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
 
 int jne_percentiles_device(jne_ctx* ctx, const void* d_eigs, uint64_t n, uint32_t p, uint32_t stride, const double* qs,
                            uint32_t nq, double* trace_out, double* maxeig_out, void* stream) {
@@ -1180,16 +1369,26 @@ int jne_percentiles_device(jne_ctx* ctx, const void* d_eigs, uint64_t n, uint32_
   if (!d_eigs || !qs || !trace_out || !maxeig_out || p < 1 || stride < p || nq < 1)
     return fail(ctx, JNE_ERR_INVALID_ARG, "jne_percentiles_device: bad arguments");
   join_worker(ctx);
-  Device& dv = ctx->devs[0];
-  JNE_CUDA(ctx, cudaSetDevice(dv.id));
-  double* d_buf = nullptr;
-  JNE_CUDA(ctx, cudaMalloc(&d_buf, 4 * std::max<uint64_t>(n, 1) * sizeof(double)));
-  cudaStream_t st = (cudaStream_t)stream;
-  if (n) jne_aggregate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const double*)d_eigs, n, p, stride, d_buf, d_buf + 2 * n);
-  ctx->launches.fetch_add(1);
-  const int rc = percentiles_of(ctx, dv, d_buf, d_buf + 2 * n, n, qs, nq, trace_out, maxeig_out, st);
-  cudaFree(d_buf);
-  return rc;
+  return guarded(ctx, [&]() -> int {
+    Device& dv = ctx->devs[0];
+    JNE_CUDA(ctx, cudaSetDevice(dv.id));
+    double* d_buf = nullptr;
+    JNE_CUDA(ctx, cudaMalloc(&d_buf, 2 * std::max<uint64_t>(n, 1) * sizeof(double)));
+    cudaStream_t st = (cudaStream_t)stream;
+    auto body = [&]() -> int {
+      if (n) jne_aggregate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const double*)d_eigs, n, p, stride, d_buf, d_buf + n);
+      JNE_CUDA(ctx, cudaGetLastError());
+      ctx->launches.fetch_add(1);
+      JNE_CUDA(ctx, cudaStreamSynchronize(st));       // the selection runs on the context's own stream
+      SelSample tr{{d_buf}, {n}}, mx{{d_buf + n}, {n}};
+      int rc = percentiles_of_sample(ctx, {0}, tr, qs, nq, trace_out);
+      if (!rc) rc = percentiles_of_sample(ctx, {0}, mx, qs, nq, maxeig_out);
+      return rc;
+    };
+    const int rc = body();
+    cudaFree(d_buf);
+    return rc;
+  });
 }
 
 int jne_simulate_percentiles(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, uint32_t first_seed, uint64_t n,
@@ -1200,35 +1399,7 @@ int jne_simulate_percentiles(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t
   if (rc) return rc;
   if (!qs || !trace_out || !maxeig_out || nq < 1) return fail(ctx, JNE_ERR_INVALID_ARG, "jne_simulate_percentiles: bad arguments");
   if ((uint64_t)first_seed + n > (1ull << 32)) return fail(ctx, JNE_ERR_INVALID_ARG, "seed range exceeds u32");
-  Device& dv = ctx->devs[0];
-  JNE_CUDA(ctx, cudaSetDevice(dv.id));
-  JneRunParams prm = make_params(model, dim, steps, false);
-  prm.jtab = jtab_for(dv, dim);
-  const uint64_t chunk = 1ull << 20;
-  double* d_agg = nullptr;     // trace[n] + sort space[n] + max[n] + sort space[n]
-  uint32_t* d_seeds = nullptr;
-  double* d_eigs = nullptr;
-  JNE_CUDA(ctx, cudaMalloc(&d_agg, 4 * std::max<uint64_t>(n, 1) * sizeof(double)));
-  JNE_CUDA(ctx, cudaMalloc(&d_seeds, chunk * sizeof(uint32_t)));
-  JNE_CUDA(ctx, cudaMalloc(&d_eigs, chunk * prm.p * sizeof(double)));
-  auto body = [&]() -> int {
-    JNE_CUDA(ctx, cudaMemsetAsync(dv.d_err, 0, sizeof(unsigned int), dv.stream));
-    for (uint64_t off = 0; off < n; off += chunk) {
-      const uint64_t m = std::min(chunk, n - off);
-      jne_iota_kernel<<<(unsigned)((m + 255) / 256), 256, 0, dv.stream>>>(first_seed + (uint32_t)off, m, d_seeds);
-      JNE_CUDA(ctx, launch_run<true>(ctx, dv, d_seeds, nullptr, m, prm, d_eigs, dv.d_err, nullptr, dv.stream));
-      jne_aggregate_kernel<<<(unsigned)((m + 255) / 256), 256, 0, dv.stream>>>(d_eigs, m, prm.p, prm.p, d_agg + off, d_agg + 2 * n + off);
-      JNE_CUDA(ctx, cudaGetLastError());
-      ctx->launches.fetch_add(3);
-    }
-    JNE_CUDA(ctx, cudaMemcpyAsync(dv.h_err, dv.d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, dv.stream));
-    JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
-    if (*dv.h_err) return fail(ctx, JNE_ERR_NONFINITE, "non-finite eigenvalues");
-    return percentiles_of(ctx, dv, d_agg, d_agg + 2 * n, n, qs, nq, trace_out, maxeig_out, dv.stream);
-  };
-  rc = body();
-  cudaFree(d_agg); cudaFree(d_seeds); cudaFree(d_eigs);
-  return rc;
+  return guarded(ctx, [&]() { return simulate_percentiles_impl(ctx, 1u << model, dim, steps, first_seed, n, qs, nq, trace_out, maxeig_out); });
 }
 
 int jne_simulate_percentiles_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps, uint32_t first_seed,
@@ -1240,50 +1411,7 @@ int jne_simulate_percentiles_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t d
     if ((model_mask >> m) & 1u) { int rc = validate(ctx, (uint8_t)m, dim, steps); if (rc) return rc; }
   if (!qs || !trace_out || !maxeig_out || nq < 1) return fail(ctx, JNE_ERR_INVALID_ARG, "jne_simulate_percentiles_multi: bad arguments");
   if ((uint64_t)first_seed + n > (1ull << 32)) return fail(ctx, JNE_ERR_INVALID_ARG, "seed range exceeds u32");
-  Device& dv = ctx->devs[0];
-  JNE_CUDA(ctx, cudaSetDevice(dv.id));
-  JneRunParams prm = make_params_mask(model_mask, dim, steps, false);
-  prm.jtab = jtab_for(dv, dim);
-  const int nm = __builtin_popcount(model_mask);
-  const uint64_t chunk = 1ull << 19, n1 = std::max<uint64_t>(n, 1);
-  double* d_agg = nullptr;     // per selected model: trace[n] + sort space[n] + max[n] + sort space[n]
-  uint32_t* d_seeds = nullptr;
-  double* d_eigs = nullptr;
-  JNE_CUDA(ctx, cudaMalloc(&d_agg, (size_t)nm * 4 * n1 * sizeof(double)));
-  JNE_CUDA(ctx, cudaMalloc(&d_seeds, chunk * sizeof(uint32_t)));
-  JNE_CUDA(ctx, cudaMalloc(&d_eigs, chunk * prm.out_stride * sizeof(double)));
-  auto body = [&]() -> int {
-    JNE_CUDA(ctx, cudaMemsetAsync(dv.d_err, 0, sizeof(unsigned int), dv.stream));
-    for (uint64_t off = 0; off < n; off += chunk) {
-      const uint64_t m = std::min(chunk, n - off);
-      jne_iota_kernel<<<(unsigned)((m + 255) / 256), 256, 0, dv.stream>>>(first_seed + (uint32_t)off, m, d_seeds);
-      JNE_CUDA(ctx, launch_run<true>(ctx, dv, d_seeds, nullptr, m, prm, d_eigs, dv.d_err, nullptr, dv.stream));
-      ctx->launches.fetch_add(2);
-      uint32_t col = 0;
-      int slot = 0;
-      for (int mod = 0; mod < 5; ++mod) {          // one Brownian path per seed serves every selected model
-        if (!((model_mask >> mod) & 1u)) continue;
-        const uint32_t p = (mod == 1 || mod == 3) ? dim + 1 : dim;
-        double* agg = d_agg + (size_t)slot * 4 * n1;
-        jne_aggregate_kernel<<<(unsigned)((m + 255) / 256), 256, 0, dv.stream>>>(d_eigs + col, m, p, prm.out_stride, agg + off, agg + 2 * n1 + off);
-        ctx->launches.fetch_add(1);
-        col += p; ++slot;
-      }
-      JNE_CUDA(ctx, cudaGetLastError());
-    }
-    JNE_CUDA(ctx, cudaMemcpyAsync(dv.h_err, dv.d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, dv.stream));
-    JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
-    if (*dv.h_err) return fail(ctx, JNE_ERR_NONFINITE, "non-finite eigenvalues");
-    for (int slot = 0; slot < nm; ++slot) {
-      double* agg = d_agg + (size_t)slot * 4 * n1;
-      const int rc = percentiles_of(ctx, dv, agg, agg + 2 * n1, n, qs, nq, trace_out + (size_t)slot * nq, maxeig_out + (size_t)slot * nq, dv.stream);
-      if (rc) return rc;
-    }
-    return JNE_OK;
-  };
-  const int rc = body();
-  cudaFree(d_agg); cudaFree(d_seeds); cudaFree(d_eigs);
-  return rc;
+  return guarded(ctx, [&]() { return simulate_percentiles_impl(ctx, model_mask, dim, steps, first_seed, n, qs, nq, trace_out, maxeig_out); });
 }
 
 int jne_fp64_peak_tflops(jne_ctx* ctx, int mode, double ms_target, double* tflops) {

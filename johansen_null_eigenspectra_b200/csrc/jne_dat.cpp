@@ -9,6 +9,7 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/vfs.h>
 #include <unistd.h>
 
 #include "../../include/jne.h"
@@ -121,13 +122,35 @@ long walk(const Reader& r, long data_end, uint64_t limit, bool scan, F&& on_reco
 }  // namespace
 
 struct jne_dat_writer {
-  FILE* f = nullptr;
+  int fd = -1;
+  uint64_t pos = 0;       // end of the valid data == offset of the next record
+  bool tmpfs = false;
   std::vector<unsigned char> buf;
   uint64_t written = 0;
   uint32_t per_run = 0;   // 0 = not yet known
   uint8_t model = 0, dim = 0;
   uint32_t steps = 0;
 };
+
+namespace {
+
+bool write_all(int fd, const unsigned char* p, size_t n, uint64_t off) {
+  while (n) {
+    const ssize_t k = pwrite(fd, p, n, (off_t)off);
+    if (k < 0) { if (errno == EINTR) continue; return false; }
+    p += k; n -= (size_t)k; off += (uint64_t)k;
+  }
+  return true;
+}
+
+inline size_t encode_record(unsigned char* q, uint32_t seed, const double* vals, uint32_t p) {
+  const int k = jne_uleb128_encode(seed, q);
+  q[k] = (unsigned char)p;
+  memcpy(q + k + 1, vals, 8 * (size_t)p);           // f64 little-endian == host representation (x86-64 / aarch64)
+  return (size_t)k + 1 + 8 * (size_t)p;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -272,14 +295,19 @@ int jne_dat_open(const char* path, uint8_t model, uint8_t dim, uint32_t steps, u
   }
   jne_dat_writer* w = new jne_dat_writer();
   w->model = model; w->dim = dim; w->steps = steps; w->written = have; w->per_run = per_run;
-  w->f = fopen(path, fresh ? "wb" : "ab");
-  if (!w->f) { delete w; return fail(std::string("cannot open ") + path + " for writing: " + strerror(errno)); }
-  setvbuf(w->f, nullptr, _IONBF, 0);                 // batches are written whole: no second buffer
+  w->fd = ::open(path, O_RDWR | O_CREAT | (fresh ? O_TRUNC : 0), 0644);
+  if (w->fd < 0) { delete w; return fail(std::string("cannot open ") + path + " for writing: " + strerror(errno)); }
+  struct stat st;
+  if (fstat(w->fd, &st) != 0) { ::close(w->fd); delete w; return fail(std::string("fstat failed: ") + strerror(errno)); }
+  w->pos = (uint64_t)st.st_size;                      // batches are appended whole at this offset: no stdio buffer
+  struct statfs fs;
+  w->tmpfs = fstatfs(w->fd, &fs) == 0 && (unsigned long)fs.f_type == 0x01021994ul;   // TMPFS_MAGIC
   if (fresh) {
     unsigned char h[kHeader];
     memcpy(h, kMagic, 12); h[12] = model; h[13] = dim;
     for (int i = 0; i < 4; ++i) h[14 + i] = (steps >> (8 * i)) & 0xFF;
-    if (fwrite(h, 1, kHeader, w->f) != (size_t)kHeader) { fclose(w->f); delete w; return fail("header write failed"); }
+    if (!write_all(w->fd, h, kHeader, 0)) { ::close(w->fd); delete w; return fail("header write failed"); }
+    w->pos = kHeader;
   }
   if (existing) *existing = have;
   *out = w;
@@ -292,7 +320,7 @@ int jne_dat_append_batch(jne_dat_writer* w, const uint32_t* seeds, const double*
 
 int jne_dat_append_batch_strided(jne_dat_writer* w, const uint32_t* seeds, const double* eigs, uint64_t n, uint32_t p,
                                  uint64_t stride) {
-  if (!w || !w->f) return fail("writer is closed");
+  if (!w || w->fd < 0) return fail("writer is closed");
   if (stride < p) return fail("stride is smaller than the eigenvalue count");
   if (p > 255) return fail("Too many eigenvalues: " + std::to_string(p) + " exceeds maximum of 255");
   if (n == 0) return JNE_OK;
@@ -306,23 +334,26 @@ int jne_dat_append_batch_strided(jne_dat_writer* w, const uint32_t* seeds, const
     const uint64_t m = n - a < chunk ? n - a : chunk;
     w->buf.resize(m * rec_max);
     unsigned char* q = w->buf.data();
-    for (uint64_t i = 0; i < m; ++i) {
-      q += jne_uleb128_encode(seeds[a + i], q);
-      *q++ = (unsigned char)p;
-      memcpy(q, eigs + (a + i) * stride, 8 * (size_t)p);   // f64 little-endian == host representation
-      q += 8 * (size_t)p;
-    }
+    for (uint64_t i = 0; i < m; ++i) q += encode_record(q, seeds[a + i], eigs + (a + i) * stride, p);
     const size_t bytes = q - w->buf.data();
-    if (fwrite(w->buf.data(), 1, bytes, w->f) != bytes) return fail(std::string("write failed: ") + strerror(errno));
+    if (!write_all(w->fd, w->buf.data(), bytes, w->pos)) return fail(std::string("write failed: ") + strerror(errno));
+    w->pos += bytes;
   }
   w->written += n;
   return JNE_OK;
 }
 
+// Batch append by `threads` encoders that write STRAIGHT INTO THE FILE'S PAGES (no intermediate buffer, no write()
+// through the inode lock): record sizes are known from the seeds, so every encoder owns a disjoint byte range of the
+// batch.  The file grows by the batch, the new range is mapped MAP_SHARED, each encoder populates and fills its own
+// part (page allocation in parallel: on tmpfs that, not the copy, was the wall of the 8-GPU job -- 4.8 GB/s through
+// write()).  Crash consistency: until the batch is complete its first bytes hold 0xFF x 5, an invalid ULEB128 at which
+// both the reference's scan reader (reader.rs:163-166: `Err(_) => break`) and walk() stop, so an interrupted run
+// resumes cleanly at the start of the batch; the first record is copied in last.  Same bytes as the serial call.
 int jne_dat_append_batch_strided_mt(jne_dat_writer* w, const uint32_t* seeds, const double* eigs, uint64_t n, uint32_t p,
                                     uint64_t stride, int threads) {
   if (threads <= 1 || n < 4096) return jne_dat_append_batch_strided(w, seeds, eigs, n, p, stride);
-  if (!w || !w->f) return fail("writer is closed");
+  if (!w || w->fd < 0) return fail("writer is closed");
   if (p > 255) return fail("Too many eigenvalues: " + std::to_string(p) + " exceeds maximum of 255");
   if (stride < p) return fail("stride is smaller than the eigenvalue count");
   if (w->per_run == 0) w->per_run = p;
@@ -330,54 +361,102 @@ int jne_dat_append_batch_strided_mt(jne_dat_writer* w, const uint32_t* seeds, co
     return fail("Eigenvalue count mismatch: expected " + std::to_string(w->per_run) + ", actual " + std::to_string(p) +
                 " (model " + std::to_string(w->model) + ", dim " + std::to_string(w->dim) + ", steps " + std::to_string(w->steps) + ")");
   if (threads > 16) threads = 16;
-  const size_t rec_max = 5 + 1 + 8 * (size_t)p;
   const uint64_t per = (n + threads - 1) / threads;
-  std::vector<std::vector<unsigned char>> bufs(threads);
-  std::vector<size_t> used(threads, 0);
-  std::vector<std::thread> th;
+  // pass 1: bytes of every encoder's range
+  std::vector<uint64_t> off(threads + 1, 0);
   for (int t = 0; t < threads; ++t) {
     const uint64_t a = std::min<uint64_t>((uint64_t)t * per, n), b = std::min<uint64_t>(a + per, n);
-    if (a == b) continue;
-    th.emplace_back([&, t, a, b]() {
-      bufs[t].resize((b - a) * rec_max);
-      unsigned char* q = bufs[t].data();
-      for (uint64_t i = a; i < b; ++i) {
-        q += jne_uleb128_encode(seeds[i], q);
-        *q++ = (unsigned char)p;
-        memcpy(q, eigs + i * stride, 8 * (size_t)p);
-        q += 8 * (size_t)p;
-      }
-      used[t] = q - bufs[t].data();
-    });
+    uint64_t bytes = (b - a) * (1 + 8 * (uint64_t)p);
+    for (uint64_t i = a; i < b; ++i) bytes += (uint64_t)jne_uleb128_encoded_size(seeds[i]);
+    off[t + 1] = off[t] + bytes;
   }
-  for (auto& t : th) t.join();
-  // (positioned parallel writes were measured on 8 GPUs / tmpfs and changed nothing: the page cache is the wall)
-  for (int t = 0; t < threads; ++t)
-    if (used[t] && fwrite(bufs[t].data(), 1, used[t], w->f) != used[t]) return fail(std::string("write failed: ") + strerror(errno));
+  const uint64_t total = off[threads];
+  const long page = sysconf(_SC_PAGESIZE);
+  const uint64_t map_off = w->pos & ~(uint64_t)(page - 1), delta = w->pos - map_off;
+  // grow the file; on a disk file system reserve the blocks now so that a full disk is an error code here, not a
+  // SIGBUS in an encoder (on tmpfs the encoders' MADV_POPULATE_WRITE reports it)
+  if (!w->tmpfs) {
+    const int e = posix_fallocate(w->fd, (off_t)w->pos, (off_t)total);
+    if (e != 0 && e != EOPNOTSUPP && e != EINVAL) return fail(std::string("cannot reserve file space: ") + strerror(e));
+  }
+  if (ftruncate(w->fd, (off_t)(w->pos + total)) != 0) return fail(std::string("cannot grow the file: ") + strerror(errno));
+  void* base = mmap(nullptr, (size_t)(delta + total), PROT_READ | PROT_WRITE, MAP_SHARED, w->fd, (off_t)map_off);
+  if (base == MAP_FAILED) {
+    const int e = errno;
+    if (ftruncate(w->fd, (off_t)w->pos) != 0) { /* keep the first error */ }
+    return fail(std::string("cannot map the file: ") + strerror(e));
+  }
+  unsigned char* dst = static_cast<unsigned char*>(base) + delta;
+  unsigned char first[5 + 1 + 8 * 255];
+  const size_t first_len = encode_record(first, seeds[0], eigs, p);
+  std::vector<int> err(threads, 0);
+  {
+    // populate the first page(s) before the poison goes in
+#ifdef MADV_POPULATE_WRITE
+    if (madvise(base, (size_t)std::min<uint64_t>(delta + total, (uint64_t)page), MADV_POPULATE_WRITE) != 0 && errno == EFAULT) err[0] = ENOSPC;
+#endif
+    if (!err[0]) memset(dst, 0xFF, 5);
+  }
+  if (!err[0]) {
+    std::vector<std::thread> th;
+    try {
+      for (int t = 0; t < threads; ++t) {
+        const uint64_t a = std::min<uint64_t>((uint64_t)t * per, n), b = std::min<uint64_t>(a + per, n);
+        if (a == b) continue;
+        th.emplace_back([&, t, a, b]() {
+          unsigned char* q = dst + off[t];
+#ifdef MADV_POPULATE_WRITE
+          {   // allocate this encoder's pages in one call (whole pages inside its range; edges fault on first touch)
+            const uintptr_t lo = ((uintptr_t)q + page - 1) & ~(uintptr_t)(page - 1), hi = (uintptr_t)(dst + off[t + 1]) & ~(uintptr_t)(page - 1);
+            if (hi > lo && madvise((void*)lo, hi - lo, MADV_POPULATE_WRITE) != 0 && errno == EFAULT) { err[t] = ENOSPC; return; }
+          }
+#endif
+          uint64_t i = a;
+          if (t == 0) { q += first_len; ++i; }          // record 0 goes in last (see above)
+          for (; i < b; ++i) q += encode_record(q, seeds[i], eigs + i * stride, p);
+        });
+      }
+    } catch (...) {
+      for (auto& t : th) t.join();
+      munmap(base, (size_t)(delta + total));
+      if (ftruncate(w->fd, (off_t)w->pos) != 0) { /* nothing more to do */ }
+      return fail("could not start an encoder thread");
+    }
+    for (auto& t : th) t.join();
+  }
+  int bad = 0;
+  for (int e : err) if (e) bad = e;
+  if (!bad) memcpy(dst, first, first_len);              // the batch becomes valid
+  munmap(base, (size_t)(delta + total));
+  if (bad) {
+    if (ftruncate(w->fd, (off_t)w->pos) != 0) { /* keep the first error */ }
+    return fail(std::string("write failed: ") + strerror(bad));
+  }
+  w->pos += total;
   w->written += n;
   return JNE_OK;
 }
 
 int jne_dat_flush(jne_dat_writer* w) {
-  if (!w || !w->f) return fail("writer is closed");
-  return fflush(w->f) == 0 ? JNE_OK : fail(std::string("flush failed: ") + strerror(errno));
+  if (!w || w->fd < 0) return fail("writer is closed");
+  return JNE_OK;      // nothing is buffered in user space: every batch is already in the OS page cache
 }
 
 int jne_dat_finish(jne_dat_writer* w) {
-  if (!w || !w->f) return fail("writer is closed");
+  if (!w || w->fd < 0) return fail("writer is closed");
   unsigned char t[kTrailer];
   memcpy(t, kEof, 8);
   for (int i = 0; i < 8; ++i) t[8 + i] = (w->written >> (8 * i)) & 0xFF;
   t[16] = (unsigned char)w->per_run;
-  const bool ok = fwrite(t, 1, kTrailer, w->f) == (size_t)kTrailer && fflush(w->f) == 0;
-  fclose(w->f);
+  const bool ok = write_all(w->fd, t, kTrailer, w->pos);
+  const bool closed = ::close(w->fd) == 0;
   delete w;
-  return ok ? JNE_OK : fail("trailer write failed");
+  return ok && closed ? JNE_OK : fail(std::string("trailer write failed: ") + strerror(errno));
 }
 
 void jne_dat_abandon(jne_dat_writer* w) {
   if (!w) return;
-  if (w->f) fclose(w->f);
+  if (w->fd >= 0) ::close(w->fd);
   delete w;
 }
 
