@@ -45,7 +45,9 @@ def box_muller(wa, wb):
     wb = np.asarray(wb, dtype=np.uint32)
     u = np.float32(wa.astype(np.float32)) * np.float32(2.0 ** -32) + np.float32(2.0 ** -33)
     u = u.astype(np.float32)
-    r = np.sqrt(np.float32(-2.0) * np.log(u.astype(np.float64))).astype(np.float32)
+    # the device multiplies lg2(u) by -0x1.62e436p+0 (= -2 ln 2, three float ulps further out: its variance
+    # calibration, see jne_rng.cuh); this mirror follows it
+    r = np.sqrt(-float.fromhex("0x1.62e436p+0") * np.log2(u.astype(np.float64))).astype(np.float32)
     th = wb.view(np.int32).astype(np.float32).astype(np.float64) * (2.0 ** -32) * 2.0 * np.pi
     return (r * np.cos(th)).astype(np.float32), (r * np.sin(th)).astype(np.float32)
 
