@@ -378,11 +378,12 @@ def main():
             eng_all.close()
         except Exception as exc:
             extras["e2e_inprocess"] = {"value": None, "error": f"{type(exc).__name__}: {exc}"}
+    torch.cuda.set_device(local_rank)
     if world > 1:
         dist.barrier()
     h2d = 4 * R
     d2h = 8 * R * width
-    tp = torch.tensor([pm_ms], dtype=torch.float64, device="cuda")
+    tp = torch.tensor([pm_ms], dtype=torch.float64, device=torch.device("cuda", local_rank))
     if world > 1:
         dist.all_reduce(tp, op=dist.ReduceOp.MAX)
     pm_value = total_runs / (float(tp.item()) * 1e-3)

@@ -103,6 +103,16 @@ int fail(jne_ctx* ctx, int code, const std::string& msg) {
     }                                                                                               \
   } while (0)
 
+// The library switches CUDA devices on the caller's thread (a context may span several); an FFI library must hand the
+// thread back as it found it, or the host application's next allocation lands on the wrong GPU.
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 int validate(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps) {
   if (model > 4) return fail(ctx, JNE_ERR_INVALID_ARG, "model must be 0..4");
   if (dim < 1 || dim > 255) return fail(ctx, JNE_ERR_INVALID_ARG, "dim must be 1..255");
@@ -805,6 +815,7 @@ int64_t jne_trend_weight_table(uint32_t steps, double* table, uint64_t capacity)
 }
 
 void jne_shutdown(jne_ctx* ctx) {
+  DeviceGuard device_guard;
   if (!ctx) return;
   join_worker(ctx);
   for (auto& dv : ctx->devs) {
@@ -829,6 +840,7 @@ void jne_shutdown(jne_ctx* ctx) {
 }
 
 int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
+  DeviceGuard device_guard;
   if (!out) return fail(nullptr, JNE_ERR_INVALID_ARG, "out is NULL");
   *out = nullptr;
   int visible = 0;
@@ -893,6 +905,7 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
 
 int jne_eigs_batch(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
                    double* out) {
+  DeviceGuard device_guard;
   if (!ctx) return JNE_ERR_INVALID_ARG;
   join_worker(ctx);
   int rc = validate(ctx, model, dim, steps);
@@ -903,6 +916,7 @@ int jne_eigs_batch(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, co
 
 int jne_eigs_batch_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps, const uint32_t* seeds,
                          uint64_t n, double* out) {
+  DeviceGuard device_guard;
   if (!ctx) return JNE_ERR_INVALID_ARG;
   join_worker(ctx);
   if (model_mask == 0 || model_mask > 31u) return fail(ctx, JNE_ERR_INVALID_ARG, "model_mask must select models 0..4");
@@ -921,6 +935,7 @@ int jne_multi_width(uint32_t model_mask, uint32_t dim) {
 
 int jne_eigs_batch_multi_device(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps, const void* d_seeds,
                                 uint64_t n, void* d_out, void* stream) {
+  DeviceGuard device_guard;
   if (!ctx) return JNE_ERR_INVALID_ARG;
   if (model_mask == 0 || model_mask > 31u) return fail(ctx, JNE_ERR_INVALID_ARG, "model_mask must select models 0..4");
   for (int m = 0; m < 5; ++m)
@@ -979,6 +994,7 @@ int64_t jne_submit_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32
 }
 
 int jne_wait(jne_ctx* ctx, int64_t ticket) {
+  DeviceGuard device_guard;
   if (!ctx) return JNE_ERR_INVALID_ARG;
   if (ticket <= 0 || ticket != ctx->pending_ticket) return fail(ctx, JNE_ERR_INVALID_ARG, "unknown ticket");
   join_worker(ctx);
@@ -988,6 +1004,7 @@ int jne_wait(jne_ctx* ctx, int64_t ticket) {
 
 int jne_eigs_batch_device(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, const void* d_seeds, uint64_t n,
                           void* d_out, void* stream) {
+  DeviceGuard device_guard;
   if (!ctx) return JNE_ERR_INVALID_ARG;
   int rc = validate(ctx, model, dim, steps);
   if (rc) return rc;
@@ -1009,6 +1026,7 @@ int jne_eigs_batch_device(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t st
 }
 
 int jne_check_async(jne_ctx* ctx) {
+  DeviceGuard device_guard;
   if (!ctx) return JNE_ERR_INVALID_ARG;
   Device& dv = ctx->devs[0];
   JNE_CUDA(ctx, cudaSetDevice(dv.id));
@@ -1072,6 +1090,7 @@ static int single_device_run(jne_ctx* ctx, const JneRunParams& prm_in, const uin
 
 int jne_eigs_from_increments(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, const double* dB, uint64_t n,
                              double* out) {
+  DeviceGuard device_guard;
   if (!ctx) return JNE_ERR_INVALID_ARG;
   join_worker(ctx);
   int rc = validate(ctx, model, dim, steps);
@@ -1083,6 +1102,7 @@ int jne_eigs_from_increments(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t
 
 int jne_eigs_batch_debug(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
                          double* out, double* mats) {
+  DeviceGuard device_guard;
   if (!ctx) return JNE_ERR_INVALID_ARG;
   join_worker(ctx);
   int rc = validate(ctx, model, dim, steps);
@@ -1093,6 +1113,7 @@ int jne_eigs_batch_debug(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t ste
 }
 
 int jne_gen_normal_matrix(jne_ctx* ctx, uint32_t dim, uint32_t steps, uint32_t seed, double* out) {
+  DeviceGuard device_guard;
   if (!ctx) return JNE_ERR_INVALID_ARG;
   join_worker(ctx);
   if (dim < 1 || steps < 1 || !out) return fail(ctx, JNE_ERR_INVALID_ARG, "dim/steps/out invalid");
@@ -1112,6 +1133,7 @@ int jne_gen_normal_matrix(jne_ctx* ctx, uint32_t dim, uint32_t steps, uint32_t s
 }
 
 int jne_brownian_motion_matrix(jne_ctx* ctx, uint32_t dim, uint32_t steps, double delta_t, uint32_t seed, double* out) {
+  DeviceGuard device_guard;
   if (!ctx) return JNE_ERR_INVALID_ARG;
   join_worker(ctx);
   if (dim < 1 || steps < 1 || !out) return fail(ctx, JNE_ERR_INVALID_ARG, "dim/steps/out invalid");
@@ -1131,6 +1153,7 @@ int jne_brownian_motion_matrix(jne_ctx* ctx, uint32_t dim, uint32_t steps, doubl
 
 int jne_pencil_eigs_batch(jne_ctx* ctx, uint32_t p, uint32_t d, const double* S1, const double* S2, uint64_t n,
                           double* out) {
+  DeviceGuard device_guard;
   if (!ctx) return JNE_ERR_INVALID_ARG;
   join_worker(ctx);
   if (p < 1 || p > 16 || d < 1 || d > p) return fail(ctx, JNE_ERR_INVALID_ARG, "need 1 <= d <= p <= 16");
@@ -1365,6 +1388,7 @@ extern "C" {
 
 int jne_percentiles_device(jne_ctx* ctx, const void* d_eigs, uint64_t n, uint32_t p, uint32_t stride, const double* qs,
                            uint32_t nq, double* trace_out, double* maxeig_out, void* stream) {
+  DeviceGuard device_guard;
   if (!ctx) return JNE_ERR_INVALID_ARG;
   if (!d_eigs || !qs || !trace_out || !maxeig_out || p < 1 || stride < p || nq < 1)
     return fail(ctx, JNE_ERR_INVALID_ARG, "jne_percentiles_device: bad arguments");
@@ -1393,6 +1417,7 @@ int jne_percentiles_device(jne_ctx* ctx, const void* d_eigs, uint64_t n, uint32_
 
 int jne_simulate_percentiles(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t steps, uint32_t first_seed, uint64_t n,
                              const double* qs, uint32_t nq, double* trace_out, double* maxeig_out) {
+  DeviceGuard device_guard;
   if (!ctx) return JNE_ERR_INVALID_ARG;
   join_worker(ctx);
   int rc = validate(ctx, model, dim, steps);
@@ -1404,6 +1429,7 @@ int jne_simulate_percentiles(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t
 
 int jne_simulate_percentiles_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps, uint32_t first_seed,
                                    uint64_t n, const double* qs, uint32_t nq, double* trace_out, double* maxeig_out) {
+  DeviceGuard device_guard;
   if (!ctx) return JNE_ERR_INVALID_ARG;
   join_worker(ctx);
   if (model_mask == 0 || model_mask > 31u) return fail(ctx, JNE_ERR_INVALID_ARG, "model_mask must select models 0..4");
@@ -1415,6 +1441,7 @@ int jne_simulate_percentiles_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t d
 }
 
 int jne_fp64_peak_tflops(jne_ctx* ctx, int mode, double ms_target, double* tflops) {
+  DeviceGuard device_guard;
   if (!ctx || !tflops) return JNE_ERR_INVALID_ARG;
   join_worker(ctx);
   Device& dv = ctx->devs[0];

@@ -35,6 +35,26 @@ def test_all_devices_bit_identical_to_one(engines):
     assert np.array_equal(out, one.eigs_batch(1, 12, 100, np.arange(1, 5001, dtype=np.uint32)))
 
 
+def test_callers_current_device_is_left_alone():
+    """An FFI library must hand the calling thread back with the CUDA device it came with: a context over several
+    devices switches devices internally (jne_init, every batched call)."""
+    import torch
+    import johansen_null_eigenspectra_b200 as jne
+    if jne.lib.jne_device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    for cur in (0, 1):
+        torch.cuda.set_device(cur)
+        eng = jne.Engine(None)
+        assert torch.cuda.current_device() == cur
+        eng.eigs_batch_multi(range(5), 3, 50, np.arange(1, 4001, dtype=np.uint32))
+        eng.simulate_percentiles(2, 3, 50, 4000, [0.5])
+        assert torch.cuda.current_device() == cur
+        assert torch.zeros(1, device="cuda").device.index == cur
+        eng.close()
+        assert torch.cuda.current_device() == cur
+    torch.cuda.set_device(0)
+
+
 def test_error_from_any_device_surfaces(engines):
     import johansen_null_eigenspectra_b200 as jne
     _, all_ = engines
