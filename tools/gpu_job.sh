@@ -26,7 +26,7 @@ for stage in "$@"; do
                 -o "gpurun_out/prof_$tag" python tools/ncu_target.py ${targs//,/ } > "gpurun_out/ncu_$tag.log" 2>&1
               tail -n 2 "gpurun_out/ncu_$tag.log" ;;
     variants) timeout 1200 python tools/variants.py run 2>&1 | tee gpurun_out/variants.txt ;;
-    gate2ks)  timeout 1200 python tools/validate_gate2.py ks --n 2000000 2>&1 | tee gpurun_out/gate2_ks.txt ;;
+    gate2ks)  timeout 1200 python tools/validate_gate2.py ks 2>&1 | tee gpurun_out/gate2_ks.txt ;;
     gate2ab:*) IFS=: read -r _ dim T n <<< "$stage"
               timeout 1500 python tools/validate_gate2.py ab --dim "$dim" --T "$T" --n "$n" 2>&1 | tee "gpurun_out/gate2_ab_dim$dim.txt" ;;
     py:*)     IFS=: read -r _ script sargs <<< "$stage"

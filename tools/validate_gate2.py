@@ -34,8 +34,9 @@ def cmd_ks(args):
             print(f"# dim {dim} T {T}: CPU grid missing, skipped")
             continue
         t0 = time.time()
-        rows = g2.compare(eng, dim, T, args.n)
-        print(f"# dim {dim}, T {T}: GPU seeds 1..{args.n} vs CPU f64-ziggurat sample of {rows[0]['n_cpu']} runs "
+        n_cpu = int(np.load(g2.cpu_grid_path(dim, T))["n"])
+        rows = g2.compare(eng, dim, T, args.n or n_cpu)
+        print(f"# dim {dim}, T {T}: GPU seeds 1..{rows[0]['n_gpu']} vs CPU f64-ziggurat sample of {rows[0]['n_cpu']} runs "
               f"({time.time() - t0:.1f} s); KS alpha = {g2.ALPHA}")
         print(g2.format_rows(rows))
         print("# quantiles (GPU | CPU | relative difference), q = " + ", ".join(str(q) for q in g2.QS))
@@ -114,7 +115,7 @@ def main():
     ap.add_argument("cmd", choices=["ks", "ab", "ab-worker"])
     ap.add_argument("--dim", type=int, default=12)
     ap.add_argument("--T", type=int, default=10000)
-    ap.add_argument("--n", type=int, default=2_000_000)
+    ap.add_argument("--n", type=int, default=0, help="GPU seeds (ks: 0 = as many as the CPU sample; ab: required)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     {"ks": cmd_ks, "ab": cmd_ab, "ab-worker": cmd_ab_worker}[args.cmd](args)
