@@ -73,6 +73,7 @@ struct jne_ctx {
                            // experimental builds only (JNE_EXPERIMENTAL_FAMILIES): 2 = FMA-tiled path for 9 <= dim <= 12
                            // (env JNE_KERNEL=v2), 3 = producer / consumer warps for dim <= 12 (env JNE_KERNEL=ws)
   bool use_lane = true;    // env JNE_LANE=0: tensor family for every dim (regression tooling)
+  bool use_group = true;   // env JNE_GROUP=0: dims 9, 10 on the tensor family (regression tooling)
   bool lane_thread_solve = true;   // env JNE_LANE_SOLVE=warp: the lane family's moments through the warp-per-run epilogue
   std::vector<Device> devs;
   std::string err;
@@ -339,6 +340,10 @@ const double* aux_table_for(jne_ctx* ctx, Device& dv, uint32_t steps) {
   if (cudaMemcpy(d, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaGetLastError(); cudaFree(d); return nullptr;
   }
+  // cudaMemcpy from pageable memory may return while the DMA is still in flight on the legacy default stream, and the
+  // kernels run on NON-BLOCKING streams, which do not wait for it: without this the first launch for a new horizon
+  // could read a half-written table (seen as non-finite runs in a freshly created multi-device context).
+  if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
   dv.aux_tabs[steps] = d;
   return d;
 }
@@ -346,8 +351,12 @@ const double* aux_table_for(jne_ctx* ctx, Device& dv, uint32_t steps) {
 // ---- lane family (jne_kernels_lane.cuh): dim <= 6, one thread per run + one warp per run for the solve ----
 constexpr uint64_t kMomChunk = 1ull << 18;   // upper bound on the runs per moments / solve pair (195 MB of moments at dim 6)
 
+// dims served by the group kernels (L lanes per run): <dim, L>
+#define JNE_GROUP_L9 3
+#define JNE_GROUP_L10 5
+bool group_dim(uint32_t dim) { return dim == 9 || dim == 10; }
 bool lane_wanted(const jne_ctx* ctx, const JneRunParams& prm) {
-  return ctx->use_lane && ctx->kernel_family == 1 && prm.dim <= JNE_LANE_MAX_DIM;
+  return ctx->use_lane && ctx->kernel_family == 1 && (prm.dim <= JNE_LANE_MAX_DIM || (ctx->use_group && group_dim(prm.dim)));
 }
 int lane_det(const JneRunParams& prm) {
   const bool multi = (prm.model_mask & (prm.model_mask - 1u)) != 0;
@@ -369,10 +378,37 @@ cudaError_t launch_lane_moments(int det, const uint32_t* s, const double* b, uin
   }
   return cudaGetLastError();
 }
+template <int D, int L, bool RNG>
+cudaError_t launch_group_moments(int det, const uint32_t* s, const double* b, uint64_t m, uint32_t steps, double* mom, cudaStream_t st) {
+  using Q = JneGroupGeo<D, L>;
+  const unsigned grid = (unsigned)((m + Q::RUNS_PER_CTA - 1) / Q::RUNS_PER_CTA);
+  if constexpr (RNG) {
+    switch (det) {
+      case 0: jne_group_moments_kernel<D, L, 0, true><<<grid, Q::THREADS, 0, st>>>(s, b, m, steps, mom); break;
+      case 1: jne_group_moments_kernel<D, L, 1, true><<<grid, Q::THREADS, 0, st>>>(s, b, m, steps, mom); break;
+      default: jne_group_moments_kernel<D, L, 2, true><<<grid, Q::THREADS, 0, st>>>(s, b, m, steps, mom); break;
+    }
+  } else {
+    jne_group_moments_kernel<D, L, 2, false><<<grid, Q::THREADS, 0, st>>>(s, b, m, steps, mom);
+  }
+  return cudaGetLastError();
+}
+template <int D, int L> uint64_t group_wave_one(const Device& dv, int det) {
+  using Q = JneGroupGeo<D, L>;
+  int nb = 0;
+  cudaError_t rc = det == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, jne_group_moments_kernel<D, L, 0, true>, Q::THREADS, 0)
+                 : det == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, jne_group_moments_kernel<D, L, 1, true>, Q::THREADS, 0)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, jne_group_moments_kernel<D, L, 2, true>, Q::THREADS, 0);
+  if (rc != cudaSuccess) { cudaGetLastError(); return 0; }
+  return (uint64_t)nb * dv.sm_count * Q::RUNS_PER_CTA;
+}
+
 template <bool RNG>
 cudaError_t launch_lane_moments_dim(uint32_t dim, int det, const uint32_t* s, const double* b, uint64_t m, uint32_t steps,
                                     double* mom, cudaStream_t st) {
   switch (dim) {
+    case 9: return launch_group_moments<9, JNE_GROUP_L9, RNG>(det, s, b, m, steps, mom, st);
+    case 10: return launch_group_moments<10, JNE_GROUP_L10, RNG>(det, s, b, m, steps, mom, st);
     case 1: return launch_lane_moments<1, RNG>(det, s, b, m, steps, mom, st);
     case 2: return launch_lane_moments<2, RNG>(det, s, b, m, steps, mom, st);
     case 3: return launch_lane_moments<3, RNG>(det, s, b, m, steps, mom, st);
@@ -421,6 +457,8 @@ template <int D> uint64_t lane_wave_one(const Device& dv, int det) {
 uint64_t lane_wave(const Device& dv, const JneRunParams& prm) {
   const int det = lane_det(prm);
   switch (prm.dim) {
+    case 9: return group_wave_one<9, JNE_GROUP_L9>(dv, det);
+    case 10: return group_wave_one<10, JNE_GROUP_L10>(dv, det);
     case 1: return lane_wave_one<1>(dv, det);
     case 2: return lane_wave_one<2>(dv, det);
     case 3: return lane_wave_one<3>(dv, det);
@@ -462,7 +500,8 @@ cudaError_t launch_lane(jne_ctx* ctx, Device& dv, const uint32_t* s, const doubl
     double* dp = dbg ? dbg + off * 512 : nullptr;
     // solve: one thread per run; the warp-per-run epilogue of the tensor family only when the caller wants the
     // assembled matrices back (jne_eigs_batch_debug) or asks for it (JNE_LANE_SOLVE=warp, regression tooling)
-    if (dp == nullptr && ctx->lane_thread_solve) rc = launch_lane_tsolve_dim(d_mom, m, prm, op, e, st);
+    if (prm.dim > 8) rc = multi ? launch_lane_solve<12, true>(d_mom, m, prm, op, e, dp, st) : launch_lane_solve<12, false>(d_mom, m, prm, op, e, dp, st);
+    else if (dp == nullptr && ctx->lane_thread_solve) rc = launch_lane_tsolve_dim(d_mom, m, prm, op, e, st);
     else if (prm.dim <= 4) rc = multi ? launch_lane_solve<4, true>(d_mom, m, prm, op, e, dp, st) : launch_lane_solve<4, false>(d_mom, m, prm, op, e, dp, st);
     else rc = multi ? launch_lane_solve<8, true>(d_mom, m, prm, op, e, dp, st) : launch_lane_solve<8, false>(d_mom, m, prm, op, e, dp, st);
     if (rc != cudaSuccess) return rc;
@@ -859,6 +898,7 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
   if (const char* kf = std::getenv("JNE_KERNEL")) ctx->kernel_family = (std::strcmp(kf, "v2") == 0) ? 2 : (std::strcmp(kf, "ws") == 0) ? 3 : 1;
 #endif
   if (const char* ln = std::getenv("JNE_LANE")) ctx->use_lane = std::strcmp(ln, "0") != 0;
+  if (const char* gr = std::getenv("JNE_GROUP")) ctx->use_group = std::strcmp(gr, "0") != 0;
   if (const char* ls = std::getenv("JNE_LANE_SOLVE")) ctx->lane_thread_solve = std::strcmp(ls, "warp") != 0;
   if (const char* ax = std::getenv("JNE_AUX")) ctx->use_aux = std::strcmp(ax, "0") != 0;
   try { ctx->devs.resize(n_devices); } catch (...) { delete ctx; return fail(nullptr, JNE_ERR_INTERNAL, "out of host memory"); }
@@ -894,6 +934,7 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
       JNE_CUDA(nullptr, cudaMemset(dv.d_err, 0, sizeof(unsigned int)));
       JNE_CUDA(nullptr, cudaMallocHost(&dv.h_err, sizeof(unsigned int)));
       *dv.h_err = 0;
+      JNE_CUDA(nullptr, cudaDeviceSynchronize());   // the uploads above ride the legacy stream; the work streams are non-blocking
       return JNE_OK;
     };
     int rc = setup();

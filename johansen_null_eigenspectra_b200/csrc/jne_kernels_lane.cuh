@@ -450,3 +450,227 @@ jne_lane_tsolve_kernel(const double* __restrict__ mom, uint64_t n, uint32_t mode
   }
   if (!ok) atomicAdd(err_count, 1u);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Group kernels: L lanes per run, R = D / L rows per lane (dim 9: 3 x 3, dim 10: 5 x 2).
+//
+// Above six rows a run's moments no longer fit one thread, and on the tensor path dims 9..11 pay for dim 12's five
+// DMMA tiles (profiles/r2_bench_all_configs_v2.jsonl: 3.28 M seeds/s at dim 9 against 3.19 M at dim 12).  Here the
+// D rows of a run are dealt to L lanes; a lane generates the normals of its own R rows and owns the products that have
+// one of its rows as the left factor:
+//     sum c_own dB'_all   R x D        sum c_own c_own' (upper)   R (R + 1) / 2
+//     sum c_own c'_partner for the next floor((L - 1) / 2) lanes of the group (full R x R blocks)
+//     L even: the half block a <= b with the lane opposite (both lanes compute its diagonal: identical bits)
+// so every unordered pair of rows is accumulated exactly once (or twice with the same bits), with no padded products.
+// Every lane keeps the WHOLE path c (D adds per step) in a frame rotated by its own first row -- own rows first,
+// then the next lane's, ... -- which makes every register index a compile-time constant while the lane dependence
+// sits in shared-memory addresses.  The only exchange is the step's increments: each lane writes the four steps of
+// its R rows of a Philox block to shared memory once per block (double-buffered, one __syncwarp per block) and reads
+// the D increments of a step back as broadcasts; the path itself never travels.  Moments leave in the layout of
+// JneLaneMom<D>; jne_lane_solve_kernel (one warp per run) finishes.
+// ---------------------------------------------------------------------------------------------
+template <int D, int L> struct JneGroupGeo {
+  static constexpr int R = (D + L - 1) / L;          // rows per lane
+  static constexpr int LR = L * R;                   // rows incl. padding (== D for the shapes in use)
+  static constexpr int G = 32 / L;                   // runs per warp (lanes >= G * L shadow the last group)
+  static constexpr int WARPS = 4, THREADS = 128;
+  static constexpr int RUNS_PER_CTA = WARPS * G;
+  static constexpr int NFULL = (L - 1) / 2;          // partners l + 1 .. l + NFULL: full R x R blocks
+  static constexpr bool HALF = (L % 2) == 0 && L > 1;   // partner l + L / 2: the half block a <= b
+  static constexpr int NOWN = R * (R + 1) / 2;
+  static constexpr int ZS = 2 * 4 * LR * G;          // doubles of shared memory per warp (two blocks of four steps)
+};
+
+template <int D, int L, int DET> struct JneGroupState {
+  using Q = JneGroupGeo<D, L>;
+  double c[Q::LR];                                   // the whole path, rotated frame: c[k] = row (l R + k) mod LR
+  double bz[Q::R][Q::LR], bown[Q::NOWN], bfull[Q::NFULL > 0 ? Q::NFULL : 1][Q::R][Q::R], bhalf[Q::NOWN];
+  double s0[Q::R], s1[Q::R], s2[Q::R];
+  double w1, w2, w2c;
+};
+
+template <int D, int L, int DET, bool SRC_RNG>
+__device__ __forceinline__ void jne_group_step(JneGroupState<D, L, DET>& S, const double (&zin)[JneGroupGeo<D, L>::LR]) {
+  using Q = JneGroupGeo<D, L>;
+  double dz[Q::LR], cn[Q::LR];
+#pragma unroll
+  for (int k = 0; k < Q::LR; ++k) {
+    cn[k] = S.c[k] + zin[k];                         // B_t = B_{t-1} + dB_t (src/matrix_utils.rs:51-63), every row, every lane
+    dz[k] = SRC_RNG ? zin[k] : cn[k] - S.c[k];       // caller increments: re-derived by subtraction (src/johansen_statistics.rs:80-82)
+  }
+#pragma unroll
+  for (int a = 0; a < Q::R; ++a) {
+#pragma unroll
+    for (int k = 0; k < Q::LR; ++k) S.bz[a][k] = fma(S.c[a], dz[k], S.bz[a][k]);
+  }
+  {
+    int idx = 0;
+#pragma unroll
+    for (int a = 0; a < Q::R; ++a)
+#pragma unroll
+      for (int b = a; b < Q::R; ++b) {
+        S.bown[idx] = fma(S.c[a], S.c[b], S.bown[idx]);
+        if (Q::HALF) S.bhalf[idx] = fma(S.c[a], S.c[(L / 2) * Q::R + b], S.bhalf[idx]);
+        ++idx;
+      }
+  }
+#pragma unroll
+  for (int p = 0; p < Q::NFULL; ++p)
+#pragma unroll
+    for (int a = 0; a < Q::R; ++a)
+#pragma unroll
+      for (int b = 0; b < Q::R; ++b) S.bfull[p][a][b] = fma(S.c[a], S.c[(p + 1) * Q::R + b], S.bfull[p][a][b]);
+#pragma unroll
+  for (int a = 0; a < Q::R; ++a) {
+    S.s0[a] += S.c[a];
+    if (DET >= 1) S.s1[a] = fma(S.w1, S.c[a], S.s1[a]);
+    if (DET >= 2) S.s2[a] = fma(S.w2, S.c[a], S.s2[a]);
+  }
+#pragma unroll
+  for (int k = 0; k < Q::LR; ++k) S.c[k] = cn[k];
+  if (DET >= 1) S.w1 += 2.0;
+  if (DET >= 2) S.w2 = fma(3.0 * S.w1, S.w1, S.w2c);
+}
+
+template <int D, int L, int DET, bool SRC_RNG>
+__global__ void __launch_bounds__(JneGroupGeo<D, L>::THREADS, 2)
+jne_group_moments_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB, uint64_t n, uint32_t T,
+                         double* __restrict__ mom) {
+  using Q = JneGroupGeo<D, L>;
+  using M = JneLaneMom<D>;
+  constexpr int R = Q::R, LR = Q::LR, G = Q::G;
+  __shared__ double zs_all[Q::WARPS][Q::ZS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool shadow = lane >= G * L;                   // spare lanes repeat the last group (identical values, no stores to global)
+  const int g = shadow ? G - 1 : lane / L, l = lane % L;
+  const uint64_t run_raw = ((uint64_t)blockIdx.x * Q::WARPS + warp) * G + g;
+  const bool live = run_raw < n && !shadow;
+  const uint64_t run = run_raw < n ? run_raw : n - 1;
+  double* zs = zs_all[warp];
+  jne_keys keys;
+  {
+    const uint32_t seed = SRC_RNG ? seeds[run] : 0u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      keys.k[r] = seed + (uint32_t)r * 0x9E3779B9u;
+      asm volatile("" : "+r"(keys.k[r]));
+    }
+  }
+  const double* dBrun = SRC_RNG ? nullptr : dB + run * (uint64_t)D * T;
+
+  JneGroupState<D, L, DET> S;
+#pragma unroll
+  for (int k = 0; k < LR; ++k) S.c[k] = 0.0;
+#pragma unroll
+  for (int a = 0; a < R; ++a) {
+    S.s0[a] = S.s1[a] = S.s2[a] = 0.0;
+#pragma unroll
+    for (int k = 0; k < LR; ++k) S.bz[a][k] = 0.0;
+#pragma unroll
+    for (int p = 0; p < (Q::NFULL > 0 ? Q::NFULL : 1); ++p)
+#pragma unroll
+      for (int b = 0; b < R; ++b) S.bfull[p][a][b] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < Q::NOWN; ++i) { S.bown[i] = 0.0; S.bhalf[i] = 0.0; }
+  const double Td = (double)T;
+  const double w1_first = 1.0 - Td;
+  const double w2c = -(Td * Td - 1.0);
+  S.w1 = w1_first;
+  S.w2c = w2c;
+  S.w2 = fma(3.0 * w1_first, w1_first, w2c);
+
+  // shared-memory addresses: element (buffer, step s, row, group) at ((buffer * 4 + s) * LR + row) * G + group
+  int rd_off[LR];                                      // this lane's rotated frame: k -> row (l R + k) mod LR
+#pragma unroll
+  for (int k = 0; k < LR; ++k) rd_off[k] = ((l * R + k) % LR) * G + g;
+  const int wr_off = (l * R) * G + g;
+
+  // writes the four steps of this lane's R rows of Philox block tb (or of the caller's increments) into buffer `buf`
+  auto publish_row = [&](uint32_t tb, int buf, int a) {
+    const int row = l * R + a;
+    double v[4];
+    if constexpr (SRC_RNG) {
+      jne_zt zf[4];
+      jne_normals4_keyed(keys, (uint32_t)row, tb, zf, row < D ? 1.0f : 0.0f);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) v[s] = (double)zf[s];
+    } else {
+#pragma unroll
+      for (int s = 0; s < 4; ++s) v[s] = (row < D && 4u * tb + s < T) ? dBrun[(uint64_t)(4u * tb + s) * D + row] : 0.0;
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) zs[((buf * 4 + s) * LR + a) * G + wr_off] = v[s];
+  };
+  auto consume_step = [&](int buf, int s) {
+    double zz[LR];
+#pragma unroll
+    for (int k = 0; k < LR; ++k) zz[k] = zs[(buf * 4 + s) * LR * G + rd_off[k]];
+    jne_group_step<D, L, DET, SRC_RNG>(S, zz);
+  };
+
+  const uint32_t nfull = T >> 2, tail = T & 3u;
+#pragma unroll
+  for (int a = 0; a < R; ++a) publish_row(0u, 0, a);
+  __syncwarp();
+  for (uint32_t tb = 0; tb < nfull; ++tb) {
+    const int buf = (int)(tb & 1u);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {                      // block tb + 1 is generated between the steps of block tb
+#pragma unroll
+      for (int a = 0; a < R; ++a)
+        if (a * 4 / R == s) publish_row(tb + 1u, buf ^ 1, a);
+      consume_step(buf, s);
+    }
+    __syncwarp();                                      // block tb + 1 is complete; block tb may be overwritten
+  }
+  {
+    const int buf = (int)(nfull & 1u);
+#pragma unroll 1
+    for (uint32_t s = 0; s < tail; ++s) consume_step(buf, (int)s);
+  }
+  if (!live) return;
+
+  // ---- moments to global memory (JneLaneMom<D>); rotated column k is row (l R + k) mod LR ----
+  double* m = mom + run * (uint64_t)M::SZ;
+  auto tri = [](int i, int j) { const int lo = i < j ? i : j, hi = i < j ? j : i; return lo * D - ((lo * (lo - 1)) >> 1) + (hi - lo); };
+  const double w1_last = w1_first + 2.0 * (Td - 1.0);
+  const double w2_last = fma(3.0 * w1_last, w1_last, w2c);
+#pragma unroll
+  for (int a = 0; a < R; ++a) {
+    const int i = l * R + a;
+    if (i >= D) continue;
+#pragma unroll
+    for (int k = 0; k < LR; ++k) {
+      const int j = (l * R + k) % LR;
+      if (j < D) m[M::OFF_BZ + i * D + j] = S.bz[a][k];
+    }
+#pragma unroll
+    for (int p = 0; p < Q::NFULL; ++p)
+#pragma unroll
+      for (int b = 0; b < R; ++b) {
+        const int j = (l * R + (p + 1) * R + b) % LR;
+        if (j < D) m[tri(i, j)] = S.bfull[p][a][b];
+      }
+    double* t = m + M::OFF_TOT + i;
+    const double cT = S.c[a];                          // own rows are the first R of the rotated frame
+    t[0 * D] = S.s0[a];
+    t[1 * D] = S.s1[a];
+    t[2 * D] = S.s2[a];
+    t[3 * D] = cT;
+    t[4 * D] = fma(w1_last, cT, -2.0 * S.s0[a]);       // summation by parts, see jne_lane_moments_kernel
+    t[5 * D] = fma(w2_last, cT, 12.0 * (S.s0[a] - S.s1[a]));
+  }
+  {
+    int idx = 0;
+#pragma unroll
+    for (int a = 0; a < R; ++a)
+#pragma unroll
+      for (int b = a; b < R; ++b) {
+        const int i = l * R + a, j = l * R + b, jh = (l * R + (L / 2) * R + b) % LR;
+        if (i < D && j < D) m[tri(i, j)] = S.bown[idx];
+        if (Q::HALF && i < D && jh < D) m[tri(i, jh)] = S.bhalf[idx];
+        ++idx;
+      }
+  }
+}

@@ -457,9 +457,10 @@ def test_warp_specialised_kernel_family():
 
 def test_lane_family_vs_tensor_family():
     """dim <= 6 runs on the lane family (csrc/jne_kernels_lane.cuh: one thread per run, FP64 FMA on registers, the sums
-    left to right); JNE_LANE=0 sends the same dims through the tensor family (one warp per run, DMMA tiles, four time
-    segments).  Both consume the same random stream, so their records agree to rounding -- well inside the gate-1
-    tolerance -- for every model, ragged T, single-model and fused entry points."""
+    left to right) and dim 9, 10 on its group kernels (3 resp. 5 lanes per run); JNE_LANE=0 sends the same dims through
+    the tensor family (one warp per run, DMMA tiles, four time segments, trend moments through the MMA).  Both consume
+    the same random stream, so their records agree to rounding -- well inside the gate-1 tolerance -- for every model,
+    ragged T (masked tail blocks, empty segments on the tensor side), single-model and fused entry points."""
     import os, subprocess, sys, textwrap
     code = textwrap.dedent('''
         import sys, numpy as np
@@ -467,7 +468,10 @@ def test_lane_family_vs_tensor_family():
         import johansen_null_eigenspectra_b200 as jne
         eng = jne.Engine([0])
         out = {}
-        for dim, T, n in [(1, 9, 70), (2, 1000, 300), (3, 37, 50), (4, 10000, 40), (5, 5000, 200), (6, 103, 3000)]:
+        cases = [(1, 9, 70), (2, 1000, 300), (3, 37, 50), (4, 10000, 40), (5, 5000, 200), (6, 103, 3000),
+                 (9, 103, 2000), (10, 1001, 300), (9, 10000, 45), (10, 10000, 30), (9, 31, 41), (10, 33, 50)]
+        cases += [(d, T, 9) for d in (1, 2, 3, 4, 5, 6, 9, 10) for T in (2 * d + 6, 67, 250)]
+        for dim, T, n in cases:
             seeds = np.arange(11, 11 + n, dtype=np.uint32)
             res = eng.eigs_batch_multi(range(5), dim, T, seeds)
             for m in range(5):
