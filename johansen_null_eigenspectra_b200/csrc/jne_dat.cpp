@@ -1,6 +1,7 @@
 // Batched EIGENVALS_V6 writer / reader / resume scan (include/jne_dat.h).  Host-only.
 #include <cerrno>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <string>
@@ -371,6 +372,38 @@ int jne_dat_append_batch_strided_mt(jne_dat_writer* w, const uint32_t* seeds, co
     off[t + 1] = off[t] + bytes;
   }
   const uint64_t total = off[threads];
+  static const bool use_mmap = [] { const char* e = getenv("JNE_DAT_MMAP"); return !(e && e[0] == '0'); }();
+  if (!use_mmap) {
+    // Alternative kept for measurement (JNE_DAT_MMAP=0): every encoder fills a private buffer and writes it with a
+    // positioned pwrite(); the byte ranges are the same.  (The first range is written last: see the crash note above.)
+    std::vector<int> werr(threads, 0);
+    std::vector<std::vector<unsigned char>> bufs(threads);
+    std::vector<std::thread> th;
+    auto work = [&](int t) {
+      const uint64_t a = std::min<uint64_t>((uint64_t)t * per, n), b = std::min<uint64_t>(a + per, n);
+      if (a == b) return;
+      bufs[t].resize(off[t + 1] - off[t]);
+      unsigned char* q = bufs[t].data();
+      for (uint64_t i = a; i < b; ++i) q += encode_record(q, seeds[i], eigs + i * stride, p);
+      if (t != 0 && !write_all(w->fd, bufs[t].data(), bufs[t].size(), w->pos + off[t])) werr[t] = errno ? errno : EIO;
+    };
+    {
+      const unsigned char poison[5] = {0xFF, 0xFF, 0xFF, 0xFF, 0xFF};
+      if (!write_all(w->fd, poison, 5, w->pos)) return fail(std::string("write failed: ") + strerror(errno));
+    }
+    try {
+      for (int t = 1; t < threads; ++t) th.emplace_back(work, t);
+    } catch (...) { for (auto& x : th) x.join(); if (ftruncate(w->fd, (off_t)w->pos) != 0) {} return fail("could not start an encoder thread"); }
+    work(0);
+    for (auto& x : th) x.join();
+    int bad = 0;
+    for (int e : werr) if (e) bad = e;
+    if (!bad && !write_all(w->fd, bufs[0].data(), bufs[0].size(), w->pos)) bad = errno ? errno : EIO;
+    if (bad) { if (ftruncate(w->fd, (off_t)w->pos) != 0) {} return fail(std::string("write failed: ") + strerror(bad)); }
+    w->pos += total;
+    w->written += n;
+    return JNE_OK;
+  }
   const long page = sysconf(_SC_PAGESIZE);
   const uint64_t map_off = w->pos & ~(uint64_t)(page - 1), delta = w->pos - map_off;
   // grow the file; on a disk file system reserve the blocks now so that a full disk is an error code here, not a

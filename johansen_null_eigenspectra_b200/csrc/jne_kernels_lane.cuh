@@ -602,32 +602,47 @@ jne_group_moments_kernel(const uint32_t* __restrict__ seeds, const double* __res
 #pragma unroll
     for (int s = 0; s < 4; ++s) zs[((buf * 4 + s) * LR + a) * G + wr_off] = v[s];
   };
-  auto consume_step = [&](int buf, int s) {
-    double zz[LR];
+  auto read_step = [&](int buf, int s, double (&zz)[LR]) {
 #pragma unroll
     for (int k = 0; k < LR; ++k) zz[k] = zs[(buf * 4 + s) * LR * G + rd_off[k]];
-    jne_group_step<D, L, DET, SRC_RNG>(S, zz);
   };
 
+  // Schedule of a block tb (its four steps lie complete in buffer tb & 1): block tb + 1 is generated and published
+  // during steps 0..2, every step's increments are read one step ahead of their use (the shared-memory latency hides
+  // behind the previous step's FMAs), and ONE warp barrier sits between steps 2 and 3: by then block tb + 1 is complete
+  // (step 3 prefetches its first step) and every lane already holds step 3 of block tb in registers, so nobody reads
+  // buffer tb & 1 again before block tb + 2 is written into it.
   const uint32_t nfull = T >> 2, tail = T & 3u;
 #pragma unroll
   for (int a = 0; a < R; ++a) publish_row(0u, 0, a);
   __syncwarp();
+  double z0[LR], z1[LR];
+  read_step(0, 0, z0);
   for (uint32_t tb = 0; tb < nfull; ++tb) {
     const int buf = (int)(tb & 1u);
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {                      // block tb + 1 is generated between the steps of block tb
+    for (int a = 0; a < R; ++a) if (a * 3 / R == 0) publish_row(tb + 1u, buf ^ 1, a);
+    read_step(buf, 1, z1);
+    jne_group_step<D, L, DET, SRC_RNG>(S, z0);
 #pragma unroll
-      for (int a = 0; a < R; ++a)
-        if (a * 4 / R == s) publish_row(tb + 1u, buf ^ 1, a);
-      consume_step(buf, s);
-    }
-    __syncwarp();                                      // block tb + 1 is complete; block tb may be overwritten
+    for (int a = 0; a < R; ++a) if (a * 3 / R == 1) publish_row(tb + 1u, buf ^ 1, a);
+    read_step(buf, 2, z0);
+    jne_group_step<D, L, DET, SRC_RNG>(S, z1);
+#pragma unroll
+    for (int a = 0; a < R; ++a) if (a * 3 / R == 2) publish_row(tb + 1u, buf ^ 1, a);
+    read_step(buf, 3, z1);
+    jne_group_step<D, L, DET, SRC_RNG>(S, z0);
+    __syncwarp();
+    read_step(buf ^ 1, 0, z0);
+    jne_group_step<D, L, DET, SRC_RNG>(S, z1);
   }
   {
     const int buf = (int)(nfull & 1u);
 #pragma unroll 1
-    for (uint32_t s = 0; s < tail; ++s) consume_step(buf, (int)s);
+    for (uint32_t s = 0; s < tail; ++s) {
+      read_step(buf, (int)s, z0);
+      jne_group_step<D, L, DET, SRC_RNG>(S, z0);
+    }
   }
   if (!live) return;
 
