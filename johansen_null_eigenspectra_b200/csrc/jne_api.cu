@@ -351,10 +351,11 @@ const double* aux_table_for(jne_ctx* ctx, Device& dv, uint32_t steps) {
 // ---- lane family (jne_kernels_lane.cuh): dim <= 6, one thread per run + one warp per run for the solve ----
 constexpr uint64_t kMomChunk = 1ull << 18;   // upper bound on the runs per moments / solve pair (195 MB of moments at dim 6)
 
-// dims served by the group kernels (L lanes per run): <dim, L>
+// dims served by the group kernels (L lanes per run).  Measured (profiles/r2_variants_group.txt, fused pass, T 10 000):
+// dim 9 with 3 lanes x 3 rows 3.83 M seeds/s against 3.28 M on the tensor family; dim 10 with 5 x 2 3.13 M against
+// 3.27 M (two idle lanes per warp, the replicated path costs 10 of 50 FP64 operations) -- so only dim 9 is routed here.
 #define JNE_GROUP_L9 3
-#define JNE_GROUP_L10 5
-bool group_dim(uint32_t dim) { return dim == 9 || dim == 10; }
+bool group_dim(uint32_t dim) { return dim == 9; }
 bool lane_wanted(const jne_ctx* ctx, const JneRunParams& prm) {
   return ctx->use_lane && ctx->kernel_family == 1 && (prm.dim <= JNE_LANE_MAX_DIM || (ctx->use_group && group_dim(prm.dim)));
 }
@@ -408,7 +409,6 @@ cudaError_t launch_lane_moments_dim(uint32_t dim, int det, const uint32_t* s, co
                                     double* mom, cudaStream_t st) {
   switch (dim) {
     case 9: return launch_group_moments<9, JNE_GROUP_L9, RNG>(det, s, b, m, steps, mom, st);
-    case 10: return launch_group_moments<10, JNE_GROUP_L10, RNG>(det, s, b, m, steps, mom, st);
     case 1: return launch_lane_moments<1, RNG>(det, s, b, m, steps, mom, st);
     case 2: return launch_lane_moments<2, RNG>(det, s, b, m, steps, mom, st);
     case 3: return launch_lane_moments<3, RNG>(det, s, b, m, steps, mom, st);
@@ -458,7 +458,6 @@ uint64_t lane_wave(const Device& dv, const JneRunParams& prm) {
   const int det = lane_det(prm);
   switch (prm.dim) {
     case 9: return group_wave_one<9, JNE_GROUP_L9>(dv, det);
-    case 10: return group_wave_one<10, JNE_GROUP_L10>(dv, det);
     case 1: return lane_wave_one<1>(dv, det);
     case 2: return lane_wave_one<2>(dv, det);
     case 3: return lane_wave_one<3>(dv, det);

@@ -452,7 +452,7 @@ jne_lane_tsolve_kernel(const double* __restrict__ mom, uint64_t n, uint32_t mode
 }
 
 // ---------------------------------------------------------------------------------------------
-// Group kernels: L lanes per run, R = D / L rows per lane (dim 9: 3 x 3, dim 10: 5 x 2).
+// Group kernels: L lanes per run, R = D / L rows per lane (in use: dim 9 as 3 x 3).
 //
 // Above six rows a run's moments no longer fit one thread, and on the tensor path dims 9..11 pay for dim 12's five
 // DMMA tiles (profiles/r2_bench_all_configs_v2.jsonl: 3.28 M seeds/s at dim 9 against 3.19 M at dim 12).  Here the

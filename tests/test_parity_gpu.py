@@ -457,7 +457,7 @@ def test_warp_specialised_kernel_family():
 
 def test_lane_family_vs_tensor_family():
     """dim <= 6 runs on the lane family (csrc/jne_kernels_lane.cuh: one thread per run, FP64 FMA on registers, the sums
-    left to right) and dim 9, 10 on its group kernels (3 resp. 5 lanes per run); JNE_LANE=0 sends the same dims through
+    left to right) and dim 9 on its group kernel (3 lanes per run); JNE_LANE=0 sends the same dims through
     the tensor family (one warp per run, DMMA tiles, four time segments, trend moments through the MMA).  Both consume
     the same random stream, so their records agree to rounding -- well inside the gate-1 tolerance -- for every model,
     ragged T (masked tail blocks, empty segments on the tensor side), single-model and fused entry points."""
