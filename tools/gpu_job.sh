@@ -24,7 +24,10 @@ for stage in "$@"; do
     ncu:*)    IFS=: read -r _ tag regex targs <<< "$stage"
               timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$regex" -s 1 -c 1 -f \
                 -o "gpurun_out/prof_$tag" python tools/ncu_target.py ${targs//,/ } > "gpurun_out/ncu_$tag.log" 2>&1
-              tail -n 2 "gpurun_out/ncu_$tag.log" ;;
+              tail -n 2 "gpurun_out/ncu_$tag.log"
+              # reports are ~17 MB each and gpurun_out/ is capped at 64 MiB: digest on the box, keep the report only on request
+              python tools/ncu_digest.py "gpurun_out/prof_$tag.ncu-rep" > "gpurun_out/ncu_digest_$tag.txt" 2>&1
+              if [ -z "$KEEP_REP" ]; then rm -f "gpurun_out/prof_$tag.ncu-rep"; fi ;;
     variants) timeout 1200 python tools/variants.py run 2>&1 | tee gpurun_out/variants.txt ;;
     gate2ks)  timeout 1200 python tools/validate_gate2.py ks 2>&1 | tee gpurun_out/gate2_ks.txt ;;
     gate2ab:*) IFS=: read -r _ dim T n <<< "$stage"
