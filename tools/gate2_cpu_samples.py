@@ -61,12 +61,13 @@ def main():
     ap.add_argument("--chunk", type=int, default=50000)
     ap.add_argument("--K", type=int, default=16384)
     ap.add_argument("--out", required=True)
+    ap.add_argument("--first-seed", type=int, default=1, help="seeds first-seed .. first-seed + n - 1")
     ap.add_argument("--work", default="/tmp/jne_gate2_work")
     args = ap.parse_args()
 
     from oracle import c_oracle
     lib = c_oracle.load()
-    work = Path(args.work) / f"d{args.dim}_T{args.T}"
+    work = Path(args.work) / (f"d{args.dim}_T{args.T}" + (f"_s{args.first_seed}" if args.first_seed != 1 else ""))
     work.mkdir(parents=True, exist_ok=True)
     t0 = time.time()
     parts = []
@@ -74,12 +75,12 @@ def main():
         b = min(a + args.chunk, args.n)
         f = work / f"chunk_{a}_{b}.npy"
         if not f.exists():
-            st = c_oracle.fast_multi_stats(lib, args.dim, args.T, np.arange(a + 1, b + 1, dtype=np.uint32), args.threads)
+            st = c_oracle.fast_multi_stats(lib, args.dim, args.T, np.arange(args.first_seed + a, args.first_seed + b, dtype=np.uint32), args.threads)
             np.save(f, st)
             print(f"[{time.time() - t0:7.0f} s] seeds {a + 1}..{b} done", flush=True)
         parts.append(np.load(f))
     st = np.concatenate(parts)                       # (n, 5, 2)
-    out = {"dim": args.dim, "T": args.T, "n": args.n, "K": args.K, "qs": np.array(QS),
+    out = {"dim": args.dim, "T": args.T, "n": args.n, "K": args.K, "qs": np.array(QS), "first_seed": args.first_seed,
            "generator": "xoshiro256++ seeded by the run seed, 256-layer ziggurat, f64 (oracle/jne_oracle.c)"}
     for m in range(5):
         for k, name in enumerate(("trace", "max")):

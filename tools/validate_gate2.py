@@ -35,8 +35,8 @@ def cmd_ks(args):
             continue
         t0 = time.time()
         n_cpu = int(np.load(g2.cpu_grid_path(dim, T))["n"])
-        rows = g2.compare(eng, dim, T, args.n or n_cpu)
-        print(f"# dim {dim}, T {T}: GPU seeds 1..{rows[0]['n_gpu']} vs CPU f64-ziggurat sample of {rows[0]['n_cpu']} runs "
+        rows = g2.compare(eng, dim, T, args.n or n_cpu, first_seed=args.first_seed)
+        print(f"# dim {dim}, T {T}: GPU seeds {args.first_seed}..{args.first_seed + rows[0]['n_gpu'] - 1} vs CPU f64-ziggurat sample of {rows[0]['n_cpu']} runs "
               f"({time.time() - t0:.1f} s); KS alpha = {g2.ALPHA}")
         print(g2.format_rows(rows))
         print("# quantiles (GPU | CPU | relative difference), q = " + ", ".join(str(q) for q in g2.QS))
@@ -117,6 +117,7 @@ def main():
     ap.add_argument("--T", type=int, default=10000)
     ap.add_argument("--n", type=int, default=0, help="GPU seeds (ks: 0 = as many as the CPU sample; ab: required)")
     ap.add_argument("--out", default="")
+    ap.add_argument("--first-seed", type=int, default=1)
     args = ap.parse_args()
     {"ks": cmd_ks, "ab": cmd_ab, "ab-worker": cmd_ab_worker}[args.cmd](args)
 
