@@ -27,7 +27,10 @@
 
 namespace {
 
-constexpr uint64_t kSlotSeeds = 1ull << 17;   // capacity of a staging slot, in runs (seed buffer) ...
+constexpr uint64_t kSlotSeeds = 1ull << 18;   // capacity of a staging slot, in runs (seed buffer) ...
+constexpr int kSlots = 3;                     // staging slots per device, each with its own stream: while the host hands chunk i-3
+                                              // to the caller (~6 GB/s), chunks i-2 and i-1 keep the device busy (two slots left
+                                              // a bubble per chunk at the small dims: c2 80 % of the device-resident rate)
 constexpr uint64_t kMaxWidth = 5 * 16;        // doubles per run: all five models at dim 15
 constexpr uint64_t kSlotDoubles = (1ull << 15) * kMaxWidth;   // ... and in eigenvalues (21 MB): 2^15 runs at the widest row,
                                                                // 2^17 runs up to 20 doubles per run
@@ -52,12 +55,12 @@ struct Slot {
 struct Device {
   int id = -1;
   cudaStream_t stream = nullptr;
-  Slot slot[2];
+  Slot slot[kSlots];
   unsigned int* d_err = nullptr;
   unsigned int* h_err = nullptr;  // pinned
   uint32_t* d_jtab = nullptr;   // 8 Jacobi step tables (ne = 2, 4, .., 16), kTabWords words each
-  double* d_mom[2] = {nullptr, nullptr};   // lane family: per-run moments between the moments and the solve kernel,
-  size_t mom_doubles[2] = {0, 0};          // one buffer per concurrently used stream (capacity in doubles)
+  double* d_mom[kSlots] = {};              // lane family: per-run moments between the moments and the solve kernel,
+  size_t mom_doubles[kSlots] = {};         // one buffer per concurrently used stream (capacity in doubles)
   int sm_count = 0;
   std::map<uint32_t, double*> aux_tabs;   // trend-weight tables of the AUX kernels, by steps (make_aux_table)
   double* d_scratch = nullptr;    // increments / pencil inputs, grown on demand
@@ -598,11 +601,36 @@ int ensure_scratch(jne_ctx* ctx, Device& dv, size_t bytes) {
   return JNE_OK;
 }
 
+// Hand-over copy pinned staging -> caller's array.  One host thread moves ~4 GB/s here, and the small dims produce
+// their rows faster than that (c2: 26 M seeds/s x 216 B); large chunks are split over a few short-lived threads.
+// (Page-locking the caller's array for a direct DMA was measured and lost: cudaHostRegister + Unregister cost more than
+// the copy they save -- dim 12: 99.7 % -> 81 % of the device-resident rate, profiles/r2_exp_e2e_small_dims.txt.)
+void handover_copy(double* dst, const double* src, size_t n_doubles) {
+  const size_t bytes = n_doubles * sizeof(double);
+  if (bytes < ((size_t)4 << 20)) { std::memcpy(dst, src, bytes); return; }
+  constexpr int kThreads = 4;
+  const size_t per = (n_doubles + kThreads - 1) / kThreads;
+  std::thread th[kThreads - 1];
+  int started = 0;
+  try {
+    for (int t = 1; t < kThreads; ++t) {
+      const size_t a = std::min(n_doubles, t * per), b = std::min(n_doubles, a + per);
+      th[t - 1] = std::thread([=]() { std::memcpy(dst + a, src + a, (b - a) * sizeof(double)); });
+      ++started;
+    }
+  } catch (...) {   // could not start a helper: copy the rest here
+    const size_t a = std::min(n_doubles, (size_t)(started + 1) * per);
+    std::memcpy(dst + a, src + a, (n_doubles - a) * sizeof(double));
+  }
+  std::memcpy(dst, src, std::min(n_doubles, per) * sizeof(double));
+  for (int t = 0; t < started; ++t) th[t].join();
+}
+
 // Drain one slot: wait for its D2H, hand the rows to the caller's array.
 int drain(jne_ctx* ctx, Slot& s, uint32_t p, double* out) {
   if (!s.busy) return JNE_OK;
   JNE_CUDA(ctx, cudaEventSynchronize(s.done));
-  std::memcpy(out + s.offset * p, s.h_out, s.n * p * sizeof(double));
+  handover_copy(out + s.offset * p, s.h_out, s.n * p);
   s.busy = false;
   return JNE_OK;
 }
@@ -626,6 +654,7 @@ int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32
     uint64_t chunk = std::min(kChunkTarget, cap);
     const uint64_t wave = wave_runs(ctx, dv, prm);
     if (wave > 0 && wave <= cap) chunk = std::max<uint64_t>(1, kChunkTarget / wave) * wave;
+    else if (wave > cap) chunk = cap;          // a wave does not fit the slot: fill the slot rather than 8 k runs
     while (done < n) {
       Slot& s = dv.slot[which];
       int rc = drain(ctx, s, prm.p, out);
@@ -641,10 +670,10 @@ int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32
       JNE_CUDA(ctx, cudaEventRecord(s.done, s.stream));
       s.n = m; s.offset = done; s.busy = true;
       done += m;
-      which ^= 1;
+      which = (which + 1) % kSlots;
     }
-    for (int i = 0; i < 2; ++i) {
-      int rc = drain(ctx, dv.slot[which ^ i], prm.p, out);
+    for (int i = 0; i < kSlots; ++i) {      // oldest first
+      int rc = drain(ctx, dv.slot[(which + i) % kSlots], prm.p, out);
       if (rc) return rc;
     }
     JNE_CUDA(ctx, cudaMemcpyAsync(dv.h_err, dv.d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, dv.stream));
@@ -659,8 +688,8 @@ int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32
   // ctx->err is shared between device threads: serialise through a local copy
   int rc = body();
   if (rc) {
-    // error exit: let whatever is still in flight on the slots' streams finish (it targets the library's own staging
-    // buffers), and forget it -- a later call must not copy stale rows into its caller's array
+    // error exit: let whatever is still in flight on the slots' streams finish (no DMA may touch the caller's array or
+    // the staging buffers after this call returns), and forget it -- a later call must not copy stale rows
     for (auto& s : dv.slot) { if (s.stream) cudaStreamSynchronize(s.stream); s.busy = false; }
     cudaGetLastError();
     if (err_out) { std::lock_guard<std::mutex> lk(ctx->err_mu); *err_out = ctx->err; }
