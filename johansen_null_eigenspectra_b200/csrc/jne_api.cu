@@ -358,7 +358,11 @@ constexpr uint64_t kMomChunk = 1ull << 18;   // upper bound on the runs per mome
 // dim 9 with 3 lanes x 3 rows 3.83 M seeds/s against 3.28 M on the tensor family; dim 10 with 5 x 2 3.13 M against
 // 3.27 M (two idle lanes per warp, the replicated path costs 10 of 50 FP64 operations) -- so only dim 9 is routed here.
 #define JNE_GROUP_L9 3
+#ifdef JNE_EXP_GROUP_78   // experiment: dims 7, 8 as 2 lanes x 4 rows, dim 10 as 5 x 2
+bool group_dim(uint32_t dim) { return dim >= 7 && dim <= 10; }
+#else
 bool group_dim(uint32_t dim) { return dim == 9; }
+#endif
 bool lane_wanted(const jne_ctx* ctx, const JneRunParams& prm) {
   return ctx->use_lane && ctx->kernel_family == 1 && (prm.dim <= JNE_LANE_MAX_DIM || (ctx->use_group && group_dim(prm.dim)));
 }
@@ -412,6 +416,11 @@ cudaError_t launch_lane_moments_dim(uint32_t dim, int det, const uint32_t* s, co
                                     double* mom, cudaStream_t st) {
   switch (dim) {
     case 9: return launch_group_moments<9, JNE_GROUP_L9, RNG>(det, s, b, m, steps, mom, st);
+#ifdef JNE_EXP_GROUP_78
+    case 7: return launch_group_moments<7, 2, RNG>(det, s, b, m, steps, mom, st);
+    case 8: return launch_group_moments<8, 2, RNG>(det, s, b, m, steps, mom, st);
+    case 10: return launch_group_moments<10, 5, RNG>(det, s, b, m, steps, mom, st);
+#endif
     case 1: return launch_lane_moments<1, RNG>(det, s, b, m, steps, mom, st);
     case 2: return launch_lane_moments<2, RNG>(det, s, b, m, steps, mom, st);
     case 3: return launch_lane_moments<3, RNG>(det, s, b, m, steps, mom, st);
@@ -461,6 +470,11 @@ uint64_t lane_wave(const Device& dv, const JneRunParams& prm) {
   const int det = lane_det(prm);
   switch (prm.dim) {
     case 9: return group_wave_one<9, JNE_GROUP_L9>(dv, det);
+#ifdef JNE_EXP_GROUP_78
+    case 7: return group_wave_one<7, 2>(dv, det);
+    case 8: return group_wave_one<8, 2>(dv, det);
+    case 10: return group_wave_one<10, 5>(dv, det);
+#endif
     case 1: return lane_wave_one<1>(dv, det);
     case 2: return lane_wave_one<2>(dv, det);
     case 3: return lane_wave_one<3>(dv, det);
@@ -502,7 +516,7 @@ cudaError_t launch_lane(jne_ctx* ctx, Device& dv, const uint32_t* s, const doubl
     double* dp = dbg ? dbg + off * 512 : nullptr;
     // solve: one thread per run; the warp-per-run epilogue of the tensor family only when the caller wants the
     // assembled matrices back (jne_eigs_batch_debug) or asks for it (JNE_LANE_SOLVE=warp, regression tooling)
-    if (prm.dim > 8) rc = multi ? launch_lane_solve<12, true>(d_mom, m, prm, op, e, dp, st) : launch_lane_solve<12, false>(d_mom, m, prm, op, e, dp, st);
+    if (prm.dim > 6) rc = multi ? launch_lane_solve<12, true>(d_mom, m, prm, op, e, dp, st) : launch_lane_solve<12, false>(d_mom, m, prm, op, e, dp, st);
     else if (dp == nullptr && ctx->lane_thread_solve) rc = launch_lane_tsolve_dim(d_mom, m, prm, op, e, st);
     else if (prm.dim <= 4) rc = multi ? launch_lane_solve<4, true>(d_mom, m, prm, op, e, dp, st) : launch_lane_solve<4, false>(d_mom, m, prm, op, e, dp, st);
     else rc = multi ? launch_lane_solve<8, true>(d_mom, m, prm, op, e, dp, st) : launch_lane_solve<8, false>(d_mom, m, prm, op, e, dp, st);

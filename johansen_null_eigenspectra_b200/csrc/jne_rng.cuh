@@ -94,7 +94,7 @@ __device__ __forceinline__ void jne_box_muller(uint32_t wa, uint32_t wb, float& 
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));   // MUFU.LG2 (u >= 2^-33: never denormal)
   // -2 ln 2 as a float is -0x1.62e430p+0; the constant below sits three ulps further out (+2.58e-7 relative).  It
   // cancels the variance deficit of this FP32 / MUFU pipeline, measured on 2^27 normals against the FP64 transform of
-  // the same Philox blocks: E[z^2]_fp32 - E[z^2]_fp64 = -2.5265e-7 +- 8e-11 (profiles/r2_rng_moments.txt; every
+  // the same Philox blocks: E[z^2]_fp32 - E[z^2]_fp64 = -2.5265e-7 +- 8e-11 (profiles/r2_rng_moments_before_calibration.txt; every
   // eigenvalue statistic carried the same -2.53e-7 relative shift, profiles/r2_gate2_ab_*).  The eigenvalues scale
   // with Var(z), so this is the one moment worth calibrating; residual +5e-9.
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -0x1.62e436p+0f));  // MUFU.SQRT

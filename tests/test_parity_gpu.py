@@ -512,3 +512,41 @@ def test_host_path_chunking_is_invisible(engine):
     multi = engine.eigs_batch_multi(range(5), 6, 16, seeds)
     for m in range(5):
         assert np.array_equal(multi[m], engine.eigs_batch(m, 6, 16, seeds))
+
+
+def test_device_normals_moments_and_tails(engine):
+    """The FP32 / MUFU Box-Muller stream (32-bit radius uniform, |z| <= 6.76) as a N(0,1) sample: mean, variance,
+    skewness, kurtosis and the |z| quantiles up to 1 - 1e-5 on 2^25 normals against the exact values, within 4.5
+    Monte Carlo standard errors; and -- when the validation build (jne_rng.cuh, -DJNE_RNG_F64: 64-bit uniforms, FP64
+    transform of the SAME Philox blocks) is present -- element by element against it: the transform's error is ~1e-6
+    per normal and its variance deficit (-2.53e-7 before the radius-constant calibration, profiles/r2_rng_moments_before_calibration.txt)
+    is gone to 3e-8.  The reference's own test is a CDF check to 1e-2 on 60 000 normals
+    (src/tests/rng_matrix_test/gen_normal_matrix_test.rs:7-16)."""
+    import os, subprocess, sys
+    from johansen_null_eigenspectra_b200 import build as jbuild
+    dim, steps, calls = 8, 1 << 20, 4
+    z = np.concatenate([engine.gen_normal_matrix(dim, steps, 4242 + c).ravel() for c in range(calls)])
+    n = z.size
+    assert abs(z.mean()) < 4.5 / np.sqrt(n)
+    assert abs((z ** 2).mean() - 1.0) < 4.5 * np.sqrt(2.0 / n)
+    assert abs((z ** 3).mean()) < 4.5 * np.sqrt(15.0 / n)
+    assert abs((z ** 4).mean() - 3.0) < 4.5 * np.sqrt(96.0 / n)
+    a = np.sort(np.abs(z))
+    for q in (0.9, 0.99, 0.999, 0.9999, 0.99999):
+        x = stats.norm.ppf(0.5 + q / 2)
+        se = np.sqrt(q * (1 - q) / n) / (2 * stats.norm.pdf(x))
+        assert abs(a[int(q * (n - 1))] - x) < 4.5 * se + 2e-6, q
+    assert np.abs(z).max() < 6.77
+    f64 = jbuild.VARIANTS["rng_f64"][1]
+    if not f64.exists():
+        return
+    code = ("import sys, numpy as np; sys.path.insert(0, '.'); import johansen_null_eigenspectra_b200 as jne; e = jne.Engine([0]); "
+            f"np.save(sys.argv[1], np.concatenate([e.gen_normal_matrix({dim}, {steps}, 4242 + c).ravel() for c in range({calls})]))")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code, "/tmp/jne_z_f64.npy"], cwd=root, env=dict(os.environ, JNE_LIBRARY=str(f64)),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    y = np.load("/tmp/jne_z_f64.npy")
+    assert np.abs(z - y).max() < 2e-3 and np.sqrt(np.mean((z - y) ** 2)) < 1e-6      # same blocks, FP32 vs FP64 transform
+    d2 = z * z - y * y
+    assert abs(d2.mean()) < 3e-8 + 4.5 * d2.std() / np.sqrt(n), d2.mean()               # variance: calibrated

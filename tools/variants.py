@@ -12,6 +12,7 @@ VARIANTS = {
     "philox7": ["-DJNE_PHILOX_ROUNDS=7"],          # Random123's smallest Crush-resistant round count (default 10)
     "nobm": ["-DJNE_EXP_NOBM"],                    # Philox only, no normal transform (NOT a valid stream)
     "norng": ["-DJNE_EXP_NORNG"],                  # no generator at all (NOT a valid stream)
+    "group78": ["-DJNE_EXP_GROUP_78"],             # dims 7, 8 on the group kernel (2 lanes x 4 rows), dim 10 as 5 x 2
     "lane_nopipe": ["-DJNE_LANE_PIPELINE=0"],      # lane family without the software pipeline (generate a block, then consume it)
     "lane_nopipe_minb3": ["-DJNE_LANE_PIPELINE=0", "-DJNE_LANE_MINB5=3"],   # ... and dim 5 at 168 registers / 3 CTAs per SM
 }
@@ -51,7 +52,7 @@ def t(models, dim, T, n, reps=3):
         best = min(best, e0.elapsed_time(e1))
     return n / best / 1e3      # M seeds/s
 res = {"fused_d12": t(range(5), 12, 10000, 133200), "m0_d12": t([0], 12, 10000, 133200), "m4_d12": t([4], 12, 10000, 133200),
-       "fused_d9": t(range(5), 9, 10000, 118400), "fused_d10": t(range(5), 10, 10000, 118400), "fused_d11": t(range(5), 11, 10000, 133200), "fused_d8": t(range(5), 8, 10000, 133200),
+       "fused_d9": t(range(5), 9, 10000, 118400), "fused_d10": t(range(5), 10, 10000, 118400), "fused_d11": t(range(5), 11, 10000, 133200), "fused_d8": t(range(5), 8, 10000, 133200), "fused_d7": t(range(5), 7, 10000, 133200),
        "fused_d5_T5000": t(range(5), 5, 5000, 1 << 20), "m0_d5_T5000": t([0], 5, 5000, 1 << 20), "m4_d5_T5000": t([4], 5, 5000, 1 << 20),
        "fused_d1": t(range(5), 1, 10000, 1 << 20), "fused_d3": t(range(5), 3, 10000, 1 << 20)}
 print(json.dumps(res))
