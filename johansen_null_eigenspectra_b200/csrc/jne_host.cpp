@@ -2,6 +2,7 @@
 // (src/data_storage/parallel_compute.rs:150-232) over the GPU hot path and the batched .dat writer.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <thread>
@@ -182,7 +183,8 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
               if (!((mask >> m) & 1u)) continue;
               th[m] = std::thread([&, m]() {
                 // encoders per file: what the host has beyond one thread per file, as far as the devices need it
-                const int enc = std::max(1, std::min({4, n_dev, hw / (2 * __builtin_popcount(mask))}));
+                static const int enc_env = [] { const char* e = getenv("JNE_DAT_ENCODERS"); return e ? atoi(e) : 0; }();
+                const int enc = enc_env > 0 ? enc_env : std::max(1, std::min({4, n_dev, hw / (2 * __builtin_popcount(mask))}));
                 rcs[m] = jne_dat_append_batch_strided_mt(w[m], seeds.data() + prev_a, rows + off[m], prev_n, pm[m], width, enc);
                 if (rcs[m] != JNE_OK) errs[m] = jne_dat_last_error();
               });
