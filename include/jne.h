@@ -85,6 +85,19 @@ int jne_eigs_batch_multi_device(jne_ctx* ctx, uint32_t model_mask, uint32_t dim,
 int jne_multi_width(uint32_t model_mask, uint32_t dim);   /* sum of jne_num_eigs over the selected models */
 int jne_ctx_device_count(const jne_ctx* ctx);             /* devices this context shards its batches over */
 
+/* Streaming form of the fused batch -- the closest counterpart of the reference's interface, which SENDS every run's
+ * record through a channel as it is finished (`sender: mpsc::Sender<(u32, Vec<f64>)>`,
+ * src/data_storage/parallel_compute.rs:14-41): the rows of seeds[first .. first + count) -- `count` rows of
+ * jne_multi_width(model_mask, dim) doubles, same content as jne_eigs_batch_multi -- are handed to `sink` as soon as
+ * they are back on the host, straight from the library's pinned staging memory (valid during the call only), without
+ * the copy into a caller array.  `sink` runs on the library's per-device host threads: it may be called concurrently
+ * for disjoint ranges, in no particular order, and must not call back into the same context; a non-zero return value
+ * aborts the batch (JNE_ERR_IO).  Returns after every row has been delivered.  run_models_simulation encodes the .dat
+ * records inside the sink. */
+typedef int (*jne_rows_sink)(void* user, uint64_t first, uint64_t count, const double* rows);
+int jne_eigs_batch_multi_stream(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps,
+                                const uint32_t* seeds, uint64_t n, jne_rows_sink sink, void* user);
+
 /* Asynchronous pair: jne_submit enqueues the batch (seeds are copied before it returns; `out`
  * must stay valid until jne_wait) and returns a ticket > 0, or a negative status.  jne_wait
  * blocks until that batch's eigenvalues are in `out`.  At most one ticket may be outstanding

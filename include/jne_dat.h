@@ -48,10 +48,26 @@ int jne_dat_append_batch(jne_dat_writer* w, const uint32_t* seeds, const double*
  * multi-model batch (jne_eigs_batch_multi) without a de-interleaving copy.  stride >= p. */
 int jne_dat_append_batch_strided(jne_dat_writer* w, const uint32_t* seeds, const double* eigs, uint64_t n, uint32_t p,
                                  uint64_t stride);
-/* The same with the records encoded by `threads` host threads (contiguous ranges, written in order): one core encodes
- * about 10^7 records/s, a multi-GPU context produces several times that per file.  Same bytes as the serial call. */
+/* The same with the records encoded by `threads` host threads straight into the file's pages (a random-access batch,
+ * below, filled in contiguous ranges).  Same bytes as the serial call. */
 int jne_dat_append_batch_strided_mt(jne_dat_writer* w, const uint32_t* seeds, const double* eigs, uint64_t n, uint32_t p,
                                     uint64_t stride, int threads);
+
+/* Random-access batch: reserves the bytes of n records (seeds[i], p values each -- the sizes follow from the seeds) at
+ * the end of the file, maps them, and lets several threads fill disjoint record ranges in any order; the file ends up
+ * byte-identical to appending the same records serially.  This is how run_models_simulation lets every device's host
+ * thread encode its rows straight from the pinned staging buffer into the file (no intermediate array, no writer
+ * phase).  `seeds` must stay valid until jne_dat_batch_end.  Crash consistency: until the batch is committed its first
+ * five bytes are 0xFF (an invalid ULEB128 at which the reference's scan reader, reader.rs:163-166, stops), so an
+ * interrupted job resumes at the start of the batch.
+ *   jne_dat_batch_fill   records first .. first+count-1 from rows (record i at rows + (i - first) * stride); thread-safe
+ *                        for disjoint ranges; threads > 1 splits a large range over short-lived helper threads
+ *   jne_dat_batch_end    commit != 0: every record must have been filled; the batch becomes part of the file.
+ *                        commit == 0: the file is truncated back to where the batch began.  Frees the batch. */
+typedef struct jne_dat_batch jne_dat_batch;
+int jne_dat_batch_begin(jne_dat_writer* w, const uint32_t* seeds, uint64_t n, uint32_t p, jne_dat_batch** out);
+int jne_dat_batch_fill(jne_dat_batch* b, uint64_t first, uint64_t count, const double* rows, uint64_t stride, int threads);
+int jne_dat_batch_end(jne_dat_batch* b, int commit);
 
 /* Flush buffered records to the OS (the reference flushes every 10 000 records, config.rs:5). */
 int jne_dat_flush(jne_dat_writer* w);

@@ -40,6 +40,7 @@ def _load() -> C.CDLL:
         "jne_eigs_batch": (C.c_int, [vp, u8, u32, u32, vp, u64, vp]),
         "jne_eigs_batch_multi": (C.c_int, [vp, u32, u32, u32, vp, u64, vp]),
         "jne_eigs_batch_multi_device": (C.c_int, [vp, u32, u32, u32, vp, u64, vp, vp]),
+        "jne_eigs_batch_multi_stream": (C.c_int, [vp, u32, u32, u32, vp, u64, vp, vp]),
         "jne_multi_width": (C.c_int, [u32, u32]),
         "jne_submit": (i64, [vp, u8, u32, u32, vp, u64, vp]),
         "jne_wait": (C.c_int, [vp, i64]),
@@ -226,6 +227,35 @@ class Engine:
             res[m] = out[:, off:off + p]
             off += p
         return res
+
+    def eigs_batch_multi_stream(self, models, dim: int, steps: int, seeds, sink) -> None:
+        """The fused batch with its rows SENT to ``sink(first, rows)`` as they arrive (the reference's channel model,
+        src/data_storage/parallel_compute.rs:14-41): ``rows`` is a (count, width) float64 view of the library's pinned
+        staging memory, valid during the call only (copy what you keep); ``first`` is the index of its first seed in
+        ``seeds``.  The sink runs on the library's per-device host threads (under the GIL here), for disjoint ranges,
+        in no particular order; an exception or a truthy return value aborts the batch."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        models = sorted({_model_number(m) for m in models})
+        mask = self._mask(models)
+        width = lib.jne_multi_width(mask, dim)
+        if width < 0:
+            raise JneError(width, "invalid model mask / dim")
+        failure = []
+
+        @C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_double))
+        def _sink(_user, first, count, rows):
+            try:
+                view = np.ctypeslib.as_array(rows, shape=(count, width))
+                return 1 if sink(int(first), view) else 0
+            except BaseException as exc:      # nothing may propagate into the C frames
+                failure.append(exc)
+                return 1
+
+        rc = lib.jne_eigs_batch_multi_stream(self._ctx, mask, dim, steps, seeds.ctypes.data, seeds.size,
+                                             C.cast(_sink, C.c_void_p), None)
+        if failure:
+            raise failure[0]
+        self._check(rc)
 
     def eigs_batch_multi_device(self, models, dim: int, steps: int, d_seeds_ptr: int, n: int, d_out_ptr: int,
                                 stream_ptr: int = 0) -> None:

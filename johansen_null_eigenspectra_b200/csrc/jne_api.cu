@@ -640,17 +640,29 @@ void handover_copy(double* dst, const double* src, size_t n_doubles) {
   for (int t = 0; t < started; ++t) th[t].join();
 }
 
-// Drain one slot: wait for its D2H, hand the rows to the caller's array.
-int drain(jne_ctx* ctx, Slot& s, uint32_t p, double* out) {
+// Where a share's rows go: into the caller's array, or to the caller's sink (jne_eigs_batch_multi_stream).
+struct RowSink {
+  double* out = nullptr;            // array of this share (row 0 = the share's first seed)
+  jne_rows_sink fn = nullptr;
+  void* user = nullptr;
+  uint64_t base = 0;                // index of the share's first seed in the caller's seed list
+};
+
+// Drain one slot: wait for its D2H, hand the rows over.
+int drain(jne_ctx* ctx, Slot& s, uint32_t p, const RowSink& sink) {
   if (!s.busy) return JNE_OK;
   JNE_CUDA(ctx, cudaEventSynchronize(s.done));
-  handover_copy(out + s.offset * p, s.h_out, s.n * p);
   s.busy = false;
+  if (sink.fn) {
+    if (sink.fn(sink.user, sink.base + s.offset, s.n, s.h_out) != 0) return fail(ctx, JNE_ERR_IO, "the row sink reported a failure");
+  } else {
+    handover_copy(sink.out + s.offset * p, s.h_out, s.n * p);
+  }
   return JNE_OK;
 }
 
 // One device's share of a host-buffer batch (called on its own host thread).
-int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32_t* seeds, uint64_t n, double* out,
+int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32_t* seeds, uint64_t n, const RowSink& out,
               std::string* err_out) {
   auto body = [&]() -> int {
     JNE_CUDA(ctx, cudaSetDevice(dv.id));
@@ -712,11 +724,11 @@ int run_share(jne_ctx* ctx, Device& dv, const JneRunParams& prm_in, const uint32
 }
 
 int eigs_batch_sync_impl(jne_ctx* ctx, uint32_t mask, uint32_t dim, uint32_t steps, const uint32_t* seeds, uint64_t n,
-                         double* out) {
+                         double* out, jne_rows_sink sink_fn = nullptr, void* sink_user = nullptr) {
   const JneRunParams prm = make_params_mask(mask, dim, steps, false);
   const size_t nd = ctx->devs.size();
   if (n == 0) return JNE_OK;
-  if (nd == 1) return run_share(ctx, ctx->devs[0], prm, seeds, n, out, nullptr);
+  if (nd == 1) return run_share(ctx, ctx->devs[0], prm, seeds, n, RowSink{out, sink_fn, sink_user, 0}, nullptr);
   // contiguous slices, one host thread per device, no collective
   std::vector<std::thread> th;
   std::vector<int> rc(nd, JNE_OK);
@@ -727,7 +739,7 @@ int eigs_batch_sync_impl(jne_ctx* ctx, uint32_t mask, uint32_t dim, uint32_t ste
       const uint64_t a = std::min<uint64_t>(i * per, n), b = std::min<uint64_t>(a + per, n);
       if (a == b) continue;
       th.emplace_back([&, i, a, b]() {
-        rc[i] = run_share(ctx, ctx->devs[i], prm, seeds + a, b - a, out + a * prm.p, &errs[i]);
+        rc[i] = run_share(ctx, ctx->devs[i], prm, seeds + a, b - a, RowSink{out ? out + a * prm.p : nullptr, sink_fn, sink_user, a}, &errs[i]);
       });
     }
   } catch (...) {            // a thread could not be started: the ones that run still use rc / errs / out
@@ -1007,6 +1019,18 @@ int jne_eigs_batch_multi(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32
     if ((model_mask >> m) & 1u) { int rc = validate(ctx, (uint8_t)m, dim, steps); if (rc) return rc; }
   if (n && (!seeds || !out)) return fail(ctx, JNE_ERR_INVALID_ARG, "seeds/out is NULL");
   return eigs_batch_sync(ctx, model_mask, dim, steps, seeds, n, out);
+}
+
+int jne_eigs_batch_multi_stream(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, uint32_t steps, const uint32_t* seeds,
+                                uint64_t n, jne_rows_sink sink, void* user) {
+  DeviceGuard device_guard;
+  if (!ctx) return JNE_ERR_INVALID_ARG;
+  join_worker(ctx);
+  if (model_mask == 0 || model_mask > 31u) return fail(ctx, JNE_ERR_INVALID_ARG, "model_mask must select models 0..4");
+  for (int m = 0; m < 5; ++m)
+    if ((model_mask >> m) & 1u) { int rc = validate(ctx, (uint8_t)m, dim, steps); if (rc) return rc; }
+  if (!sink || (n && !seeds)) return fail(ctx, JNE_ERR_INVALID_ARG, "seeds/sink is NULL");
+  return guarded(ctx, [&]() { return eigs_batch_sync_impl(ctx, model_mask, dim, steps, seeds, n, nullptr, sink, user); });
 }
 
 int jne_ctx_device_count(const jne_ctx* ctx) { return ctx ? (int)ctx->devs.size() : JNE_ERR_INVALID_ARG; }

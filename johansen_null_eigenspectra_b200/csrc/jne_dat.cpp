@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -344,130 +346,159 @@ int jne_dat_append_batch_strided(jne_dat_writer* w, const uint32_t* seeds, const
   return JNE_OK;
 }
 
-// Batch append by `threads` encoders that write STRAIGHT INTO THE FILE'S PAGES (no intermediate buffer, no write()
-// through the inode lock): record sizes are known from the seeds, so every encoder owns a disjoint byte range of the
-// batch.  The file grows by the batch, the new range is mapped MAP_SHARED, each encoder populates and fills its own
-// part (page allocation in parallel: on tmpfs that, not the copy, was the wall of the 8-GPU job -- 4.8 GB/s through
-// write()).  Crash consistency: until the batch is complete its first bytes hold 0xFF x 5, an invalid ULEB128 at which
-// both the reference's scan reader (reader.rs:163-166: `Err(_) => break`) and walk() stop, so an interrupted run
-// resumes cleanly at the start of the batch; the first record is copied in last.  Same bytes as the serial call.
-int jne_dat_append_batch_strided_mt(jne_dat_writer* w, const uint32_t* seeds, const double* eigs, uint64_t n, uint32_t p,
-                                    uint64_t stride, int threads) {
-  if (threads <= 1 || n < 4096) return jne_dat_append_batch_strided(w, seeds, eigs, n, p, stride);
+// ---- random-access batch (see include/jne_dat.h) ----
+// Record sizes are known from the seeds, so every record of a batch has its place before any is written: the file grows
+// by the batch, the new range is mapped MAP_SHARED, and whoever has rows encodes them straight into the file's pages
+// (page allocation in parallel; no intermediate buffer, no write() through the inode lock).
+}  // extern "C"
+
+struct jne_dat_batch {
+  static constexpr uint64_t kBlk = 1024;      // prefix table granularity, in records
+  jne_dat_writer* w = nullptr;
+  const uint32_t* seeds = nullptr;
+  uint64_t n = 0, total = 0;
+  uint32_t p = 0;
+  std::vector<uint64_t> blk;                  // byte offset of record i * kBlk inside the batch
+  void* base = nullptr;
+  size_t map_len = 0;
+  unsigned char* dst = nullptr;
+  long page = 4096;
+  unsigned char first[5 + 1 + 8 * 255];
+  size_t first_len = 0;
+  std::atomic<uint64_t> filled{0};
+  std::atomic<int> err{0};
+};
+
+namespace {
+void batch_fill_range(jne_dat_batch* b, uint64_t first, uint64_t count, const double* rows, uint64_t stride) {
+  const uint32_t p = b->p;
+  uint64_t off = b->blk[first / jne_dat_batch::kBlk];
+  for (uint64_t j = (first / jne_dat_batch::kBlk) * jne_dat_batch::kBlk; j < first; ++j)
+    off += (uint64_t)jne_uleb128_encoded_size(b->seeds[j]) + 1 + 8 * (uint64_t)p;
+  unsigned char* q = b->dst + off;
+#ifdef MADV_POPULATE_WRITE
+  {   // allocate this range's pages in one call (whole pages inside it; the edges fault on first touch).  On tmpfs this
+      // is also what turns a full file system into an error code instead of a SIGBUS.
+    uint64_t bytes = count * (1 + 8 * (uint64_t)p);
+    for (uint64_t j = first; j < first + count; ++j) bytes += (uint64_t)jne_uleb128_encoded_size(b->seeds[j]);
+    const uintptr_t lo = ((uintptr_t)q + b->page - 1) & ~(uintptr_t)(b->page - 1), hi = ((uintptr_t)q + bytes) & ~(uintptr_t)(b->page - 1);
+    if (hi > lo && madvise((void*)lo, hi - lo, MADV_POPULATE_WRITE) != 0 && errno == EFAULT) { b->err.store(ENOSPC); return; }
+  }
+#endif
+  uint64_t i = first;
+  if (first == 0 && count > 0) {               // record 0 goes in last (jne_dat_batch_end): the batch stays invalid until then
+    b->first_len = encode_record(b->first, b->seeds[0], rows, p);
+    q += b->first_len;
+    ++i;
+  }
+  for (; i < first + count; ++i) q += encode_record(q, b->seeds[i], rows + (i - first) * stride, p);
+  b->filled.fetch_add(count);
+}
+}  // namespace
+
+extern "C" {
+
+int jne_dat_batch_begin(jne_dat_writer* w, const uint32_t* seeds, uint64_t n, uint32_t p, jne_dat_batch** out) {
+  if (!out) return fail("out is NULL");
+  *out = nullptr;
   if (!w || w->fd < 0) return fail("writer is closed");
-  if (p > 255) return fail("Too many eigenvalues: " + std::to_string(p) + " exceeds maximum of 255");
-  if (stride < p) return fail("stride is smaller than the eigenvalue count");
+  if (p < 1 || p > 255) return fail("Too many eigenvalues: " + std::to_string(p) + " exceeds maximum of 255");
+  if (n == 0 || !seeds) return fail("empty batch");
   if (w->per_run == 0) w->per_run = p;
   if (p != w->per_run)
     return fail("Eigenvalue count mismatch: expected " + std::to_string(w->per_run) + ", actual " + std::to_string(p) +
                 " (model " + std::to_string(w->model) + ", dim " + std::to_string(w->dim) + ", steps " + std::to_string(w->steps) + ")");
-  if (threads > 16) threads = 16;
-  const uint64_t per = (n + threads - 1) / threads;
-  // pass 1: bytes of every encoder's range
-  std::vector<uint64_t> off(threads + 1, 0);
-  for (int t = 0; t < threads; ++t) {
-    const uint64_t a = std::min<uint64_t>((uint64_t)t * per, n), b = std::min<uint64_t>(a + per, n);
-    uint64_t bytes = (b - a) * (1 + 8 * (uint64_t)p);
-    for (uint64_t i = a; i < b; ++i) bytes += (uint64_t)jne_uleb128_encoded_size(seeds[i]);
-    off[t + 1] = off[t] + bytes;
+  jne_dat_batch* b = new (std::nothrow) jne_dat_batch();
+  if (!b) return fail("out of memory");
+  b->w = w; b->seeds = seeds; b->n = n; b->p = p;
+  b->page = sysconf(_SC_PAGESIZE);
+  try { b->blk.resize((n + jne_dat_batch::kBlk - 1) / jne_dat_batch::kBlk + 1); } catch (...) { delete b; return fail("out of memory"); }
+  uint64_t off = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (i % jne_dat_batch::kBlk == 0) b->blk[i / jne_dat_batch::kBlk] = off;
+    off += (uint64_t)jne_uleb128_encoded_size(seeds[i]) + 1 + 8 * (uint64_t)p;
   }
-  const uint64_t total = off[threads];
-  static const bool use_mmap = [] { const char* e = getenv("JNE_DAT_MMAP"); return !(e && e[0] == '0'); }();
-  if (!use_mmap) {
-    // Alternative kept for measurement (JNE_DAT_MMAP=0): every encoder fills a private buffer and writes it with a
-    // positioned pwrite(); the byte ranges are the same.  (The first range is written last: see the crash note above.)
-    std::vector<int> werr(threads, 0);
-    std::vector<std::vector<unsigned char>> bufs(threads);
-    std::vector<std::thread> th;
-    auto work = [&](int t) {
-      const uint64_t a = std::min<uint64_t>((uint64_t)t * per, n), b = std::min<uint64_t>(a + per, n);
-      if (a == b) return;
-      bufs[t].resize(off[t + 1] - off[t]);
-      unsigned char* q = bufs[t].data();
-      for (uint64_t i = a; i < b; ++i) q += encode_record(q, seeds[i], eigs + i * stride, p);
-      if (t != 0 && !write_all(w->fd, bufs[t].data(), bufs[t].size(), w->pos + off[t])) werr[t] = errno ? errno : EIO;
-    };
-    {
-      const unsigned char poison[5] = {0xFF, 0xFF, 0xFF, 0xFF, 0xFF};
-      if (!write_all(w->fd, poison, 5, w->pos)) return fail(std::string("write failed: ") + strerror(errno));
-    }
-    try {
-      for (int t = 1; t < threads; ++t) th.emplace_back(work, t);
-    } catch (...) { for (auto& x : th) x.join(); if (ftruncate(w->fd, (off_t)w->pos) != 0) {} return fail("could not start an encoder thread"); }
-    work(0);
-    for (auto& x : th) x.join();
-    int bad = 0;
-    for (int e : werr) if (e) bad = e;
-    if (!bad && !write_all(w->fd, bufs[0].data(), bufs[0].size(), w->pos)) bad = errno ? errno : EIO;
-    if (bad) { if (ftruncate(w->fd, (off_t)w->pos) != 0) {} return fail(std::string("write failed: ") + strerror(bad)); }
-    w->pos += total;
-    w->written += n;
-    return JNE_OK;
-  }
-  const long page = sysconf(_SC_PAGESIZE);
-  const uint64_t map_off = w->pos & ~(uint64_t)(page - 1), delta = w->pos - map_off;
+  b->total = off;
+  const uint64_t map_off = w->pos & ~(uint64_t)(b->page - 1), delta = w->pos - map_off;
   // grow the file; on a disk file system reserve the blocks now so that a full disk is an error code here, not a
-  // SIGBUS in an encoder (on tmpfs the encoders' MADV_POPULATE_WRITE reports it)
+  // SIGBUS in an encoder (on tmpfs MADV_POPULATE_WRITE reports it)
   if (!w->tmpfs) {
-    const int e = posix_fallocate(w->fd, (off_t)w->pos, (off_t)total);
-    if (e != 0 && e != EOPNOTSUPP && e != EINVAL) return fail(std::string("cannot reserve file space: ") + strerror(e));
+    const int e = posix_fallocate(w->fd, (off_t)w->pos, (off_t)b->total);
+    if (e != 0 && e != EOPNOTSUPP && e != EINVAL) { delete b; return fail(std::string("cannot reserve file space: ") + strerror(e)); }
   }
-  if (ftruncate(w->fd, (off_t)(w->pos + total)) != 0) return fail(std::string("cannot grow the file: ") + strerror(errno));
-  void* base = mmap(nullptr, (size_t)(delta + total), PROT_READ | PROT_WRITE, MAP_SHARED, w->fd, (off_t)map_off);
-  if (base == MAP_FAILED) {
+  if (ftruncate(w->fd, (off_t)(w->pos + b->total)) != 0) { const int e = errno; delete b; return fail(std::string("cannot grow the file: ") + strerror(e)); }
+  b->map_len = (size_t)(delta + b->total);
+  b->base = mmap(nullptr, b->map_len, PROT_READ | PROT_WRITE, MAP_SHARED, w->fd, (off_t)map_off);
+  if (b->base == MAP_FAILED) {
     const int e = errno;
     if (ftruncate(w->fd, (off_t)w->pos) != 0) { /* keep the first error */ }
+    delete b;
     return fail(std::string("cannot map the file: ") + strerror(e));
   }
-  unsigned char* dst = static_cast<unsigned char*>(base) + delta;
-  unsigned char first[5 + 1 + 8 * 255];
-  const size_t first_len = encode_record(first, seeds[0], eigs, p);
-  std::vector<int> err(threads, 0);
-  {
-    // populate the first page(s) before the poison goes in
+  b->dst = static_cast<unsigned char*>(b->base) + delta;
 #ifdef MADV_POPULATE_WRITE
-    if (madvise(base, (size_t)std::min<uint64_t>(delta + total, (uint64_t)page), MADV_POPULATE_WRITE) != 0 && errno == EFAULT) err[0] = ENOSPC;
+  if (madvise(b->base, (size_t)std::min<uint64_t>(b->map_len, (uint64_t)b->page), MADV_POPULATE_WRITE) != 0 && errno == EFAULT) {
+    jne_dat_batch_end(b, 0);
+    return fail(std::string("write failed: ") + strerror(ENOSPC));
+  }
 #endif
-    if (!err[0]) memset(dst, 0xFF, 5);
-  }
-  if (!err[0]) {
-    std::vector<std::thread> th;
-    try {
-      for (int t = 0; t < threads; ++t) {
-        const uint64_t a = std::min<uint64_t>((uint64_t)t * per, n), b = std::min<uint64_t>(a + per, n);
-        if (a == b) continue;
-        th.emplace_back([&, t, a, b]() {
-          unsigned char* q = dst + off[t];
-#ifdef MADV_POPULATE_WRITE
-          {   // allocate this encoder's pages in one call (whole pages inside its range; edges fault on first touch)
-            const uintptr_t lo = ((uintptr_t)q + page - 1) & ~(uintptr_t)(page - 1), hi = (uintptr_t)(dst + off[t + 1]) & ~(uintptr_t)(page - 1);
-            if (hi > lo && madvise((void*)lo, hi - lo, MADV_POPULATE_WRITE) != 0 && errno == EFAULT) { err[t] = ENOSPC; return; }
-          }
-#endif
-          uint64_t i = a;
-          if (t == 0) { q += first_len; ++i; }          // record 0 goes in last (see above)
-          for (; i < b; ++i) q += encode_record(q, seeds[i], eigs + i * stride, p);
-        });
-      }
-    } catch (...) {
-      for (auto& t : th) t.join();
-      munmap(base, (size_t)(delta + total));
-      if (ftruncate(w->fd, (off_t)w->pos) != 0) { /* nothing more to do */ }
-      return fail("could not start an encoder thread");
-    }
-    for (auto& t : th) t.join();
-  }
-  int bad = 0;
-  for (int e : err) if (e) bad = e;
-  if (!bad) memcpy(dst, first, first_len);              // the batch becomes valid
-  munmap(base, (size_t)(delta + total));
-  if (bad) {
-    if (ftruncate(w->fd, (off_t)w->pos) != 0) { /* keep the first error */ }
-    return fail(std::string("write failed: ") + strerror(bad));
-  }
-  w->pos += total;
-  w->written += n;
+  memset(b->dst, 0xFF, 5);                     // poison: a scan stops here until the batch is committed
+  *out = b;
   return JNE_OK;
+}
+
+int jne_dat_batch_fill(jne_dat_batch* b, uint64_t first, uint64_t count, const double* rows, uint64_t stride, int threads) {
+  if (!b || !rows) return fail("batch / rows is NULL");
+  if (first + count > b->n || stride < b->p) return fail("record range outside the batch");
+  if (count == 0) return JNE_OK;
+  const uint64_t bytes = count * 8 * (uint64_t)b->p;
+  if (threads <= 1 || bytes < ((uint64_t)4 << 20)) { batch_fill_range(b, first, count, rows, stride); }
+  else {
+    if (threads > 16) threads = 16;
+    const uint64_t per = (count + threads - 1) / threads;
+    std::vector<std::thread> th;
+    int started = 1;                               // range 0 is this thread's
+    try {
+      for (; started < threads; ++started) {
+        const uint64_t a = std::min<uint64_t>((uint64_t)started * per, count), e = std::min<uint64_t>(a + per, count);
+        if (a < e) th.emplace_back(batch_fill_range, b, first + a, e - a, rows + a * stride, stride);
+      }
+    } catch (...) { /* ranges started .. threads-1 did not get a helper: filled below */ }
+    batch_fill_range(b, first, std::min<uint64_t>(per, count), rows, stride);
+    const uint64_t a = std::min<uint64_t>((uint64_t)started * per, count);
+    if (started < threads && a < count) batch_fill_range(b, first + a, count - a, rows + a * stride, stride);
+    for (auto& x : th) x.join();
+  }
+  const int e = b->err.load();
+  return e ? fail(std::string("write failed: ") + strerror(e)) : JNE_OK;
+}
+
+int jne_dat_batch_end(jne_dat_batch* b, int commit) {
+  if (!b) return fail("batch is NULL");
+  jne_dat_writer* w = b->w;
+  int rc = JNE_OK;
+  const bool ok = commit && b->err.load() == 0 && b->filled.load() == b->n && b->first_len > 0;
+  if (commit && !ok)
+    rc = fail(b->err.load() ? std::string("write failed: ") + strerror(b->err.load())
+                            : "batch committed with " + std::to_string(b->filled.load()) + " of " + std::to_string(b->n) + " records filled");
+  if (ok) memcpy(b->dst, b->first, b->first_len);       // the batch becomes valid
+  if (b->base && b->base != MAP_FAILED) munmap(b->base, b->map_len);
+  if (ok) { w->pos += b->total; w->written += b->n; }
+  else if (ftruncate(w->fd, (off_t)w->pos) != 0 && rc == JNE_OK && commit) rc = fail(std::string("truncate failed: ") + strerror(errno));
+  delete b;
+  return rc;
+}
+
+int jne_dat_append_batch_strided_mt(jne_dat_writer* w, const uint32_t* seeds, const double* eigs, uint64_t n, uint32_t p,
+                                    uint64_t stride, int threads) {
+  if (threads <= 1 || n < 4096) return jne_dat_append_batch_strided(w, seeds, eigs, n, p, stride);
+  if (stride < p) return fail("stride is smaller than the eigenvalue count");
+  jne_dat_batch* b = nullptr;
+  int rc = jne_dat_batch_begin(w, seeds, n, p, &b);
+  if (rc != JNE_OK) return rc;
+  rc = jne_dat_batch_fill(b, 0, n, eigs, stride, threads);
+  const int rc2 = jne_dat_batch_end(b, rc == JNE_OK);
+  return rc != JNE_OK ? rc : rc2;
 }
 
 int jne_dat_flush(jne_dat_writer* w) {

@@ -53,6 +53,12 @@ lib.jne_run_model_simulation.argtypes = [_vp, C.c_uint8, C.c_uint32, C.c_uint32,
 lib.jne_run_models_simulation.restype = C.c_int
 lib.jne_run_models_simulation.argtypes = [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_char_p), C.c_int,
                                           C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_uint64)]
+lib.jne_dat_batch_begin.restype = C.c_int
+lib.jne_dat_batch_begin.argtypes = [_vp, _vp, C.c_uint64, C.c_uint32, C.POINTER(_vp)]
+lib.jne_dat_batch_fill.restype = C.c_int
+lib.jne_dat_batch_fill.argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, C.c_int]
+lib.jne_dat_batch_end.restype = C.c_int
+lib.jne_dat_batch_end.argtypes = [_vp, C.c_int]
 lib.jne_dat_append_batch_strided_mt.restype = C.c_int
 lib.jne_dat_append_batch_strided_mt.argtypes = [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int]
 lib.jne_dat_append_batch_strided.restype = C.c_int
@@ -114,6 +120,10 @@ class AppendOnlyWriter:
         _check(lib.jne_dat_append_batch_strided_mt(self._w, seeds.ctypes.data, rows.ctypes.data + 8 * offset, seeds.size, p,
                                                    rows.shape[1], int(threads)))
 
+    def batch(self, seeds, p: int) -> "RandomAccessBatch":
+        """Reserve the bytes of ``len(seeds)`` records at the end of the file; fill record ranges in any order."""
+        return RandomAccessBatch(self, seeds, p)
+
     def append_eigenvalues(self, seed: int, eigenvalues) -> None:   # the reference's per-record call
         self.append_batch([seed], np.asarray(eigenvalues, dtype=np.float64)[None, :])
 
@@ -132,6 +142,34 @@ class AppendOnlyWriter:
     def __del__(self):
         try:
             self.abandon()
+        except Exception:
+            pass
+
+
+class RandomAccessBatch:
+    """jne_dat_batch_*: the records of a batch have their place in the file before any is written (sizes follow from
+    the seeds), so several producers fill disjoint ranges in any order; ``end(commit=True)`` makes the batch part of
+    the file, ``end(False)`` truncates it away.  Until then the batch starts with an invalid ULEB128 (crash safety)."""
+
+    def __init__(self, writer: AppendOnlyWriter, seeds, p: int):
+        self._seeds = np.ascontiguousarray(seeds, dtype=np.uint32)     # must outlive the batch
+        self.p = int(p)
+        self._b = _vp()
+        _check(lib.jne_dat_batch_begin(writer._w, self._seeds.ctypes.data, self._seeds.size, self.p, C.byref(self._b)))
+
+    def fill(self, first: int, rows, offset: int = 0, threads: int = 1) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        assert rows.ndim == 2 and offset + self.p <= rows.shape[1]
+        _check(lib.jne_dat_batch_fill(self._b, first, rows.shape[0], rows.ctypes.data + 8 * offset, rows.shape[1], int(threads)))
+
+    def end(self, commit: bool = True) -> None:
+        b, self._b = self._b, _vp()
+        if b:
+            _check(lib.jne_dat_batch_end(b, 1 if commit else 0))
+
+    def __del__(self):
+        try:
+            self.end(False)
         except Exception:
             pass
 

@@ -231,3 +231,46 @@ def test_damaged_finished_file(tmp_path):
     assert w.existing_records == 6
     w.finish()
     assert os.path.getsize(torn) == 18 + 6 * rec + 17 and not (tmp_path / "torn.dat.damaged").exists()
+
+
+def test_random_access_batch(tmp_path):
+    """jne_dat_batch_*: ranges filled out of order by several producers give the bytes of the serial writer; an
+    uncommitted batch is invisible (poisoned head) and is truncated away; a short commit is refused."""
+    rng = np.random.default_rng(5)
+    n, p, width, off = 30000, 13, 62, 12
+    seeds = np.concatenate([np.arange(100, 100 + n // 2), np.arange(5_000_000, 5_000_000 + n - n // 2)]).astype(np.uint32)   # 1-, 2-, 3- and 4-byte ULEB128s
+    seeds[:200] = np.arange(1, 201)
+    rows = rng.standard_normal((n, width))
+    ref = tmp_path / "serial.dat"
+    w = dat.AppendOnlyWriter(ref, 3, 12, 77); w.append_batch([7], np.ones((1, p))); w.append_batch_strided(seeds, rows, off, p); w.finish()
+    f = tmp_path / "ra.dat"
+    w = dat.AppendOnlyWriter(f, 3, 12, 77); w.append_batch([7], np.ones((1, p)))
+    b = w.batch(seeds, p)
+    cuts = [0, 1, 999, 1024, 1025, 7000, 20000, n]
+    order = [3, 0, 6, 2, 5, 1, 4]                      # any order, record 0's range not first
+    import threading
+    th = [threading.Thread(target=lambda k=k: b.fill(cuts[k], rows[cuts[k]:cuts[k + 1]], off, threads=3)) for k in order]
+    # mid-way the file is longer but a scan stops at the poisoned head of the batch: only the record before it is visible
+    for t in th[:3]: t.start()
+    for t in th[:3]: t.join()
+    assert dat.file_info(f)["records"] == 1 and not dat.file_info(f)["has_trailer"]
+    for t in th[3:]: t.start()
+    for t in th[3:]: t.join()
+    b.end(True)
+    w.finish()
+    assert f.read_bytes() == ref.read_bytes()
+    # abort: the file returns to its length before the batch; a batch with a hole cannot be committed
+    g = tmp_path / "abort.dat"
+    w = dat.AppendOnlyWriter(g, 3, 12, 77); w.append_batch([7], np.ones((1, p)))
+    size0 = 18 + 1 + 1 + 8 * p
+    b = w.batch(seeds, p); b.fill(0, rows[:5000], off); b.end(False)
+    assert os.path.getsize(g) == size0
+    b = w.batch(seeds, p); b.fill(0, rows[:5000], off)
+    with pytest.raises(JneError, match="5000 of 30000 records filled"):
+        b.end(True)
+    assert os.path.getsize(g) == size0
+    w.append_batch_strided(seeds, rows, off, p, threads=4)           # the mt append is a batch filled in ranges
+    w.finish()
+    assert g.read_bytes() == ref.read_bytes()
+    with pytest.raises(JneError, match="Eigenvalue count mismatch"):
+        w2 = dat.AppendOnlyWriter(g, 3, 12, 77); w2.batch(seeds, p + 1)

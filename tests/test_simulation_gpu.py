@@ -123,3 +123,34 @@ def test_streaming_percentiles(engine):
     for k in range(1, ev.shape[1]):
         trace += ev[:, k]
     assert np.array_equal(tr, orc.percentiles(trace, [0.5]))
+
+
+def test_streaming_sink_delivers_the_batch(engine):
+    """jne_eigs_batch_multi_stream: the reference's channel model (rows SENT as they finish,
+    src/data_storage/parallel_compute.rs:14-41).  Every seed's row arrives exactly once, bit-identical to the batch
+    call, whatever the chunking; a failing sink aborts the call with an error and leaves the context usable."""
+    import johansen_null_eigenspectra_b200 as jne
+    for dim, T, n in [(12, 64, 20011), (5, 50, 300001), (9, 40, 12345), (2, 30, 7)]:
+        seeds = np.arange(5, 5 + n, dtype=np.uint32)
+        ref = engine.eigs_batch_multi(range(5), dim, T, seeds)
+        width = sum(v.shape[1] for v in ref.values())
+        got = np.full((n, width), np.nan)
+        hits = np.zeros(n, dtype=np.int32)
+
+        def sink(first, rows):
+            got[first:first + rows.shape[0]] = rows
+            hits[first:first + rows.shape[0]] += 1
+
+        engine.eigs_batch_multi_stream(range(5), dim, T, seeds, sink)
+        assert np.all(hits == 1)
+        off = 0
+        for m in range(5):
+            assert np.array_equal(got[:, off:off + ref[m].shape[1]], ref[m]), (dim, m)
+            off += ref[m].shape[1]
+    calls = []
+    with pytest.raises(jne.JneError) as e:
+        engine.eigs_batch_multi_stream([0, 3], 12, 64, np.arange(1, 50001, dtype=np.uint32), lambda first, rows: calls.append(first) or True)
+    assert e.value.status == -5 and len(calls) >= 1
+    with pytest.raises(ZeroDivisionError):
+        engine.eigs_batch_multi_stream([0], 3, 20, np.arange(1, 100, dtype=np.uint32), lambda first, rows: 1 / 0)
+    assert engine.eigs_batch(0, 3, 20, np.arange(1, 100, dtype=np.uint32)).shape == (99, 3)
