@@ -1,6 +1,7 @@
 // run_model_simulation: the reference's orchestration of one (model, dim, steps, num_runs) job
 // (src/data_storage/parallel_compute.rs:150-232) over the GPU hot path and the batched .dat writer.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -26,15 +27,34 @@ struct BatchSink {
 
 int batch_sink(void* user, uint64_t first, uint64_t count, const double* rows) {
   BatchSink* c = static_cast<BatchSink*>(user);
-  for (int m = 0; m < 5; ++m) {
-    if (!((c->mask >> m) & 1u)) continue;
-    if (jne_dat_batch_fill(c->batch[m], first, count, rows + c->off[m], c->width, c->threads) != JNE_OK) {
-      std::lock_guard<std::mutex> lk(c->mu);
-      if (c->err.empty()) c->err = jne_dat_last_error();
-      return 1;
+  int models[5], nm = 0;
+  for (int m = 0; m < 5; ++m) if ((c->mask >> m) & 1u) models[nm++] = m;
+  std::atomic<int> bad{0};
+  auto fill = [&](int t, int T) {           // models t, t + T, ... of the mask
+    for (int k = t; k < nm; k += T) {
+      const int m = models[k];
+      // a fill large enough is split further inside (small dims: tens of MB per file and sub-chunk)
+      if (jne_dat_batch_fill(c->batch[m], first, count, rows + c->off[m], c->width, c->threads) != JNE_OK) {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (c->err.empty()) c->err = jne_dat_last_error();
+        bad.store(1);
+      }
     }
-  }
-  return 0;
+  };
+  // One device thread cannot encode five files' records AND fault in their new pages as fast as its GPU produces rows
+  // (~1 KB of memory traffic per seed, 3.2 M seeds/s at dim 12): the models of a sub-chunk are spread over a few
+  // short-lived helpers.
+  const int T = std::min(nm, (count * c->width * sizeof(double) >= ((size_t)1 << 20)) ? c->threads : 1);
+  if (T <= 1) { fill(0, 1); return bad.load(); }
+  std::thread th[4];
+  int started = 0;
+  try {
+    for (int t = 1; t < T && t <= 4; ++t) { th[t - 1] = std::thread(fill, t, T); ++started; }
+  } catch (...) { /* not started: filled below */ }
+  fill(0, T);
+  for (int t = started + 1; t < T; ++t) fill(t, T);
+  for (int t = 0; t < started; ++t) th[t].join();
+  return bad.load();
 }
 
 }  // namespace
@@ -108,7 +128,7 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
   const int n_dev = std::max(1, jne_ctx_device_count(gpu.ctx()));
   const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
   static const int enc_env = [] { const char* e = getenv("JNE_DAT_ENCODERS"); return e ? atoi(e) : 0; }();
-  const size_t batch_max = (size_t)n_dev << (dim <= 6 ? 21 : 19);   // ~0.15 s of GPU work and more
+  const size_t batch_max = (size_t)n_dev << (dim <= 6 ? 23 : 21);   // 0.1-0.7 s of GPU work: the pipelines drain once per batch
   try {
     for (uint32_t mask = 1; mask < 32; ++mask) {
       const std::vector<uint32_t>& seeds = groups[mask];
@@ -117,7 +137,7 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
       sink.mask = mask;
       sink.width = (uint32_t)jne_multi_width(mask, dim);
       // a sub-chunk of a small dim is tens of MB per file: give the device thread's encoder a few helpers
-      sink.threads = enc_env > 0 ? enc_env : std::max(1, std::min(4, hw / (2 * n_dev)));
+      sink.threads = enc_env > 0 ? std::min(enc_env, 5) : std::max(1, std::min(4, hw / (2 * n_dev)));
       { uint32_t o = 0; for (int m = 0; m < 5; ++m) { sink.pm[m] = (uint32_t)Model((uint8_t)m).num_eigs(dim); sink.off[m] = o; if ((mask >> m) & 1u) o += sink.pm[m]; } }
       for (size_t a = 0; a < seeds.size(); a += batch_max) {
         const size_t nb = std::min(batch_max, seeds.size() - a);

@@ -368,6 +368,12 @@ def _experimental_library():
     path = jbuild.VARIANTS["experimental"][1]
     if not path.exists():
         pytest.skip("libjne_experimental.so not built (build.py --experimental)")
+    import ctypes, re
+    lib = ctypes.CDLL(str(path))
+    header = re.sub(r"/\*.*?\*/", "", (jbuild.PKG_DIR.parent / "include" / "jne.h").read_text(), flags=re.S)
+    missing = [n for n in set(re.findall(r"\b(jne_[a-z0-9_]+)\s*\(", header)) if not hasattr(lib, n)]
+    if missing:
+        pytest.skip(f"libjne_experimental.so is older than include/jne.h (lacks {missing[0]}): rebuild it")
     return str(path)
 
 
