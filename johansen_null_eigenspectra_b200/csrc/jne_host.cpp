@@ -1,6 +1,7 @@
 // run_model_simulation: the reference's orchestration of one (model, dim, steps, num_runs) job
 // (src/data_storage/parallel_compute.rs:150-232) over the GPU hot path and the batched .dat writer.
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -14,6 +15,18 @@
 namespace jne {
 
 namespace {
+
+// JNE_DAT_TIMING=1: phase times of run_models_simulation on stderr (where does a job's wall time go)
+struct PhaseTimer {
+  bool on = [] { const char* e = getenv("JNE_DAT_TIMING"); return e && e[0] == '1'; }();
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[jne_dat timing] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 // The row sink of one batch: every device's host thread hands its rows (pinned staging memory) to this function as
 // they arrive, and the records of every selected model are encoded straight into that model's file.
@@ -73,6 +86,7 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
                            const std::string (&filenames)[5], bool quiet, SimulationStats (&stats)[5]) {
   if (model_mask == 0 || model_mask > 31u) throw Error(JNE_ERR_INVALID_ARG, "model_mask must select models 0..4");
   if (dim > 255) throw Error(JNE_ERR_INVALID_ARG, "dim must fit the u8 header field");
+  PhaseTimer timer;
   // ---- resume scan per file; need[s-1] = models that still lack seed s ----
   std::vector<uint8_t> need(num_runs, 0);
   {
@@ -99,6 +113,7 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
         if (!((bitmap[s >> 3] >> (s & 7)) & 1u)) need[s] |= (uint8_t)(1u << m);
     }
   }
+  timer.lap("resume scan");
   // ---- writers for the files that lack something (a complete file is not touched, parallel_compute.rs:182-198) ----
   jne_dat_writer* w[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t existing[5] = {0, 0, 0, 0, 0};
@@ -120,6 +135,7 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
       if (need[s]) groups[need[s]].push_back((uint32_t)(s + 1));
     std::vector<uint8_t>().swap(need);
   }
+  timer.lap("open + group seeds");
   // ---- one fused pass per distinct set of lacking models, in batches.  A batch reserves its bytes in every file (the
   //      record sizes follow from the seeds), then the GPUs stream their rows to the sink, where the device threads
   //      encode them into the files' pages as they arrive: no intermediate array and no separate writer phase (the
@@ -141,28 +157,56 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
       { uint32_t o = 0; for (int m = 0; m < 5; ++m) { sink.pm[m] = (uint32_t)Model((uint8_t)m).num_eigs(dim); sink.off[m] = o; if ((mask >> m) & 1u) o += sink.pm[m]; } }
       for (size_t a = 0; a < seeds.size(); a += batch_max) {
         const size_t nb = std::min(batch_max, seeds.size() - a);
-        auto end_all = [&](int commit) {
-          int first_rc = JNE_OK; std::string msg;
-          for (int m = 0; m < 5; ++m) {
-            if (!sink.batch[m]) continue;
-            const int rc = jne_dat_batch_end(sink.batch[m], commit);
+        auto end_all = [&](int commit) {            // unmapping ~10^5 populated pages per file takes tens of ms: one thread per file
+          int erc[5] = {0, 0, 0, 0, 0};
+          std::string emsg[5];
+          std::thread th[5];
+          auto end_one = [&](int m) {
+            erc[m] = jne_dat_batch_end(sink.batch[m], commit);
             sink.batch[m] = nullptr;
-            if (rc != JNE_OK && first_rc == JNE_OK) { first_rc = rc; msg = jne_dat_last_error(); }
-          }
-          if (first_rc != JNE_OK) throw Error(first_rc, msg);
+            if (erc[m] != JNE_OK) emsg[m] = jne_dat_last_error();
+          };
+          int last = -1;
+          for (int m = 0; m < 5; ++m) if (sink.batch[m]) last = m;
+          if (last < 0) return;
+          try {
+            for (int m = 0; m < last; ++m) if (sink.batch[m]) th[m] = std::thread(end_one, m);
+          } catch (...) { /* ended below */ }
+          end_one(last);
+          for (int m = 0; m < 5; ++m) if (th[m].joinable()) th[m].join();
+          for (int m = 0; m < 5; ++m) if (sink.batch[m]) end_one(m);     // a thread that never started
+          for (int m = 0; m < 5; ++m) if (erc[m] != JNE_OK) throw Error(erc[m], emsg[m]);
         };
-        for (int m = 0; m < 5; ++m) {
-          if (!((mask >> m) & 1u)) continue;
-          const int rc = jne_dat_batch_begin(w[m], seeds.data() + a, nb, sink.pm[m], &sink.batch[m]);
-          if (rc != JNE_OK) { const std::string msg = jne_dat_last_error(); try { end_all(0); } catch (...) {} throw Error(rc, msg); }
+        {   // reserve the batch in every file (a pass over the seeds per file: one thread each)
+          int brc[5] = {0, 0, 0, 0, 0};
+          std::string bmsg[5];
+          std::thread th[5];
+          auto begin = [&](int m) {
+            brc[m] = jne_dat_batch_begin(w[m], seeds.data() + a, nb, sink.pm[m], &sink.batch[m]);
+            if (brc[m] != JNE_OK) bmsg[m] = jne_dat_last_error();
+          };
+          int last = -1;
+          for (int m = 0; m < 5; ++m) if ((mask >> m) & 1u) last = m;
+          try {
+            for (int m = 0; m < 5; ++m) if (((mask >> m) & 1u) && m != last) th[m] = std::thread(begin, m);
+          } catch (...) { for (auto& t : th) if (t.joinable()) t.join(); try { end_all(0); } catch (...) {} throw; }
+          begin(last);
+          for (int m = 0; m < 5; ++m) if (th[m].joinable()) th[m].join();
+          for (int m = 0; m < 5; ++m) {
+            if (((mask >> m) & 1u) && m != last && sink.batch[m] == nullptr && brc[m] == JNE_OK) begin(m);   // its thread never started
+            if (brc[m] != JNE_OK) { try { end_all(0); } catch (...) {} throw Error(brc[m], bmsg[m]); }
+          }
         }
+        timer.lap("batch begin");
         const int rc = jne_eigs_batch_multi_stream(gpu.ctx(), mask, dim, steps, seeds.data() + a, nb, batch_sink, &sink);
+        timer.lap("stream (GPU + encode)");
         if (rc != JNE_OK) {
           const std::string msg = !sink.err.empty() ? sink.err : std::string(jne_last_error(gpu.ctx()));
           try { end_all(0); } catch (...) {}
           throw Error(sink.err.empty() ? rc : JNE_ERR_IO, msg);
         }
         end_all(1);
+        timer.lap("batch end");
         for (int m = 0; m < 5; ++m) if ((mask >> m) & 1u) stats[m].computed += nb;
         if (!quiet) printf("Simulation progress (models mask 0x%x): %llu/%llu seeds\n", mask,
                            (unsigned long long)(a + nb), (unsigned long long)seeds.size());
@@ -172,6 +216,7 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
     abandon_all();        // trailer-less, resumable files, like an interrupted reference run
     throw;
   }
+  timer.lap("(loop exit)");
   for (int m = 0; m < 5; ++m) {
     if (!w[m]) continue;
     const int rc = jne_dat_finish(w[m]);
