@@ -359,6 +359,7 @@ struct jne_dat_batch {
   uint64_t n = 0, total = 0;
   uint32_t p = 0;
   std::vector<uint64_t> blk;                  // byte offset of record i * kBlk inside the batch
+  bool mapped = false;                         // false: ranges are encoded into a private buffer and pwrite()n in place
   void* base = nullptr;
   size_t map_len = 0;
   unsigned char* dst = nullptr;
@@ -375,23 +376,37 @@ void batch_fill_range(jne_dat_batch* b, uint64_t first, uint64_t count, const do
   uint64_t off = b->blk[first / jne_dat_batch::kBlk];
   for (uint64_t j = (first / jne_dat_batch::kBlk) * jne_dat_batch::kBlk; j < first; ++j)
     off += (uint64_t)jne_uleb128_encoded_size(b->seeds[j]) + 1 + 8 * (uint64_t)p;
-  unsigned char* q = b->dst + off;
+  uint64_t bytes = count * (1 + 8 * (uint64_t)p);
+  for (uint64_t j = first; j < first + count; ++j) bytes += (uint64_t)jne_uleb128_encoded_size(b->seeds[j]);
+  unsigned char* q;
+  thread_local std::vector<unsigned char> scratch;
+  if (b->mapped) {
+    q = b->dst + off;
 #ifdef MADV_POPULATE_WRITE
-  {   // allocate this range's pages in one call (whole pages inside it; the edges fault on first touch).  On tmpfs this
-      // is also what turns a full file system into an error code instead of a SIGBUS.
-    uint64_t bytes = count * (1 + 8 * (uint64_t)p);
-    for (uint64_t j = first; j < first + count; ++j) bytes += (uint64_t)jne_uleb128_encoded_size(b->seeds[j]);
-    const uintptr_t lo = ((uintptr_t)q + b->page - 1) & ~(uintptr_t)(b->page - 1), hi = ((uintptr_t)q + bytes) & ~(uintptr_t)(b->page - 1);
-    if (hi > lo && madvise((void*)lo, hi - lo, MADV_POPULATE_WRITE) != 0 && errno == EFAULT) { b->err.store(ENOSPC); return; }
-  }
+    {   // allocate this range's pages in one call (whole pages inside it; the edges fault on first touch).  On tmpfs this
+        // is also what turns a full file system into an error code instead of a SIGBUS.
+      const uintptr_t lo = ((uintptr_t)q + b->page - 1) & ~(uintptr_t)(b->page - 1), hi = ((uintptr_t)q + bytes) & ~(uintptr_t)(b->page - 1);
+      if (hi > lo && madvise((void*)lo, hi - lo, MADV_POPULATE_WRITE) != 0 && errno == EFAULT) { b->err.store(ENOSPC); return; }
+    }
 #endif
+  } else {
+    try { if (scratch.size() < bytes) scratch.resize(bytes); } catch (...) { b->err.store(ENOMEM); return; }
+    q = scratch.data();
+  }
+  unsigned char* const q0 = q;
   uint64_t i = first;
+  size_t skip = 0;
   if (first == 0 && count > 0) {               // record 0 goes in last (jne_dat_batch_end): the batch stays invalid until then
     b->first_len = encode_record(b->first, b->seeds[0], rows, p);
     q += b->first_len;
+    skip = b->first_len;
     ++i;
   }
   for (; i < first + count; ++i) q += encode_record(q, b->seeds[i], rows + (i - first) * stride, p);
+  if (!b->mapped && bytes > skip && !write_all(b->w->fd, q0 + skip, bytes - skip, b->w->pos + off + skip)) {
+    b->err.store(errno ? errno : EIO);
+    return;
+  }
   b->filled.fetch_add(count);
 }
 }  // namespace
@@ -419,30 +434,45 @@ int jne_dat_batch_begin(jne_dat_writer* w, const uint32_t* seeds, uint64_t n, ui
     off += (uint64_t)jne_uleb128_encoded_size(seeds[i]) + 1 + 8 * (uint64_t)p;
   }
   b->total = off;
-  const uint64_t map_off = w->pos & ~(uint64_t)(b->page - 1), delta = w->pos - map_off;
-  // grow the file; on a disk file system reserve the blocks now so that a full disk is an error code here, not a
-  // SIGBUS in an encoder (on tmpfs MADV_POPULATE_WRITE reports it)
+  // Two ways to put a range's bytes in place (JNE_DAT_MMAP=1 selects the second):
+  //   pwrite (default)  a private buffer per range, then one positioned pwrite() -- on the 8-GPU box write() produces
+  //                     new tmpfs pages at 20 GB/s into five files, a mapping at 12 GB/s, and tearing a mapping down
+  //                     costs another 0.7 us per page (142 ms per 830 MB batch and file), profiles/r2_io_bench_8gpu_box.txt
+  //   mapped pages      MAP_SHARED + MADV_POPULATE_WRITE, encoders write straight into the page cache
+  static const bool want_map = [] { const char* e = getenv("JNE_DAT_MMAP"); return e && e[0] == '1'; }();
+  b->mapped = want_map;
+  // grow the file; on a disk file system reserve the blocks now so that a full disk is an error code here (on tmpfs the
+  // pwrite / MADV_POPULATE_WRITE of the range reports it)
   if (!w->tmpfs) {
     const int e = posix_fallocate(w->fd, (off_t)w->pos, (off_t)b->total);
     if (e != 0 && e != EOPNOTSUPP && e != EINVAL) { delete b; return fail(std::string("cannot reserve file space: ") + strerror(e)); }
   }
   if (ftruncate(w->fd, (off_t)(w->pos + b->total)) != 0) { const int e = errno; delete b; return fail(std::string("cannot grow the file: ") + strerror(e)); }
-  b->map_len = (size_t)(delta + b->total);
-  b->base = mmap(nullptr, b->map_len, PROT_READ | PROT_WRITE, MAP_SHARED, w->fd, (off_t)map_off);
-  if (b->base == MAP_FAILED) {
+  const unsigned char poison[5] = {0xFF, 0xFF, 0xFF, 0xFF, 0xFF};     // a scan stops here until the batch is committed
+  if (b->mapped) {
+    const uint64_t map_off = w->pos & ~(uint64_t)(b->page - 1), delta = w->pos - map_off;
+    b->map_len = (size_t)(delta + b->total);
+    b->base = mmap(nullptr, b->map_len, PROT_READ | PROT_WRITE, MAP_SHARED, w->fd, (off_t)map_off);
+    if (b->base == MAP_FAILED) {
+      const int e = errno;
+      if (ftruncate(w->fd, (off_t)w->pos) != 0) { /* keep the first error */ }
+      delete b;
+      return fail(std::string("cannot map the file: ") + strerror(e));
+    }
+    b->dst = static_cast<unsigned char*>(b->base) + delta;
+#ifdef MADV_POPULATE_WRITE
+    if (madvise(b->base, (size_t)std::min<uint64_t>(b->map_len, (uint64_t)b->page), MADV_POPULATE_WRITE) != 0 && errno == EFAULT) {
+      jne_dat_batch_end(b, 0);
+      return fail(std::string("write failed: ") + strerror(ENOSPC));
+    }
+#endif
+    memcpy(b->dst, poison, 5);
+  } else if (!write_all(w->fd, poison, 5, w->pos)) {
     const int e = errno;
     if (ftruncate(w->fd, (off_t)w->pos) != 0) { /* keep the first error */ }
     delete b;
-    return fail(std::string("cannot map the file: ") + strerror(e));
+    return fail(std::string("write failed: ") + strerror(e));
   }
-  b->dst = static_cast<unsigned char*>(b->base) + delta;
-#ifdef MADV_POPULATE_WRITE
-  if (madvise(b->base, (size_t)std::min<uint64_t>(b->map_len, (uint64_t)b->page), MADV_POPULATE_WRITE) != 0 && errno == EFAULT) {
-    jne_dat_batch_end(b, 0);
-    return fail(std::string("write failed: ") + strerror(ENOSPC));
-  }
-#endif
-  memset(b->dst, 0xFF, 5);                     // poison: a scan stops here until the batch is committed
   *out = b;
   return JNE_OK;
 }
@@ -481,9 +511,13 @@ int jne_dat_batch_end(jne_dat_batch* b, int commit) {
   if (commit && !ok)
     rc = fail(b->err.load() ? std::string("write failed: ") + strerror(b->err.load())
                             : "batch committed with " + std::to_string(b->filled.load()) + " of " + std::to_string(b->n) + " records filled");
-  if (ok) memcpy(b->dst, b->first, b->first_len);       // the batch becomes valid
-  if (b->base && b->base != MAP_FAILED) munmap(b->base, b->map_len);
-  if (ok) { w->pos += b->total; w->written += b->n; }
+  bool ok2 = ok;
+  if (ok) {                                             // the batch becomes valid
+    if (b->mapped) memcpy(b->dst, b->first, b->first_len);
+    else if (!write_all(w->fd, b->first, b->first_len, w->pos)) { ok2 = false; rc = fail(std::string("write failed: ") + strerror(errno)); }
+  }
+  if (b->mapped && b->base && b->base != MAP_FAILED) munmap(b->base, b->map_len);
+  if (ok2) { w->pos += b->total; w->written += b->n; }
   else if (ftruncate(w->fd, (off_t)w->pos) != 0 && rc == JNE_OK && commit) rc = fail(std::string("truncate failed: ") + strerror(errno));
   delete b;
   return rc;
