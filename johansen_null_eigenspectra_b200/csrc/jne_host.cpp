@@ -109,16 +109,40 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
       if (completed >= num_runs) continue;               // parallel_compute.rs:182-188: enough records, whatever their seeds
       if (!quiet && completed)   // a resumed file continues with THIS library's stream (Philox), whoever wrote the head of it
         printf("Resuming %s: %llu of %llu runs present\n", filenames[m].c_str(), (unsigned long long)completed, (unsigned long long)num_runs);
-      for (uint64_t s = 0; s < num_runs; ++s)
-        if (!((bitmap[s >> 3] >> (s & 7)) & 1u)) need[s] |= (uint8_t)(1u << m);
+      // need[s] |= bit for every seed whose bitmap bit is clear, eight seeds per bitmap byte
+      const uint8_t bit = (uint8_t)(1u << m);
+      const uint64_t full = num_runs & ~7ull;
+      for (uint64_t s = 0; s < full; s += 8) {
+        const uint8_t byte = bitmap[s >> 3];
+        if (byte == 0xFF) continue;
+        if (byte == 0) {
+          uint64_t v;
+          std::memcpy(&v, need.data() + s, 8);
+          v |= 0x0101010101010101ull * bit;
+          std::memcpy(need.data() + s, &v, 8);
+        } else {
+          for (int k = 0; k < 8; ++k) if (!((byte >> k) & 1u)) need[s + k] |= bit;
+        }
+      }
+      for (uint64_t s = full; s < num_runs; ++s)
+        if (!((bitmap[s >> 3] >> (s & 7)) & 1u)) need[s] |= bit;
     }
   }
   timer.lap("resume scan");
   // ---- writers for the files that lack something (a complete file is not touched, parallel_compute.rs:182-198) ----
   jne_dat_writer* w[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t existing[5] = {0, 0, 0, 0, 0};
+  // fresh jobs (and most resumes) have ONE set of lacking models for every seed: detect it in words
+  bool uniform = num_runs > 0;
+  {
+    const uint64_t pat = 0x0101010101010101ull * (num_runs ? need[0] : 0);
+    const uint64_t full = num_runs & ~7ull;
+    for (uint64_t s = 0; s < full && uniform; s += 8) { uint64_t v; std::memcpy(&v, need.data() + s, 8); uniform = v == pat; }
+    for (uint64_t s = full; s < num_runs && uniform; ++s) uniform = need[s] == need[0];
+  }
   uint32_t lacking = 0;
-  for (uint64_t s = 0; s < num_runs; ++s) lacking |= need[s];
+  if (uniform) lacking = need[0];
+  else for (uint64_t s = 0; s < num_runs; ++s) lacking |= need[s];
   auto abandon_all = [&]() { for (auto& x : w) if (x) { jne_dat_abandon(x); x = nullptr; } };
   for (int m = 0; m < 5; ++m) {
     if (!((lacking >> m) & 1u)) continue;
@@ -127,7 +151,14 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
   }
   // seeds by the set of models that lack them, one pass (ascending within a group)
   std::vector<uint32_t> groups[32];
-  {
+  if (uniform) {
+    if (need[0]) {
+      std::vector<uint32_t>& g = groups[need[0]];
+      g.resize(num_runs);
+      for (uint64_t s = 0; s < num_runs; ++s) g[s] = (uint32_t)(s + 1);
+    }
+    std::vector<uint8_t>().swap(need);
+  } else {
     uint64_t counts[32] = {0};
     for (uint64_t s = 0; s < num_runs; ++s) ++counts[need[s]];
     for (uint32_t mask = 1; mask < 32; ++mask) groups[mask].reserve(counts[mask]);
