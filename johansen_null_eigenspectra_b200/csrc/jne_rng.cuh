@@ -54,7 +54,11 @@ __device__ __forceinline__ jne_u4 jne_philox4x32_10(uint32_t c0, uint32_t c1, ui
 
 // Same function with the round keys of word 0 precomputed (key0[r] = seed + r * W0); the round keys of
 // word 1 are compile-time constants.  Lets the per-run key schedule live in registers across the time loop.
+#ifdef JNE_EXP_XOSHIRO
+struct jne_keys { mutable uint32_t k[10]; };   // experiment: words 2..5 are a sequential generator's state
+#else
 struct jne_keys { uint32_t k[10]; };
+#endif
 // `stage` is 10 words of the warp's shared memory: the round trip through memory stops ptxas from
 // rematerialising "seed + r*W0" inside the time loop (it re-added all nine keys on every call).
 __device__ __forceinline__ jne_keys jne_make_keys(uint32_t seed, volatile uint32_t* stage) {
@@ -67,7 +71,33 @@ __device__ __forceinline__ jne_keys jne_make_keys(uint32_t seed, volatile uint32
   __syncwarp();
   return ks;
 }
+#ifdef JNE_EXP_THREEFRY   // experiment only (= number of rounds): Threefry4x32 (Random123) in place of Philox4x32-10
+__device__ __forceinline__ jne_u4 jne_threefry4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                   uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3) {
+  constexpr int R[8][2] = {{10, 26}, {11, 21}, {13, 27}, {23, 5}, {6, 20}, {17, 11}, {25, 10}, {18, 20}};
+  const uint32_t ks[5] = {k0, k1, k2, k3, 0x1BD11BDAu ^ k0 ^ k1 ^ k2 ^ k3};
+  uint32_t X0 = c0 + ks[0], X1 = c1 + ks[1], X2 = c2 + ks[2], X3 = c3 + ks[3];
+#pragma unroll
+  for (int r = 0; r < JNE_EXP_THREEFRY; ++r) {
+    if ((r & 1) == 0) {
+      X0 += X1; X1 = __funnelshift_l(X1, X1, R[r & 7][0]) ^ X0;
+      X2 += X3; X3 = __funnelshift_l(X3, X3, R[r & 7][1]) ^ X2;
+    } else {
+      X0 += X3; X3 = __funnelshift_l(X3, X3, R[r & 7][0]) ^ X0;
+      X2 += X1; X1 = __funnelshift_l(X1, X1, R[r & 7][1]) ^ X2;
+    }
+    if ((r & 3) == 3) {
+      const int s = (r + 1) >> 2;
+      X0 += ks[s % 5]; X1 += ks[(s + 1) % 5]; X2 += ks[(s + 2) % 5]; X3 += ks[(s + 3) % 5] + (uint32_t)s;
+    }
+  }
+  return jne_u4{X0, X1, X2, X3};
+}
+#endif
 __device__ __forceinline__ jne_u4 jne_philox4x32_10_keyed(uint32_t c0, uint32_t c1, const jne_keys& ks, uint32_t c2 = 0u) {
+#ifdef JNE_EXP_THREEFRY
+  return jne_threefry4x32(c0, c1, c2, 0u, ks.k[0], JNE_KEY1, 0u, 0u);
+#endif
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W1 = 0xBB67AE85u;
   uint32_t c3 = 0u;
 #pragma unroll
@@ -144,6 +174,22 @@ __device__ __forceinline__ void jne_normals4_keyed(const jne_keys& ks, uint32_t 
 #ifdef JNE_EXP_NORNG   // experiment only: no Philox / Box-Muller (NOT a valid stream)
   z[0] = scale * 0.5f; z[1] = -scale * (float)(row + 1) * 0.25f; z[2] = scale * 0.125f * (tb & 3); z[3] = -scale;
   return;
+#endif
+#ifdef JNE_EXP_XOSHIRO   // experiment only: xoshiro128++ advanced per call, (row, tb) ignored (NOT a valid stream): the
+  {                      // cost ceiling of a sequential generator seeded once per run, row and segment
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t &s0 = ks.k[2], &s1 = ks.k[3], &s2 = ks.k[4], &s3 = ks.k[5];
+      const uint32_t a = s0 + s3;
+      w[i] = __funnelshift_l(a, a, 7) + s0;
+      const uint32_t t = s1 << 9;
+      s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3; s2 ^= t; s3 = __funnelshift_l(s3, s3, 11);
+    }
+    jne_box_muller(w[0], w[1], z[0], z[1], scale);
+    jne_box_muller(w[2], w[3], z[2], z[3], scale);
+    return;
+  }
 #endif
 #ifdef JNE_EXP_NOBM    // experiment only: Philox but no Box-Muller
   { const jne_u4 w = jne_philox4x32_10_keyed(tb, row, ks);

@@ -12,6 +12,9 @@ VARIANTS = {
     "philox7": ["-DJNE_PHILOX_ROUNDS=7"],          # Random123's smallest Crush-resistant round count (default 10)
     "nobm": ["-DJNE_EXP_NOBM"],                    # Philox only, no normal transform (NOT a valid stream)
     "norng": ["-DJNE_EXP_NORNG"],                  # no generator at all (NOT a valid stream)
+    "threefry20": ["-DJNE_EXP_THREEFRY=20"],       # Threefry4x32-20 (Random123 default rounds) in place of Philox4x32-10: ARX, no wide multiplies
+    "threefry12": ["-DJNE_EXP_THREEFRY=12"],       # Threefry4x32-12 (smallest Crush-resistant count per the Random123 paper)
+    "xoshiro": ["-DJNE_EXP_XOSHIRO"],              # sequential xoshiro128++ per lane, counters ignored (NOT a valid stream): ceiling of a sequential generator
     "group78": ["-DJNE_EXP_GROUP_78"],             # dims 7, 8 on the group kernel (2 lanes x 4 rows), dim 10 as 5 x 2
     "lane_nopipe": ["-DJNE_LANE_PIPELINE=0"],      # lane family without the software pipeline (generate a block, then consume it)
     "lane_nopipe_minb3": ["-DJNE_LANE_PIPELINE=0", "-DJNE_LANE_MINB5=3"],   # ... and dim 5 at 168 registers / 3 CTAs per SM
