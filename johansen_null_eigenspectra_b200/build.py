@@ -11,7 +11,6 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libjne.so"
 SOURCES = [CSRC / "jne_api.cu", CSRC / "jne_dat.cpp", CSRC / "jne_host.cpp"]
 HEADERS = [CSRC / "jne_kernels.cuh", CSRC / "jne_kernels_lane.cuh", CSRC / "jne_rng.cuh", CSRC / "jne_host.hpp",
-           CSRC / "experimental" / "jne_kernels_v2.cuh", CSRC / "experimental" / "jne_kernels_ws.cuh",
            PKG_DIR.parent / "include" / "jne.h", PKG_DIR.parent / "include" / "jne_dat.h"]
 
 NVCC_FLAGS = [
@@ -39,8 +38,7 @@ def build_library(force: bool = False, verbose: bool = False, defines=(), out: P
     """Compile csrc/*.cu|cpp -> libjne.so next to this file.
 
     `defines` / `out` build a VARIANT library beside it (never loaded by default; select it with the JNE_LIBRARY
-    environment variable): e.g. defines=("JNE_EXPERIMENTAL_FAMILIES",) adds the measured-slower kernel families of
-    csrc/experimental/ behind JNE_KERNEL=v2|ws, defines=("JNE_RNG_F64",) the validation stream of jne_rng.cuh."""
+    environment variable): e.g. defines=("JNE_RNG_F64",) the validation stream of jne_rng.cuh."""
     target = Path(out) if out is not None else LIB_PATH
     if out is None and not force and not is_stale():
         return LIB_PATH
@@ -58,7 +56,6 @@ def build_library(force: bool = False, verbose: bool = False, defines=(), out: P
 
 VARIANTS = {
     # name -> (defines, file): built on request only (tools/, the family regression tests)
-    "experimental": (("JNE_EXPERIMENTAL_FAMILIES",), PKG_DIR / "libjne_experimental.so"),
     "rng_f64": (("JNE_RNG_F64",), PKG_DIR / "libjne_rng_f64.so"),
 }
 

@@ -18,10 +18,6 @@
 #include "../../include/jne.h"
 #include "jne_kernels.cuh"
 #include "jne_kernels_lane.cuh"
-#ifdef JNE_EXPERIMENTAL_FAMILIES   // measured-slower formulations kept for regression experiments (build.py --experimental)
-#include "experimental/jne_kernels_v2.cuh"
-#include "experimental/jne_kernels_ws.cuh"
-#endif
 
 #define JNE_VERSION_STR "jne-b200 0.1.0 (sm_100a)"
 
@@ -72,9 +68,6 @@ struct Device {
 struct jne_ctx {
   bool use_aux = true;        // trend moments through the MMA for dim <= 6 and 9..12 (env JNE_AUX=0: scalar FP64 sums)
   std::mutex aux_mu;
-  int kernel_family = 1;   // 1: production dispatch (lane family for dim <= 6, tensor family above);
-                           // experimental builds only (JNE_EXPERIMENTAL_FAMILIES): 2 = FMA-tiled path for 9 <= dim <= 12
-                           // (env JNE_KERNEL=v2), 3 = producer / consumer warps for dim <= 12 (env JNE_KERNEL=ws)
   bool use_lane = true;    // env JNE_LANE=0: tensor family for every dim (regression tooling)
   bool use_group = true;   // env JNE_GROUP=0: dims 9, 10 on the tensor family (regression tooling)
   bool lane_thread_solve = true;   // env JNE_LANE_SOLVE=warp: the lane family's moments through the warp-per-run epilogue
@@ -146,8 +139,16 @@ void segment_weights(uint64_t a, uint64_t b, uint64_t T, double* w1, double* w2)
 //   m = 2: w2_i        m = 3: w1_i
 // Integer-valued, evaluated in 128-bit integers and rounded once; steps outside the segment carry 0.
 constexpr uint32_t kAuxMaxSteps = 1u << 22;   // 128 MiB of table; longer runs use the scalar-sum kernels
+// Length of the four time segments of the tensor family: whole generator epochs (jne_rng.cuh), so that the lanes of a
+// warp -- one segment each -- start new substreams in the same block of the time loop.
+uint32_t seg_len_for(uint32_t steps) {
+#ifdef JNE_EXP_SEGLEN8   // experiment only: segments of whole 8-step blocks (misaligned epochs: NOT a valid stream)
+  return 8u * ((steps + 31u) / 32u);
+#endif
+  return (uint32_t)(JNE_EPOCH_STEPS * (((uint64_t)steps + 4u * JNE_EPOCH_STEPS - 1u) / (4u * JNE_EPOCH_STEPS)));
+}
 std::vector<double> make_aux_table(uint32_t steps) {
-  const uint32_t seg_len = 8u * ((steps + 31u) / 32u);
+  const uint32_t seg_len = seg_len_for(steps);
   std::vector<double> tab((size_t)seg_len * 16, 0.0);
   const __int128 T = steps;
   for (int k = 0; k < 4; ++k) {
@@ -217,7 +218,7 @@ JneRunParams make_params_mask(uint32_t mask, uint32_t dim, uint32_t steps, bool 
   p.model = 0;
   for (int m = 0; m < 5; ++m) if ((mask >> m) & 1u) p.model = m;   // highest selected model
   p.p = p.out_stride;   // doubles per run (== eigenvalues per run for a single model)
-  p.seg_len = 8u * ((steps + 31u) / 32u);
+  p.seg_len = seg_len_for(steps);
   p.T = (double)steps;
   p.factor = from_increments ? (double)steps : 1.0;
   uint64_t full = p.seg_len / 8;
@@ -271,32 +272,6 @@ cudaError_t launch_det(int det, const uint32_t* s, const double* b, uint64_t n, 
   }
 }
 
-#ifdef JNE_EXPERIMENTAL_FAMILIES
-// warp-specialised persistent kernel (jne_kernels_ws.cuh): one CTA per SM, RNG path, dim <= 12
-template <int DP, int DET, bool MULTI>
-cudaError_t launch_ws_one(const Device& dv, const uint32_t* d_seeds, uint64_t n, const JneRunParams& prm, double* d_out,
-                          unsigned int* d_err, cudaStream_t st) {
-  using W = JneWs<DP, MULTI>;
-  auto kern = jne_run_kernel_ws<DP, DET, MULTI>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::CTA_SMEM);
-  if (e != cudaSuccess) return e;
-  const uint64_t ctas = std::min<uint64_t>((uint64_t)dv.sm_count, (n + JNE_WS_CONS - 1) / JNE_WS_CONS);
-  kern<<<(unsigned)ctas, 32 * (JNE_WS_CONS + JNE_WS_PROD), W::CTA_SMEM, st>>>(d_seeds, n, prm, d_out, d_err);
-  return cudaGetLastError();
-}
-template <int DP>
-cudaError_t launch_ws(const Device& dv, const uint32_t* s, uint64_t n, const JneRunParams& prm, double* o, unsigned int* e,
-                      cudaStream_t st) {
-  if (prm.model_mask & (prm.model_mask - 1u)) return launch_ws_one<DP, 2, true>(dv, s, n, prm, o, e, st);
-  const int det = (prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2);
-  switch (det) {
-    case 0: return launch_ws_one<DP, 0, false>(dv, s, n, prm, o, e, st);
-    case 1: return launch_ws_one<DP, 1, false>(dv, s, n, prm, o, e, st);
-    default: return launch_ws_one<DP, 2, false>(dv, s, n, prm, o, e, st);
-  }
-}
-
-#endif  // JNE_EXPERIMENTAL_FAMILIES
 
 // Runs in one full wave of the kernel launch_run would pick for prm (resident CTAs per SM x SMs x runs per CTA):
 // the host-buffer path sizes its chunks in whole waves so that a chunk does not end on a mostly empty wave.
@@ -324,7 +299,7 @@ uint64_t wave_runs(const jne_ctx* ctx, const Device& dv, const JneRunParams& prm
 // The AUX kernels serve dim <= 4 and 9..12 (the MMA tile layouts with four F rows and four dB rows in one group) and
 // dim 5, 6 (two padding rows in the 8-row F group) when a selected model has a trend row and the weight table fits.
 bool aux_wanted(const jne_ctx* ctx, const JneRunParams& prm) {
-  return ctx->use_aux && ctx->kernel_family == 1 && prm.model >= 2 && prm.steps <= kAuxMaxSteps &&
+  return ctx->use_aux && prm.model >= 2 && prm.steps <= kAuxMaxSteps &&
          (prm.dim <= 6 || (prm.dim >= 9 && prm.dim <= 12));
 }
 // Device copy of make_aux_table(steps), built on first use; nullptr when it cannot be had (callers fall back).
@@ -364,7 +339,7 @@ bool group_dim(uint32_t dim) { return dim >= 7 && dim <= 10; }
 bool group_dim(uint32_t dim) { return dim == 9; }
 #endif
 bool lane_wanted(const jne_ctx* ctx, const JneRunParams& prm) {
-  return ctx->use_lane && ctx->kernel_family == 1 && (prm.dim <= JNE_LANE_MAX_DIM || (ctx->use_group && group_dim(prm.dim)));
+  return ctx->use_lane && (prm.dim <= JNE_LANE_MAX_DIM || (ctx->use_group && group_dim(prm.dim)));
 }
 int lane_det(const JneRunParams& prm) {
   const bool multi = (prm.model_mask & (prm.model_mask - 1u)) != 0;
@@ -526,67 +501,10 @@ cudaError_t launch_lane(jne_ctx* ctx, Device& dv, const uint32_t* s, const doubl
   return cudaSuccess;
 }
 
-#ifdef JNE_EXPERIMENTAL_FAMILIES
-template <int DET, bool RNG>
-cudaError_t launch_v2_det(const uint32_t* s, const double* b, uint64_t m, const JneRunParams& prm, double* mom, cudaStream_t st) {
-  constexpr unsigned runs_per_cta = 8 * JNE_V2_WARPS;
-  const unsigned grid = (unsigned)((m + runs_per_cta - 1) / runs_per_cta);
-  jne_moments12_kernel<DET, RNG><<<grid, 32 * JNE_V2_WARPS, 0, st>>>(s, b, m, prm, mom);
-  return cudaGetLastError();
-}
-
-// v2 (9 <= dim <= 12): moments kernel + solve kernel per chunk of runs, both on stream st
-template <bool RNG>
-cudaError_t launch_v2(jne_ctx* ctx, Device& dv, const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm,
-                      double* o, unsigned int* e, double* dbg, cudaStream_t st, int ms) {
-  const size_t need = (size_t)std::min<uint64_t>(n, kMomChunk) * JNE_MOM_DOUBLES;
-  if (dv.mom_doubles[ms] < need) {
-    if (dv.d_mom[ms]) { cudaError_t f = cudaFree(dv.d_mom[ms]); dv.d_mom[ms] = nullptr; dv.mom_doubles[ms] = 0; if (f != cudaSuccess) return f; }
-    cudaError_t a = cudaMalloc(&dv.d_mom[ms], need * sizeof(double));
-    if (a != cudaSuccess) return a;
-    dv.mom_doubles[ms] = need;
-  }
-  double* d_mom = dv.d_mom[ms];
-  const bool multi = (prm.model_mask & (prm.model_mask - 1u)) != 0;
-  const int det = multi ? 2 : ((prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2));
-  cudaError_t rc = cudaFuncSetAttribute(jne_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jne_solve_smem<true>());
-  if (rc != cudaSuccess) return rc;
-  rc = cudaFuncSetAttribute(jne_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jne_solve_smem<false>());
-  if (rc != cudaSuccess) return rc;
-  for (uint64_t off = 0; off < n; off += kMomChunk) {
-    const uint64_t m = std::min(kMomChunk, n - off);
-    const uint32_t* sp = s ? s + off : nullptr;
-    const double* bp = b ? b + off * (uint64_t)prm.dim * prm.steps : nullptr;
-    switch (det) {
-      case 0: rc = launch_v2_det<0, RNG>(sp, bp, m, prm, d_mom, st); break;
-      case 1: rc = launch_v2_det<1, RNG>(sp, bp, m, prm, d_mom, st); break;
-      default: rc = launch_v2_det<2, RNG>(sp, bp, m, prm, d_mom, st); break;
-    }
-    if (rc != cudaSuccess) return rc;
-    const unsigned grid = (unsigned)((m + JNE_WARPS_PER_CTA - 1) / JNE_WARPS_PER_CTA);
-    double* op = o + off * prm.out_stride;
-    double* dp = dbg ? dbg + off * 512 : nullptr;
-    if (multi) jne_solve_kernel<true><<<grid, 32 * JNE_WARPS_PER_CTA, jne_solve_smem<true>(), st>>>(d_mom, m, prm, op, e, dp);
-    else jne_solve_kernel<false><<<grid, 32 * JNE_WARPS_PER_CTA, jne_solve_smem<false>(), st>>>(d_mom, m, prm, op, e, dp);
-    rc = cudaGetLastError();
-    if (rc != cudaSuccess) return rc;
-    ctx->launches.fetch_add(1);   // the solve kernel; the caller counts the moments kernel
-  }
-  return cudaSuccess;
-}
-#endif  // JNE_EXPERIMENTAL_FAMILIES
 
 template <bool RNG>
 cudaError_t launch_run(jne_ctx* ctx, Device& dv, const uint32_t* s, const double* b, uint64_t n, const JneRunParams& prm,
                        double* o, unsigned int* e, double* dbg, cudaStream_t st, int mom_slot = 0) {
-#ifdef JNE_EXPERIMENTAL_FAMILIES
-  if (ctx->kernel_family == 2 && prm.dim >= 9 && prm.dim <= 12) return launch_v2<RNG>(ctx, dv, s, b, n, prm, o, e, dbg, st, mom_slot);
-  if (RNG && ctx->kernel_family == 3 && prm.dim <= 12 && dbg == nullptr) {
-    if (prm.dim <= 4) return launch_ws<4>(dv, s, n, prm, o, e, st);
-    if (prm.dim <= 8) return launch_ws<8>(dv, s, n, prm, o, e, st);
-    return launch_ws<12>(dv, s, n, prm, o, e, st);
-  }
-#endif
   if (lane_wanted(ctx, prm)) return launch_lane<RNG>(ctx, dv, s, b, n, prm, o, e, dbg, st, mom_slot);
   const int det = (prm.model <= 1) ? 0 : (prm.model <= 3 ? 1 : 2);
   JneRunParams q = prm;
@@ -598,7 +516,6 @@ cudaError_t launch_run(jne_ctx* ctx, Device& dv, const uint32_t* s, const double
 }
 
 uint64_t wave_runs(const jne_ctx* ctx, const Device& dv, const JneRunParams& prm) {
-  if (ctx->kernel_family != 1) return 0;     // the experimental families have their own geometry: keep the fixed chunk
   if (lane_wanted(ctx, prm)) return lane_wave(dv, prm);
   const bool aux = aux_wanted(ctx, prm);
   uint64_t w = prm.dim <= 4 ? wave_det<4>(dv, prm, aux) : prm.dim <= 8 ? wave_det<8>(dv, prm, aux)
@@ -898,7 +815,7 @@ int jne_jacobi_table(uint32_t ne, uint32_t* words, uint32_t capacity) {
 
 int64_t jne_trend_weight_table(uint32_t steps, double* table, uint64_t capacity) {
   if (steps < 1 || steps > kAuxMaxSteps) return JNE_ERR_INVALID_ARG;
-  const uint64_t n = (uint64_t)(8u * ((steps + 31u) / 32u)) * 16u;
+  const uint64_t n = (uint64_t)seg_len_for(steps) * 16u;
   if (n <= capacity) {
     if (!table) return JNE_ERR_INVALID_ARG;
     const std::vector<double> tab = make_aux_table(steps);
@@ -948,9 +865,6 @@ int jne_init(const int* device_ids, int n_devices, jne_ctx** out) {
   if (n_devices == 0) n_devices = visible;
   jne_ctx* ctx = new (std::nothrow) jne_ctx();
   if (!ctx) return fail(nullptr, JNE_ERR_INTERNAL, "out of host memory");
-#ifdef JNE_EXPERIMENTAL_FAMILIES
-  if (const char* kf = std::getenv("JNE_KERNEL")) ctx->kernel_family = (std::strcmp(kf, "v2") == 0) ? 2 : (std::strcmp(kf, "ws") == 0) ? 3 : 1;
-#endif
   if (const char* ln = std::getenv("JNE_LANE")) ctx->use_lane = std::strcmp(ln, "0") != 0;
   if (const char* gr = std::getenv("JNE_GROUP")) ctx->use_group = std::strcmp(gr, "0") != 0;
   if (const char* ls = std::getenv("JNE_LANE_SOLVE")) ctx->lane_thread_solve = std::strcmp(ls, "warp") != 0;

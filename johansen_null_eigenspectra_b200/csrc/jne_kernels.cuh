@@ -568,18 +568,45 @@ __device__ __forceinline__ bool jne_warp_models(double* __restrict__ wsm, const 
 // block's increments (Philox + Box-Muller, or global loads), jne_consume8 feeds them to the MMAs.  Both
 // are branch-free.
 //
-// RNG balance: a Philox call yields 4 steps of one row, and a lane owns DP/8 rows (0.5, 1, 1.5 or 2).  With
-// 1.5 rows (DP = 12) lanes g >= 4 would idle through the second row's call, so the calls are spread over
+// RNG balance: a generator call yields 4 steps of one row, and a lane owns DP/8 rows (0.5, 1, 1.5 or 2).  With
+// 1.5 rows (DP = 12) lanes g >= 4 would idle through the second row's calls, so the calls are spread over
 // all lanes instead: per 8 steps every lane generates its row g twice (steps 0-3, 4-7) and ONE block of a
 // row 8 + (g & 3) -- lanes g < 4 for steps 0-3, lanes g >= 4 for steps 4-7 -- and the upper lanes hand
 // theirs to lane g - 4 with four FP32 shuffles: 3 calls per lane instead of 4.  DP = 4 likewise: 1 instead of 2.
-// The value of element (row, step) is unchanged: it depends on (seed, row, step) only.
+// This is what the two substreams per row and epoch (jne_rng.cuh: the halves, by parity of the four-step block) are
+// for: the two lanes that share a row each advance their own generator.  The value of element (row, step) is
+// unchanged: it depends on (seed, row, step) only.
 // ---------------------------------------------------------------------------------------------
+// Generator state of a lane: both halves of the rows it owns whole (state 2 j + h), one half of the shared row slot
+// (DP = 4, 12; the last state).  Registers: keeping the states in the warp's loop-idle shared memory instead (one
+// LDS.128 / STS.128 pair per call) measured 1 % slower (profiles/r2_variants_generators.txt).
+#ifdef JNE_EXP_NORESEED   // experiment only: substreams keyed once per run and segment (NOT a valid stream)
+#define JNE_EPOCH_MASK 0xFFFFFFFFu
+#else
+#define JNE_EPOCH_MASK (JNE_EPOCH_STEPS - 1u)
+#endif
+template <int DP> struct JneGen {
+  using G = JneGeo<DP>;
+  static constexpr int NOWN = (G::B == 0) ? G::NRT : G::NRT - 1;
+  static constexpr int NST = 2 * NOWN + (G::B != 0 ? 1 : 0);
+  jne_sub st[NST];
+};
+// Start of an epoch (every JNE_EPOCH_STEPS steps of the lane's segment, warp-uniform): new substream keys.
+template <int DP>
+__device__ __forceinline__ void jne_gen_seed(JneGen<DP>& gs, uint32_t seed, uint32_t epoch, int g) {
+  using G = JneGeo<DP>;
+#pragma unroll
+  for (int j = 0; j < JneGen<DP>::NOWN; ++j) {
+    jne_sub_seed(gs.st[2 * j], seed, 8 * j + g, epoch, 0u);
+    jne_sub_seed(gs.st[2 * j + 1], seed, 8 * j + g, epoch, 1u);
+  }
+  if (G::B != 0) jne_sub_seed(gs.st[JneGen<DP>::NST - 1], seed, 8 * (G::NRT - 1) + (g & 3), epoch, (uint32_t)(g >> 2));
+}
 template <int DP, bool SRC_RNG> struct JneZ { using type = jne_zt; };
 template <int DP> struct JneZ<DP, false> { using type = double; };
 
 template <int DP, bool SRC_RNG>
-__device__ __forceinline__ void jne_gen8(uint32_t t, uint32_t t_end, uint32_t d, int g, const jne_keys& keys,
+__device__ __forceinline__ void jne_gen8(uint32_t t, uint32_t t_end, uint32_t d, int g, JneGen<DP>& gs,
                                          const float (&rowscale)[JneGeo<DP>::NRT], float xscale,
                                          const double* __restrict__ dBrun,
                                          typename JneZ<DP, SRC_RNG>::type (&z)[JneGeo<DP>::NRT][8]) {
@@ -593,19 +620,19 @@ __device__ __forceinline__ void jne_gen8(uint32_t t, uint32_t t_end, uint32_t d,
     }
   } else if constexpr (G::B == 0) {           // DP = 8, 16: every lane owns whole rows
 #pragma unroll
-    for (int j = 0; j < G::NRT; ++j) {
-      jne_normals4_keyed(keys, 8 * j + g, t >> 2, &z[j][0], rowscale[j]);
-      jne_normals4_keyed(keys, 8 * j + g, (t >> 2) + 1, &z[j][4], rowscale[j]);
+    for (int j = 0; j < G::NRT; ++j) {     // t is a multiple of 8: steps 0-3 are an even block (half 0), 4-7 an odd one
+      jne_sub_normals4(gs.st[2 * j], &z[j][0], rowscale[j]);
+      jne_sub_normals4(gs.st[2 * j + 1], &z[j][4], rowscale[j]);
     }
   } else {                                    // DP = 4, 12: the last row slot is shared by lanes g and g ^ 4
     constexpr int L = G::NRT - 1;             // the shared slot
 #pragma unroll
     for (int j = 0; j < L; ++j) {
-      jne_normals4_keyed(keys, 8 * j + g, t >> 2, &z[j][0], rowscale[j]);
-      jne_normals4_keyed(keys, 8 * j + g, (t >> 2) + 1, &z[j][4], rowscale[j]);
+      jne_sub_normals4(gs.st[2 * j], &z[j][0], rowscale[j]);
+      jne_sub_normals4(gs.st[2 * j + 1], &z[j][4], rowscale[j]);
     }
     jne_zt x[4];
-    jne_normals4_keyed(keys, 8 * L + (g & 3), (t >> 2) + (g >> 2), x, xscale);
+    jne_sub_normals4(gs.st[2 * L], x, xscale);     // row 8 L + (g & 3), block (t >> 2) + (g >> 2)
     // Lanes g >= 4 own no row in this slot: what they accumulate there (a path nobody reads: their operand in
     // the mixed group is the received increment or the trend weight, and rows >= DP of the dump are ignored) is
     // left unmasked -- zeroing it cost two FSEL per step after the widening.
@@ -849,7 +876,8 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   const uint32_t d = prm.dim, T = prm.steps;
   const uint32_t t_begin = min((uint32_t)k * prm.seg_len, T);
   const uint32_t t_end = min(T, t_begin + prm.seg_len);
-  const jne_keys keys = jne_make_keys(SRC_RNG ? seeds[run] : 0u, reinterpret_cast<volatile uint32_t*>(wsm));
+  const uint32_t seed = SRC_RNG ? seeds[run] : 0u;
+  JneGen<DP> gs;
   const double* dBrun = SRC_RNG ? nullptr : dB + run * (uint64_t)d * T;
   float rowscale[G::NRT];
 #pragma unroll
@@ -875,13 +903,17 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   // (DP = 8: lane g = 6 reads weight 3 = w1, lane g = 7 weight 2 = w2)
   const int aux_m = (G::B == 4) ? (g & 3) : (g == 7 ? 2 : 3);
   const double* aux = AUX ? prm.aux_tab + ((aux_m << 2) | k) : nullptr;
+  // segments are whole epochs long (JneRunParams::seg_len), so every lane of the warp enters a new epoch in the
+  // same block; the lanes of an empty segment (t_begin = T) compute an epoch nobody reads
   for (; t < t_full; t += 8) {
-    jne_gen8<DP, SRC_RNG>(t, t_end, d, g, keys, rowscale, xscale, dBrun, z);
+    if (SRC_RNG && ((t - t_begin) & JNE_EPOCH_MASK) == 0u) jne_gen_seed<DP>(gs, seed, t / JNE_EPOCH_STEPS, g);
+    jne_gen8<DP, SRC_RNG>(t, t_end, d, g, gs, rowscale, xscale, dBrun, z);
     jne_consume8<DP, DET, SRC_RNG, false, AUX>(t, t_end, g, src_lane, z, L, w2c, aux);
     if (AUX) aux += 128;
   }
   for (; t < t_stop; t += 8) {
-    jne_gen8<DP, SRC_RNG>(t, t_end, d, g, keys, rowscale, xscale, dBrun, z);
+    if (SRC_RNG && ((t - t_begin) & JNE_EPOCH_MASK) == 0u) jne_gen_seed<DP>(gs, seed, t / JNE_EPOCH_STEPS, g);
+    jne_gen8<DP, SRC_RNG>(t, t_end, d, g, gs, rowscale, xscale, dBrun, z);
     jne_consume8<DP, DET, SRC_RNG, true, AUX>(t, t_end, g, src_lane, z, L, w2c, aux);
     if (AUX) aux += 128;
   }

@@ -23,21 +23,29 @@
 //                                                                                  src/johansen_statistics.rs:35-46
 // The random stream is the same function of (seed, row, step) as everywhere else.
 #pragma once
+#include <type_traits>
 #include "jne_kernels.cuh"
 
 #define JNE_LANE_MAX_DIM 6
 // Launch geometry: 128 threads per CTA (one warp per SM sub-partition) and the resident CTAs per SM the register
 // budget is sized for.  Registers are allocated per sub-partition (16 384 each): 6 / 5 / 4 / 3 / 2 resident warps
-// leave 85 / 102 / 128 / 168 / 255 registers per thread.
+// leave 85 / 102 / 128 / 168 / 255 registers per thread.  A run carries 8 D registers of generator state (two
+// substreams per row, jne_rng.cuh) next to its moments.
 #ifndef JNE_LANE_MINB5
 #define JNE_LANE_MINB5 2      // dim 5: 255 registers, 2 resident CTAs per SM; 3 = 168 registers (measured equal without
 #endif                        // the software pipeline, whose second block of normals needs the room)
 #ifndef JNE_LANE_PIPELINE
 #define JNE_LANE_PIPELINE 1   // 0: generate a block, then consume it (regression / ablation)
 #endif
+#ifndef JNE_LANE_MINB3
+#define JNE_LANE_MINB3 4      // dim 3: 128 registers (5 CTAs = 102 registers spill the substream states: 27.3 -> 31.0 M seeds/s)
+#endif
+#ifndef JNE_LANE_MINB4
+#define JNE_LANE_MINB4 3      // dim 4: 168 registers (17.9 -> 19.6 M seeds/s)
+#endif
 template <int D> struct JneLaneGeo {
   static constexpr int THREADS = 128;
-  static constexpr int MINB = D <= 2 ? 6 : D == 3 ? 5 : D == 4 ? 4 : D == 5 ? JNE_LANE_MINB5 : 2;
+  static constexpr int MINB = D <= 2 ? 6 : D == 3 ? JNE_LANE_MINB3 : D == 4 ? JNE_LANE_MINB4 : D == 5 ? JNE_LANE_MINB5 : 2;
 };
 
 // Per-run moments in global memory (doubles):
@@ -96,17 +104,16 @@ jne_lane_moments_kernel(const uint32_t* __restrict__ seeds, const double* __rest
   const uint64_t run_raw = (uint64_t)blockIdx.x * JneLaneGeo<D>::THREADS + threadIdx.x;
   const bool live = run_raw < n;
   const uint64_t run = live ? run_raw : n - 1;         // idle lanes shadow the last run (no divergence in the loop)
-  // round keys of Philox word 0; the empty asm makes each one opaque, so that ptxas keeps them in registers instead
-  // of re-adding "seed + r * W0" inside the time loop (jne_make_keys does the same through shared memory)
-  jne_keys keys;
-  {
-    const uint32_t seed = SRC_RNG ? seeds[run] : 0u;
+  // generator state: both substreams (halves) of every row of the current epoch, jne_rng.cuh
+  const uint32_t seed = SRC_RNG ? seeds[run] : 0u;
+  jne_sub st[D][2];
+  auto seed_all = [&](uint32_t epoch) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      keys.k[r] = seed + (uint32_t)r * 0x9E3779B9u;
-      asm volatile("" : "+r"(keys.k[r]));
+    for (int r = 0; r < D; ++r) {
+      jne_sub_seed(st[r][0], seed, (uint32_t)r, epoch, 0u);
+      jne_sub_seed(st[r][1], seed, (uint32_t)r, epoch, 1u);
     }
-  }
+  };
   const double* dBrun = SRC_RNG ? nullptr : dB + run * (uint64_t)D * T;
 
   JneLaneState<D, DET> S;
@@ -123,23 +130,29 @@ jne_lane_moments_kernel(const uint32_t* __restrict__ seeds, const double* __rest
   S.w2c = w2c;
   S.w2 = fma(3.0 * w1_first, w1_first, w2c);
 
-  // Four steps per Philox call and row.  The ragged tail (T mod 4 steps) is uniform over the grid: T is a launch
+  // Four steps per generator call and row.  The ragged tail (T mod 4 steps) is uniform over the grid: T is a launch
   // parameter.
   const uint32_t nfull = T >> 2, tail = T & 3u;
   if constexpr (SRC_RNG && JNE_LANE_PIPELINE) {
     // Software pipeline: the normals of block b + 1 are generated BETWEEN the steps of block b (rows spread over the
-    // four steps), so that every stretch of the instruction stream carries both a Philox / MUFU dependency chain and a
-    // batch of independent FP64 FMAs.  With two or three resident warps per sub-partition the generator's latency
+    // four steps), so that every stretch of the instruction stream carries both a generator / MUFU dependency chain
+    // and a batch of independent FP64 FMAs.  With two or three resident warps per sub-partition the generator's latency
     // is otherwise exposed (ncu: 55 % issue-slot use, FP64 and XU pipes 45 / 42 % busy, `wait` the top stall).
+    // Blocks alternate between the two substreams of a row (half = parity of the block), so the loop handles an even
+    // and an odd block per iteration and every state index is a compile-time constant.
     jne_zt zc[D][4], zn[D][4];
+    seed_all(0u);
 #pragma unroll
-    for (int r = 0; r < D; ++r) jne_normals4_keyed(keys, (uint32_t)r, 0u, zc[r]);
-    for (uint32_t tb = 0; tb < nfull; ++tb) {
+    for (int r = 0; r < D; ++r) jne_sub_normals4(st[r][0], zc[r]);
+    // block tb (parity H) is consumed from zc while block tb + 1 (parity 1 - H) is generated into zn
+    auto block = [&](auto Hc, uint32_t tb) {
+      constexpr int H = decltype(Hc)::value;
+      if (H == 1 && ((tb + 1u) & (JNE_EPOCH_BLOCKS - 1u)) == 0u) seed_all((tb + 1u) / JNE_EPOCH_BLOCKS);   // next block opens an epoch
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
 #pragma unroll
         for (int r = 0; r < D; ++r)
-          if (r * 4 / D == s) jne_normals4_keyed(keys, (uint32_t)r, tb + 1u, zn[r]);
+          if (r * 4 / D == s) jne_sub_normals4(st[r][1 - H], zn[r]);
         double zz[D];
 #pragma unroll
         for (int r = 0; r < D; ++r) zz[r] = (double)zc[r][s];
@@ -149,7 +162,13 @@ jne_lane_moments_kernel(const uint32_t* __restrict__ seeds, const double* __rest
       for (int r = 0; r < D; ++r)
 #pragma unroll
         for (int s = 0; s < 4; ++s) zc[r][s] = zn[r][s];
+    };
+    uint32_t tb = 0;
+    for (; tb + 1u < nfull; tb += 2u) {
+      block(std::integral_constant<int, 0>{}, tb);
+      block(std::integral_constant<int, 1>{}, tb + 1u);
     }
+    if (tb < nfull) block(std::integral_constant<int, 0>{}, tb);
 #pragma unroll 1
     for (uint32_t s = 0; s < tail; ++s) {            // zc holds block nfull
       double zz[D];
@@ -163,7 +182,7 @@ jne_lane_moments_kernel(const uint32_t* __restrict__ seeds, const double* __rest
 #pragma unroll
         for (int r = 0; r < D; ++r) {
           jne_zt zf[4];
-          jne_normals4_keyed(keys, (uint32_t)r, tb, zf);
+          jne_normals4(seed, (uint32_t)r, tb, zf);     // random access (ablation builds only: JNE_LANE_PIPELINE=0)
 #pragma unroll
           for (int s = 0; s < 4; ++s) z[s][r] = (double)zf[s];
         }
@@ -547,15 +566,16 @@ jne_group_moments_kernel(const uint32_t* __restrict__ seeds, const double* __res
   const bool live = run_raw < n && !shadow;
   const uint64_t run = run_raw < n ? run_raw : n - 1;
   double* zs = zs_all[warp];
-  jne_keys keys;
-  {
-    const uint32_t seed = SRC_RNG ? seeds[run] : 0u;
+  // generator state: both substreams (halves) of this lane's R rows for the current epoch, jne_rng.cuh
+  const uint32_t seed = SRC_RNG ? seeds[run] : 0u;
+  jne_sub st[R][2];
+  auto seed_all = [&](uint32_t epoch) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      keys.k[r] = seed + (uint32_t)r * 0x9E3779B9u;
-      asm volatile("" : "+r"(keys.k[r]));
+    for (int a = 0; a < R; ++a) {
+      jne_sub_seed(st[a][0], seed, (uint32_t)(l * R + a), epoch, 0u);
+      jne_sub_seed(st[a][1], seed, (uint32_t)(l * R + a), epoch, 1u);
     }
-  }
+  };
   const double* dBrun = SRC_RNG ? nullptr : dB + run * (uint64_t)D * T;
 
   JneGroupState<D, L, DET> S;
@@ -586,13 +606,15 @@ jne_group_moments_kernel(const uint32_t* __restrict__ seeds, const double* __res
   for (int k = 0; k < LR; ++k) rd_off[k] = ((l * R + k) % LR) * G + g;
   const int wr_off = (l * R) * G + g;
 
-  // writes the four steps of this lane's R rows of Philox block tb (or of the caller's increments) into buffer `buf`
-  auto publish_row = [&](uint32_t tb, int buf, int a) {
+  // writes the four steps of row a of this lane of block tb (the next block of substream tb & 1 = BUF, or the caller's
+  // increments) into buffer BUF
+  auto publish_row = [&](auto Bc, uint32_t tb, int a) {
+    constexpr int BUF = decltype(Bc)::value;
     const int row = l * R + a;
     double v[4];
     if constexpr (SRC_RNG) {
       jne_zt zf[4];
-      jne_normals4_keyed(keys, (uint32_t)row, tb, zf, row < D ? 1.0f : 0.0f);
+      jne_sub_normals4(st[a][BUF], zf, row < D ? 1.0f : 0.0f);
 #pragma unroll
       for (int s = 0; s < 4; ++s) v[s] = (double)zf[s];
     } else {
@@ -600,7 +622,7 @@ jne_group_moments_kernel(const uint32_t* __restrict__ seeds, const double* __res
       for (int s = 0; s < 4; ++s) v[s] = (row < D && 4u * tb + s < T) ? dBrun[(uint64_t)(4u * tb + s) * D + row] : 0.0;
     }
 #pragma unroll
-    for (int s = 0; s < 4; ++s) zs[((buf * 4 + s) * LR + a) * G + wr_off] = v[s];
+    for (int s = 0; s < 4; ++s) zs[((BUF * 4 + s) * LR + a) * G + wr_off] = v[s];
   };
   auto read_step = [&](int buf, int s, double (&zz)[LR]) {
 #pragma unroll
@@ -611,30 +633,42 @@ jne_group_moments_kernel(const uint32_t* __restrict__ seeds, const double* __res
   // during steps 0..2, every step's increments are read one step ahead of their use (the shared-memory latency hides
   // behind the previous step's FMAs), and ONE warp barrier sits between steps 2 and 3: by then block tb + 1 is complete
   // (step 3 prefetches its first step) and every lane already holds step 3 of block tb in registers, so nobody reads
-  // buffer tb & 1 again before block tb + 2 is written into it.
+  // buffer tb & 1 again before block tb + 2 is written into it.  The buffer of a block is also the substream (half)
+  // it comes from, so the loop takes an even and an odd block per iteration: every index is a compile-time constant.
   const uint32_t nfull = T >> 2, tail = T & 3u;
+  if (SRC_RNG) seed_all(0u);
 #pragma unroll
-  for (int a = 0; a < R; ++a) publish_row(0u, 0, a);
+  for (int a = 0; a < R; ++a) publish_row(std::integral_constant<int, 0>{}, 0u, a);
   __syncwarp();
   double z0[LR], z1[LR];
   read_step(0, 0, z0);
-  for (uint32_t tb = 0; tb < nfull; ++tb) {
-    const int buf = (int)(tb & 1u);
+  auto block = [&](auto Hc, uint32_t tb) {
+    constexpr int buf = decltype(Hc)::value;
+    using NB = std::integral_constant<int, 1 - buf>;
+    if (SRC_RNG && buf == 1 && ((tb + 1u) & (JNE_EPOCH_BLOCKS - 1u)) == 0u) seed_all((tb + 1u) / JNE_EPOCH_BLOCKS);
 #pragma unroll
-    for (int a = 0; a < R; ++a) if (a * 3 / R == 0) publish_row(tb + 1u, buf ^ 1, a);
+    for (int a = 0; a < R; ++a) if (a * 3 / R == 0) publish_row(NB{}, tb + 1u, a);
     read_step(buf, 1, z1);
     jne_group_step<D, L, DET, SRC_RNG>(S, z0);
 #pragma unroll
-    for (int a = 0; a < R; ++a) if (a * 3 / R == 1) publish_row(tb + 1u, buf ^ 1, a);
+    for (int a = 0; a < R; ++a) if (a * 3 / R == 1) publish_row(NB{}, tb + 1u, a);
     read_step(buf, 2, z0);
     jne_group_step<D, L, DET, SRC_RNG>(S, z1);
 #pragma unroll
-    for (int a = 0; a < R; ++a) if (a * 3 / R == 2) publish_row(tb + 1u, buf ^ 1, a);
+    for (int a = 0; a < R; ++a) if (a * 3 / R == 2) publish_row(NB{}, tb + 1u, a);
     read_step(buf, 3, z1);
     jne_group_step<D, L, DET, SRC_RNG>(S, z0);
     __syncwarp();
     read_step(buf ^ 1, 0, z0);
     jne_group_step<D, L, DET, SRC_RNG>(S, z1);
+  };
+  {
+    uint32_t tb = 0;
+    for (; tb + 1u < nfull; tb += 2u) {
+      block(std::integral_constant<int, 0>{}, tb);
+      block(std::integral_constant<int, 1>{}, tb + 1u);
+    }
+    if (tb < nfull) block(std::integral_constant<int, 0>{}, tb);
   }
   {
     const int buf = (int)(nfull & 1u);

@@ -1,22 +1,35 @@
-// Counter-based Gaussian stream, in registers (sm_100a).
+// Gaussian stream of a run, in registers (sm_100a).
 //
 // Replaces gen_normal_matrix (reference src/rng_matrix.rs:11-37: per-chunk Xoshiro256++ +
 // ziggurat StandardNormal, whose stream depends on the machine's physical core count,
 // :16-20).  Here element (row r, step t) of the d x T normal matrix is a pure function of
-// (seed, r, t):   Philox4x32-10(key = (seed, JNE_KEY1), ctr = (t >> 2, r, 0, 0))
-// yields four 32-bit words; words (0,1) -> Box-Muller pair for steps 4b, 4b+1 and words
-// (2,3) -> steps 4b+2, 4b+3.  The stream does not depend on model, dim, batch size, GPU
-// count or launch geometry (SURVEY.md section 8b "semantics that must hold").
+// (seed, r, t) -- stream "JNE2":
+//   * time is cut into EPOCHS of 128 steps = 32 four-step blocks; block b = t >> 2 belongs to epoch e = b >> 5 and
+//     to HALF h = b & 1 of it, where it is block number j = (b & 31) >> 1 of that half;
+//   * every (row, epoch, half) owns a SUBSTREAM: the counter-based Philox4x32-10(key = (seed, "JNE2"),
+//     ctr = (e, r, h, 0)) yields the 128-bit state of a xoshiro128++ generator (Blackman & Vigna), whose outputs
+//     4j .. 4j+3 are the four words of block j: words (0,1) -> Box-Muller pair for steps 4b, 4b+1, words (2,3) ->
+//     steps 4b+2, 4b+3.
+// The stream does not depend on model, dim, batch size, GPU count or launch geometry (SURVEY.md section 8b
+// "semantics that must hold"); element (r, t) costs one Philox call and at most 16 generator steps to reach.
 //
-// Pipes (measured, profiles/r1_microbench_pipes.txt): IMAD.WIDE 32 lanes/clk/SM, MUFU 16,
-// F2F.F64.F32 16; FP64 37.0 TFLOP/s.  The transform therefore stays in FP32 + MUFU and never
-// touches the FP64 pipe until the final widening.
+// Why not a Philox call per block (the stream of round 1, "JNE1"): IMAD.WIDE.U32 executes on the FP64 datapath
+// (profiles/r1_microbench_dmma_interference.txt), so the 20 wide multiplies per four normals competed with the DMMA /
+// DFMA work the kernels are bound by: the generator cost 36 % of the dim-12 throughput.  ARX counter generators move
+// the cost to the issue slots instead (Threefry4x32-20: -10 %, Threefry4x32-12: +1.6 %); a xoshiro128++ step is 8
+// ALU instructions per word (profiles/r2_variants_generators.txt).  Philox stays where random access is needed -- the
+// substream keys -- at 1/16 of its former rate.  Two substreams per row and epoch (the halves) let two lanes of the
+// tensor kernels share a row without exchanging generator state.
+//
+// Pipes (measured, profiles/r1_microbench_pipes.txt): MUFU 16 lanes/clk/SM, F2F.F64.F32 16; FP64 37.0 TFLOP/s.  The
+// transform stays in FP32 + MUFU and never touches the FP64 pipe until the final widening.
 #pragma once
 #include <cstdint>
 
-#define JNE_KEY1 0x4A4E4531u  // "JNE1"
-// Philox rounds.  10 is the Random123 / cuRAND default and what this library ships; 7 is the smallest count the
-// Random123 paper reports as Crush-resistant -- available as a build-time ablation only (profiles/: the lever table).
+#define JNE_KEY1 0x4A4E4532u  // "JNE2"
+#define JNE_EPOCH_STEPS 128u  // steps per epoch; JNE_EPOCH_BLOCKS four-step blocks, half of them per substream
+#define JNE_EPOCH_BLOCKS 32u
+// Philox rounds of the substream keys.  10 is the Random123 / cuRAND default.
 #ifndef JNE_PHILOX_ROUNDS
 #define JNE_PHILOX_ROUNDS 10
 #endif
@@ -29,11 +42,6 @@ typedef float jne_zt;
 #endif
 
 struct jne_u4 { uint32_t x, y, z, w; };
-
-// 32 x 32 -> (hi, lo) in one IMAD.WIDE.U32
-__device__ __forceinline__ void jne_mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-  asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%1, %0}, p;\n\t}" : "=r"(hi), "=r"(lo) : "r"(a), "r"(b));
-}
 
 __device__ __forceinline__ jne_u4 jne_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                     uint32_t k0, uint32_t k1) {
@@ -52,67 +60,38 @@ __device__ __forceinline__ jne_u4 jne_philox4x32_10(uint32_t c0, uint32_t c1, ui
   return jne_u4{c0, c1, c2, c3};
 }
 
-// Same function with the round keys of word 0 precomputed (key0[r] = seed + r * W0); the round keys of
-// word 1 are compile-time constants.  Lets the per-run key schedule live in registers across the time loop.
-#ifdef JNE_EXP_XOSHIRO
-struct jne_keys { mutable uint32_t k[10]; };   // experiment: words 2..5 are a sequential generator's state
-#else
-struct jne_keys { uint32_t k[10]; };
-#endif
-// `stage` is 10 words of the warp's shared memory: the round trip through memory stops ptxas from
-// rematerialising "seed + r*W0" inside the time loop (it re-added all nine keys on every call).
-__device__ __forceinline__ jne_keys jne_make_keys(uint32_t seed, volatile uint32_t* stage) {
-  jne_keys ks;
-  const int lane = threadIdx.x & 31;
-  if (lane < 10) stage[lane] = seed + (uint32_t)lane * 0x9E3779B9u;
-  __syncwarp();
-#pragma unroll
-  for (int r = 0; r < 10; ++r) ks.k[r] = stage[r];
-  __syncwarp();
-  return ks;
+// One step of xoshiro128++ (Blackman & Vigna, "Scrambled linear pseudorandom number generators", 2021).
+__device__ __forceinline__ uint32_t jne_xoshiro128pp(uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
+  const uint32_t a = s0 + s3;
+  const uint32_t out = __funnelshift_l(a, a, 7) + s0;
+  const uint32_t t = s1 << 9;
+  s2 ^= s0;
+  s3 ^= s1;
+  s1 ^= s2;
+  s0 ^= s3;
+  s2 ^= t;
+  s3 = __funnelshift_l(s3, s3, 11);
+  return out;
 }
-#ifdef JNE_EXP_THREEFRY   // experiment only (= number of rounds): Threefry4x32 (Random123) in place of Philox4x32-10
-__device__ __forceinline__ jne_u4 jne_threefry4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                   uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3) {
-  constexpr int R[8][2] = {{10, 26}, {11, 21}, {13, 27}, {23, 5}, {6, 20}, {17, 11}, {25, 10}, {18, 20}};
-  const uint32_t ks[5] = {k0, k1, k2, k3, 0x1BD11BDAu ^ k0 ^ k1 ^ k2 ^ k3};
-  uint32_t X0 = c0 + ks[0], X1 = c1 + ks[1], X2 = c2 + ks[2], X3 = c3 + ks[3];
-#pragma unroll
-  for (int r = 0; r < JNE_EXP_THREEFRY; ++r) {
-    if ((r & 1) == 0) {
-      X0 += X1; X1 = __funnelshift_l(X1, X1, R[r & 7][0]) ^ X0;
-      X2 += X3; X3 = __funnelshift_l(X3, X3, R[r & 7][1]) ^ X2;
-    } else {
-      X0 += X3; X3 = __funnelshift_l(X3, X3, R[r & 7][0]) ^ X0;
-      X2 += X1; X1 = __funnelshift_l(X1, X1, R[r & 7][1]) ^ X2;
-    }
-    if ((r & 3) == 3) {
-      const int s = (r + 1) >> 2;
-      X0 += ks[s % 5]; X1 += ks[(s + 1) % 5]; X2 += ks[(s + 2) % 5]; X3 += ks[(s + 3) % 5] + (uint32_t)s;
-    }
-  }
-  return jne_u4{X0, X1, X2, X3};
-}
+
+// State of one substream (row, epoch, half).  The validation build carries a second generator for the low halves of
+// its 64-bit uniforms (substream counter word 3 = 1).
+struct jne_sub {
+  uint32_t s0, s1, s2, s3;
+#ifdef JNE_RNG_F64
+  uint32_t l0, l1, l2, l3;
 #endif
-__device__ __forceinline__ jne_u4 jne_philox4x32_10_keyed(uint32_t c0, uint32_t c1, const jne_keys& ks, uint32_t c2 = 0u) {
-#ifdef JNE_EXP_THREEFRY
-  return jne_threefry4x32(c0, c1, c2, 0u, ks.k[0], JNE_KEY1, 0u, 0u);
+};
+
+__device__ __forceinline__ void jne_sub_seed(jne_sub& st, uint32_t seed, uint32_t row, uint32_t epoch, uint32_t half) {
+  jne_u4 w = jne_philox4x32_10(epoch, row, half, 0u, seed, JNE_KEY1);
+  if ((w.x | w.y | w.z | w.w) == 0u) w.x = 1u;   // the generator's one forbidden state (probability 2^-128)
+  st.s0 = w.x; st.s1 = w.y; st.s2 = w.z; st.s3 = w.w;
+#ifdef JNE_RNG_F64
+  jne_u4 v = jne_philox4x32_10(epoch, row, half, 1u, seed, JNE_KEY1);
+  if ((v.x | v.y | v.z | v.w) == 0u) v.x = 1u;
+  st.l0 = v.x; st.l1 = v.y; st.l2 = v.z; st.l3 = v.w;
 #endif
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W1 = 0xBB67AE85u;
-  uint32_t c3 = 0u;
-#pragma unroll
-  for (int r = 0; r < JNE_PHILOX_ROUNDS; ++r) {
-    uint32_t h0, l0, h1, l1;
-    jne_mulhilo(M0, c0, h0, l0);
-    jne_mulhilo(M1, c2, h1, l1);
-    const uint32_t n0 = h1 ^ c1 ^ ks.k[r];
-    const uint32_t n2 = h0 ^ c3 ^ (JNE_KEY1 + (uint32_t)r * W1);
-    c1 = l1;
-    c3 = l0;
-    c0 = n0;
-    c2 = n2;
-  }
-  return jne_u4{c0, c1, c2, c3};
 }
 
 // Two N(0,1) variates from two 32-bit words.  u = (wa + 1/2) 2^-32 in (0, 1], radius
@@ -124,7 +103,7 @@ __device__ __forceinline__ void jne_box_muller(uint32_t wa, uint32_t wb, float& 
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));   // MUFU.LG2 (u >= 2^-33: never denormal)
   // -2 ln 2 as a float is -0x1.62e430p+0; the constant below sits three ulps further out (+2.58e-7 relative).  It
   // cancels the variance deficit of this FP32 / MUFU pipeline, measured on 2^27 normals against the FP64 transform of
-  // the same Philox blocks: E[z^2]_fp32 - E[z^2]_fp64 = -2.5265e-7 +- 8e-11 (profiles/r2_rng_moments_before_calibration.txt; every
+  // the same uniform words: E[z^2]_fp32 - E[z^2]_fp64 = -2.5265e-7 +- 8e-11 (profiles/r2_rng_moments_before_calibration.txt; every
   // eigenvalue statistic carried the same -2.53e-7 relative shift, profiles/r2_gate2_ab_*).  The eigenvalues scale
   // with Var(z), so this is the one moment worth calibrating; residual +5e-9.
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -0x1.62e436p+0f));  // MUFU.SQRT
@@ -134,9 +113,9 @@ __device__ __forceinline__ void jne_box_muller(uint32_t wa, uint32_t wb, float& 
   z1 = r * __sinf(th);
 }
 
-// VALIDATION STREAM (-DJNE_RNG_F64, never in libjne.so): the same counters, keys and word assignment, but the radius
-// uniform and the angle carry 64 bits -- the product's 32-bit word on top, the matching word of a second Philox block
-// (counter word 2 = 1) below -- and the transform runs in FP64 (log, sqrt, sincospi).  u = (x + 1/2) 2^-64, so the
+// VALIDATION STREAM (-DJNE_RNG_F64, never in libjne.so): the same substreams and word assignment, but the radius
+// uniform and the angle carry 64 bits -- the product's 32-bit word on top, the matching word of a second generator
+// (substream key with counter word 3 = 1) below -- and the transform runs in FP64 (log, sqrt, sincospi).  u = (x + 1/2) 2^-64, so the
 // radius reaches 9.5 instead of 6.76 and the tail is not quantised at 2^-32.  Element (row, step) of this stream differs
 // from the product's by the MUFU / FP32 rounding (~1e-6) and the low-order refinement only, which makes the A/B of
 // tools/validate_gate2.py a PAIRED comparison of the statistics, run by run.
@@ -152,52 +131,42 @@ __device__ __forceinline__ void jne_box_muller_f64(uint32_t wa, uint32_t wa_lo, 
   z1 = r * sn;
 }
 
-// The four normals of (row, time block tb = t >> 2) for one seed.
-__device__ __forceinline__ void jne_normals4(uint32_t seed, uint32_t row, uint32_t tb, jne_zt z[4]) {
-  const jne_u4 w = jne_philox4x32_10(tb, row, 0u, 0u, seed, JNE_KEY1);
+// The next four-step block of a substream: four words -> four normals (times `scale`: 1, or 0 for a row the run
+// does not have, which keeps the generation branch-free).
+__device__ __forceinline__ void jne_sub_normals4(jne_sub& st, jne_zt* z, float scale = 1.0f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w[i] = jne_xoshiro128pp(st.s0, st.s1, st.s2, st.s3);
 #ifdef JNE_RNG_F64
-  const jne_u4 v = jne_philox4x32_10(tb, row, 1u, 0u, seed, JNE_KEY1);
-  jne_box_muller_f64(w.x, v.x, w.y, v.y, z[0], z[1], 1.0);
-  jne_box_muller_f64(w.z, v.z, w.w, v.w, z[2], z[3], 1.0);
+  uint32_t v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = jne_xoshiro128pp(st.l0, st.l1, st.l2, st.l3);
+  jne_box_muller_f64(w[0], v[0], w[1], v[1], z[0], z[1], (double)scale);
+  jne_box_muller_f64(w[2], v[2], w[3], v[3], z[2], z[3], (double)scale);
 #else
-  jne_box_muller(w.x, w.y, z[0], z[1]);
-  jne_box_muller(w.z, w.w, z[2], z[3]);
-#endif
-}
-__device__ __forceinline__ void jne_normals4_keyed(const jne_keys& ks, uint32_t row, uint32_t tb, jne_zt* z,
-                                                   float scale = 1.0f) {
-#ifdef JNE_RNG_F64
-  const jne_u4 w = jne_philox4x32_10_keyed(tb, row, ks), v = jne_philox4x32_10_keyed(tb, row, ks, 1u);
-  jne_box_muller_f64(w.x, v.x, w.y, v.y, z[0], z[1], (double)scale);
-  jne_box_muller_f64(w.z, v.z, w.w, v.w, z[2], z[3], (double)scale);
-#else
-#ifdef JNE_EXP_NORNG   // experiment only: no Philox / Box-Muller (NOT a valid stream)
-  z[0] = scale * 0.5f; z[1] = -scale * (float)(row + 1) * 0.25f; z[2] = scale * 0.125f * (tb & 3); z[3] = -scale;
+#ifdef JNE_EXP_NORNG   // experiment only: no generator, no transform (NOT a valid stream)
+  z[0] = scale * 0.5f; z[1] = -scale * 0.25f; z[2] = scale * 0.125f; z[3] = -scale;
   return;
 #endif
-#ifdef JNE_EXP_XOSHIRO   // experiment only: xoshiro128++ advanced per call, (row, tb) ignored (NOT a valid stream): the
-  {                      // cost ceiling of a sequential generator seeded once per run, row and segment
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint32_t &s0 = ks.k[2], &s1 = ks.k[3], &s2 = ks.k[4], &s3 = ks.k[5];
-      const uint32_t a = s0 + s3;
-      w[i] = __funnelshift_l(a, a, 7) + s0;
-      const uint32_t t = s1 << 9;
-      s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3; s2 ^= t; s3 = __funnelshift_l(s3, s3, 11);
-    }
-    jne_box_muller(w[0], w[1], z[0], z[1], scale);
-    jne_box_muller(w[2], w[3], z[2], z[3], scale);
-    return;
-  }
+#ifdef JNE_EXP_NOBM    // experiment only: the generator without the normal transform (NOT a valid stream)
+  z[0] = scale * __int_as_float((w[0] >> 9) | 0x3f800000); z[1] = scale * __int_as_float((w[1] >> 9) | 0x3f800000);
+  z[2] = scale * __int_as_float((w[2] >> 9) | 0x3f800000); z[3] = scale * __int_as_float((w[3] >> 9) | 0x3f800000);
+  return;
 #endif
-#ifdef JNE_EXP_NOBM    // experiment only: Philox but no Box-Muller
-  { const jne_u4 w = jne_philox4x32_10_keyed(tb, row, ks);
-    z[0] = scale * __int_as_float((w.x >> 9) | 0x3f800000); z[1] = scale * __int_as_float((w.y >> 9) | 0x3f800000);
-    z[2] = scale * __int_as_float((w.z >> 9) | 0x3f800000); z[3] = scale * __int_as_float((w.w >> 9) | 0x3f800000); return; }
-#endif
-  const jne_u4 w = jne_philox4x32_10_keyed(tb, row, ks);
-  jne_box_muller(w.x, w.y, z[0], z[1], scale);
-  jne_box_muller(w.z, w.w, z[2], z[3], scale);
+  jne_box_muller(w[0], w[1], z[0], z[1], scale);
+  jne_box_muller(w[2], w[3], z[2], z[3], scale);
 #endif
 }
+
+// Random access (test entries, never on the hot path): the four normals of (row, block tb = t >> 2).
+__device__ __forceinline__ void jne_normals4(uint32_t seed, uint32_t row, uint32_t tb, jne_zt z[4]) {
+  jne_sub st;
+  jne_sub_seed(st, seed, row, tb / JNE_EPOCH_BLOCKS, tb & 1u);
+  const uint32_t j = (tb % JNE_EPOCH_BLOCKS) >> 1;
+  for (uint32_t i = 0; i < j; ++i) {
+    jne_zt skip[4];
+    jne_sub_normals4(st, skip);
+  }
+  jne_sub_normals4(st, z);
+}
+

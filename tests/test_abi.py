@@ -150,7 +150,7 @@ def test_trend_weight_table(T):
     which is the identity the kernels rely on (summation by parts)."""
     import johansen_null_eigenspectra_b200 as jne
     tab = jne.trend_weight_table(T)
-    seg_len = 8 * ((T + 31) // 32)
+    seg_len = 128 * ((T + 511) // 512)          # whole generator epochs (jne_rng.cuh)
     assert tab.shape == (seg_len, 4, 4)
     w1 = [2 * i + 1 - T for i in range(T)]
     w2 = [3 * w * w - (T * T - 1) for w in w1]

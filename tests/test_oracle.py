@@ -202,6 +202,29 @@ def test_philox_known_answers():
         assert tuple(int(x) for x in philox_ref.philox4x32_10(*ctr, *key)) == exp
 
 
+def test_xoshiro128pp_known_answers():
+    """The substream generator of the device stream against the published reference vector of xoshiro128++
+    (state {1, 2, 3, 4}; the vector rand_xoshiro 0.7.0 -- the reference's own generator crate -- tests its
+    Xoshiro128PlusPlus with, produced by Vigna's C implementation)."""
+    st = [np.array([v], dtype=np.uint32) for v in (1, 2, 3, 4)]
+    got = [int(philox_ref.xoshiro128pp(st)[0]) for _ in range(10)]
+    assert got == [641, 1573767, 3222811527, 3517856514, 836907274, 4247214768, 3867114732, 1355841295, 495546011,
+                   621204420]
+
+
+def test_stream_words_layout():
+    """Block b of row r is block (b & 31) >> 1 of substream (r, b >> 5, b & 1): check the vectorised restatement
+    against a scalar walk of one substream, across an epoch boundary."""
+    seed, row = 12345, 3
+    w = philox_ref.stream_words(5, 600, seed)          # 150 blocks: epochs 0..4
+    for b in (0, 1, 2, 31, 32, 33, 95, 149):
+        e, h, j = b >> 5, b & 1, (b & 31) >> 1
+        st = [np.array([int(x)], dtype=np.uint32) for x in philox_ref.philox4x32_10(e, row, h, 0, seed, philox_ref.KEY1)]
+        for _ in range(4 * j):
+            philox_ref.xoshiro128pp(st)
+        assert [int(philox_ref.xoshiro128pp(st)[0]) for _ in range(4)] == [int(x) for x in w[row, b]]
+
+
 def test_philox_normal_matrix_is_standard_normal():
     z = philox_ref.normal_matrix(200, 300, 42)
     qs = np.arange(1, 100) / 100

@@ -361,72 +361,11 @@ def test_increment_scale_covariance(engine):
             assert_close(got / scale / scale, ref, f"model {model} scale {scale}")
 
 
-def _experimental_library():
-    """The measured-slower kernel families live in csrc/experimental/ and are compiled only into the variant library
-    (python -m johansen_null_eigenspectra_b200.build --experimental); libjne.so does not contain them."""
-    from johansen_null_eigenspectra_b200 import build as jbuild
-    path = jbuild.VARIANTS["experimental"][1]
-    if not path.exists():
-        pytest.skip("libjne_experimental.so not built (build.py --experimental)")
-    import ctypes, re
-    lib = ctypes.CDLL(str(path))
-    header = re.sub(r"/\*.*?\*/", "", (jbuild.PKG_DIR.parent / "include" / "jne.h").read_text(), flags=re.S)
-    missing = [n for n in set(re.findall(r"\b(jne_[a-z0-9_]+)\s*\(", header)) if not hasattr(lib, n)]
-    if missing:
-        pytest.skip(f"libjne_experimental.so is older than include/jne.h (lacks {missing[0]}): rebuild it")
-    return str(path)
-
-
-def test_fma_tiled_kernel_family():
-    """JNE_KERNEL=v2 selects the register-tiled FMA family (csrc/experimental/jne_kernels_v2.cuh) for 9 <= dim <= 12.  It consumes
-    the same random stream, so it must agree with the oracle fed the device normals (gate-1 tolerance), with the
-    increments entry, and -- to rounding, not bits: the summation order differs -- with the default tensor family."""
-    import os, subprocess, sys, textwrap
-    code = textwrap.dedent('''
-        import sys, numpy as np
-        sys.path.insert(0, ".")
-        import johansen_null_eigenspectra_b200 as jne
-        from oracle import johansen_oracle as orc
-        eng = jne.Engine([0])
-        seeds = np.array([1, 2, 77], dtype=np.uint32)
-        rng = np.random.default_rng(3)
-        worst = 0.0
-        for dim, T in [(9, 50), (10, 103), (11, 257), (12, 1001), (12, 10000)]:
-            multi = eng.eigs_batch_multi(range(5), dim, T, seeds)
-            db = rng.standard_normal((2, T, dim)) / np.sqrt(T)
-            for m in range(5):
-                got = eng.eigs_batch(m, dim, T, seeds)
-                assert np.array_equal(got, multi[m])
-                for i, s in enumerate(seeds):
-                    ref = orc.eigs_from_normals(eng.gen_normal_matrix(dim, T, int(s)), m)
-                    worst = max(worst, float(np.max(np.abs(got[i] - ref) / (1e-9 * np.abs(ref) + 1e-12 * ref.max()))))
-                ref = orc.eigs_batch_from_increments(db, m)
-                got = eng.eigs_from_increments(m, db)
-                worst = max(worst, float(np.max(np.abs(got - ref) / (1e-9 * np.abs(ref) + 1e-12 * ref.max(axis=1, keepdims=True)))))
-        np.save(sys.argv[1], eng.eigs_batch(3, 12, 400, np.arange(1, 501, dtype=np.uint32)))
-        print("WORST", worst)
-    ''')
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = {}
-    explib = _experimental_library()
-    for fam in ("v2", "v1"):
-        path = f"/tmp/jne_family_{fam}.npy"
-        env = dict(os.environ, JNE_KERNEL=fam, JNE_LIBRARY=explib)
-        r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=env, capture_output=True, text=True, timeout=900)
-        assert r.returncode == 0, r.stderr[-2000:]
-        worst = float(r.stdout.split("WORST")[1])
-        assert worst <= 1.0, (fam, worst)
-        out[fam] = np.load(path)
-    assert np.allclose(out["v1"], out["v2"], rtol=1e-10, atol=1e-12 * out["v1"].max())
-
-
-def test_warp_specialised_kernel_family():
-    """JNE_KERNEL=ws selects the producer / consumer family (csrc/experimental/jne_kernels_ws.cuh) for dim <= 12.  Its generator
-    warps compute the very values the default family computes in place, so every record must be bit-identical to
-    the default family with the same trend-moment arithmetic (JNE_AUX=0: scalar FP64 sums) -- for partial CTAs
-    (fewer runs than consumer warps), several runs per consumer warp, ragged T, all models.  Against the default
-    family's AUX kernels (trend moments through the MMA, dim <= 6 and 9..12) the records agree to the gate-1
-    tolerance."""
+def test_aux_kernels_vs_scalar_sum_kernels():
+    """The AUX kernels of the tensor family take the trend moments out of the MMA (table-driven weights in operand
+    slots that were padding); JNE_AUX=0 selects the scalar-sum kernels (FP64 sums per lane, summation by parts)
+    everywhere.  Same stream, same products otherwise: the records agree to the gate-1 tolerance for every tensor
+    layout (JNE_LANE=0: 4, 8 and 12 rows), partial CTAs, ragged T, all models, fused and single-model entries."""
     import os, subprocess, sys, textwrap
     code = textwrap.dedent('''
         import sys, numpy as np
@@ -446,17 +385,15 @@ def test_warp_specialised_kernel_family():
     ''')
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    explib = _experimental_library()
-    for fam, kern, aux in (("ws", "ws", "0"), ("v1", "v1", "0"), ("v1aux", "v1", "1")):
-        path = f"/tmp/jne_family_{fam}.npz"
-        env = dict(os.environ, JNE_KERNEL=kern, JNE_AUX=aux, JNE_LANE="0", JNE_LIBRARY=explib)   # tensor family for every dim
+    for aux in ("0", "1"):
+        path = f"/tmp/jne_aux_{aux}.npz"
+        env = dict(os.environ, JNE_AUX=aux, JNE_LANE="0")   # tensor family for every dim
         r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
-        res[fam] = np.load(path)
-    assert set(res["ws"].files) == set(res["v1"].files) == set(res["v1aux"].files)
-    for k in res["v1"].files:
-        assert np.array_equal(res["ws"][k], res["v1"][k]), k
-        a, b = res["v1aux"][k], res["v1"][k]
+        res[aux] = np.load(path)
+    assert set(res["0"].files) == set(res["1"].files)
+    for k in res["0"].files:
+        a, b = res["1"][k], res["0"][k]
         tol = 1e-9 * np.abs(b) + 1e-12 * b.max(axis=1, keepdims=True)
         assert np.all(np.abs(a - b) <= tol), k
 

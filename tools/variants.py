@@ -9,12 +9,13 @@ ROOT = Path(__file__).resolve().parents[1]
 PKG = ROOT / "johansen_null_eigenspectra_b200"
 VARIANTS = {
     "base": [],
-    "philox7": ["-DJNE_PHILOX_ROUNDS=7"],          # Random123's smallest Crush-resistant round count (default 10)
-    "nobm": ["-DJNE_EXP_NOBM"],                    # Philox only, no normal transform (NOT a valid stream)
+    "nobm": ["-DJNE_EXP_NOBM"],                    # generator only, no normal transform (NOT a valid stream)
     "norng": ["-DJNE_EXP_NORNG"],                  # no generator at all (NOT a valid stream)
-    "threefry20": ["-DJNE_EXP_THREEFRY=20"],       # Threefry4x32-20 (Random123 default rounds) in place of Philox4x32-10: ARX, no wide multiplies
-    "threefry12": ["-DJNE_EXP_THREEFRY=12"],       # Threefry4x32-12 (smallest Crush-resistant count per the Random123 paper)
-    "xoshiro": ["-DJNE_EXP_XOSHIRO"],              # sequential xoshiro128++ per lane, counters ignored (NOT a valid stream): ceiling of a sequential generator
+    "seglen8": ["-DJNE_EXP_SEGLEN8"],              # tensor family: segments of whole 8-step blocks instead of whole epochs (NOT a valid stream): cost of the longer masked tail
+    "noreseed": ["-DJNE_EXP_NORESEED"],            # tensor family: substreams keyed once per run (NOT a valid stream): cost of the in-loop key generation
+    "seglen8_noreseed": ["-DJNE_EXP_SEGLEN8", "-DJNE_EXP_NORESEED"],
+    "minb4": ["-DJNE_MULTI_MINB=4"],               # fused tensor kernel at 4 CTAs per SM (116 registers: no spill of the substream states)
+    "lane_minb_hi": ["-DJNE_LANE_MINB3=5", "-DJNE_LANE_MINB4=4"],   # lane family dims 3 / 4 at 102 / 128 registers (the substream states spill)
     "group78": ["-DJNE_EXP_GROUP_78"],             # dims 7, 8 on the group kernel (2 lanes x 4 rows), dim 10 as 5 x 2
     "lane_nopipe": ["-DJNE_LANE_PIPELINE=0"],      # lane family without the software pipeline (generate a block, then consume it)
     "lane_nopipe_minb3": ["-DJNE_LANE_PIPELINE=0", "-DJNE_LANE_MINB5=3"],   # ... and dim 5 at 168 registers / 3 CTAs per SM
@@ -57,7 +58,8 @@ def t(models, dim, T, n, reps=3):
 res = {"fused_d12": t(range(5), 12, 10000, 133200), "m0_d12": t([0], 12, 10000, 133200), "m4_d12": t([4], 12, 10000, 133200),
        "fused_d9": t(range(5), 9, 10000, 118400), "fused_d10": t(range(5), 10, 10000, 118400), "fused_d11": t(range(5), 11, 10000, 133200), "fused_d8": t(range(5), 8, 10000, 133200), "fused_d7": t(range(5), 7, 10000, 133200),
        "fused_d5_T5000": t(range(5), 5, 5000, 1 << 20), "m0_d5_T5000": t([0], 5, 5000, 1 << 20), "m4_d5_T5000": t([4], 5, 5000, 1 << 20),
-       "fused_d1": t(range(5), 1, 10000, 1 << 20), "fused_d3": t(range(5), 3, 10000, 1 << 20)}
+       "fused_d1": t(range(5), 1, 10000, 1 << 20), "fused_d2": t(range(5), 2, 10000, 1 << 20), "fused_d3": t(range(5), 3, 10000, 1 << 20),
+       "fused_d4": t(range(5), 4, 10000, 1 << 20), "fused_d6": t(range(5), 6, 10000, 1 << 19)}
 print(json.dumps(res))
 '''
 
