@@ -405,7 +405,7 @@ def main():
         # launch shape (tools/ncu_target.py --n R; tools/ncu_traffic.py writes the file).  Only quoted when the capture
         # was taken at the same seeds-per-launch and configuration; never extrapolated.
         traffic, traffic_src = None, None
-        tfile = ROOT / "profiles" / "r2_traffic_fused_d12.json"
+        tfile = ROOT / "profiles" / "r2_traffic_fused_d12_jne2.json"
         if tfile.exists():
             try:
                 tj = json.loads(tfile.read_text())
@@ -421,7 +421,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"models 0-4, dim {dim}, T {T}, {R} runs per model per step per GPU, seeds {int(seeds_np[0])}..",
-                "runs_per_step": len(MODELS) * R * world, "rng": "philox4x32-10 + box-muller, in registers",
+                "runs_per_step": len(MODELS) * R * world, "rng": "stream JNE2: philox4x32-10-keyed xoshiro128++ substreams + fp32 box-muller, in registers",
                 "l2": "256 MiB buffer written between steps (inputs are 4 B per run; the path is FP64-bound)",
                 "parallelism": f"seed-sharded x{world}, no collective",
             },

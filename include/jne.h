@@ -129,7 +129,7 @@ int jne_eigs_from_increments(jne_ctx* ctx, uint8_t model, uint32_t dim, uint32_t
 /* ---- pieces of the path exposed for parity tests ------------------------------------------ */
 
 /* gen_normal_matrix(nrows = dim, ncols = steps, seed) (src/rng_matrix.rs:11-37): dim x steps
- * column-major standard normals of the device stream (Philox4x32-10 + Box-Muller). */
+ * column-major standard normals of the device stream (stream JNE2: Philox4x32-10-keyed xoshiro128++ substreams + FP32 Box-Muller, jne_rng.cuh). */
 int jne_gen_normal_matrix(jne_ctx* ctx, uint32_t dim, uint32_t steps, uint32_t seed, double* out);
 
 /* brownian_motion_matrix(dim, steps, delta_t, AlongColumns, zeros, seed) (src/rng_matrix.rs:57-141):

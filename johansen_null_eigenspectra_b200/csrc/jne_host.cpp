@@ -107,7 +107,7 @@ void run_models_simulation(const Engine& gpu, uint32_t model_mask, uint32_t dim,
       stats[m].completed_before = completed;
       stats[m].total_in_file = completed;
       if (completed >= num_runs) continue;               // parallel_compute.rs:182-188: enough records, whatever their seeds
-      if (!quiet && completed)   // a resumed file continues with THIS library's stream (Philox), whoever wrote the head of it
+      if (!quiet && completed)   // a resumed file continues with THIS library's stream (JNE2), whoever wrote the head of it
         printf("Resuming %s: %llu of %llu runs present\n", filenames[m].c_str(), (unsigned long long)completed, (unsigned long long)num_runs);
       // need[s] |= bit for every seed whose bitmap bit is clear, eight seeds per bitmap byte
       const uint8_t bit = (uint8_t)(1u << m);

@@ -1,6 +1,6 @@
 // Device side of the Johansen null-eigenspectra hot path (sm_100a).
 //
-//   K1  jne_normals4            (jne_rng.cuh)  replaces gen_normal_matrix        src/rng_matrix.rs:11-37
+//   K1  jne_sub_normals4        (jne_rng.cuh)  replaces gen_normal_matrix        src/rng_matrix.rs:11-37
 //   K2  jne_run_kernel main loop               replaces brownian_motion_matrix   src/rng_matrix.rs:57-141,
 //                                              dmatrix_cumsum RowWise            src/matrix_utils.rs:51-63,
 //                                              construct_f_matrix                src/johansen_statistics.rs:102-197,
@@ -565,7 +565,7 @@ __device__ __forceinline__ bool jne_warp_models(double* __restrict__ wsm, const 
 
 // ---------------------------------------------------------------------------------------------
 // The time loop works on blocks of 8 consecutive steps of the lane's segment.  jne_gen8 produces the
-// block's increments (Philox + Box-Muller, or global loads), jne_consume8 feeds them to the MMAs.  Both
+// block's increments (generator + Box-Muller, or global loads), jne_consume8 feeds them to the MMAs.  Both
 // are branch-free.
 //
 // RNG balance: a generator call yields 4 steps of one row, and a lane owns DP/8 rows (0.5, 1, 1.5 or 2).  With
@@ -838,7 +838,7 @@ __device__ __forceinline__ void jne_warp_dump(JneLoopState<DP>& L, double* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused per-run kernel.  SRC_RNG: increments come from the Philox stream keyed by seeds[run];
+// Fused per-run kernel.  SRC_RNG: increments come from the random stream keyed by seeds[run];
 // otherwise from caller-supplied dB (n runs x (dim x steps) column-major per run, the layout of
 // src/rng_matrix.rs:36) and the path is rebuilt exactly as src/johansen_statistics.rs:80-82 does.
 // DET: 0 = models 0,1 (sum c only), 1 = models 2,3 (+ w1 moments), 2 = model 4 (+ w2 moments).

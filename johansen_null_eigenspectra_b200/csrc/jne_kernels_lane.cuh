@@ -2,19 +2,19 @@
 //
 // Why a second family.  On the tensor path (jne_kernels.cuh) a warp owns one run and feeds V = [F ; dB] to
 // mma.sync.m8n8k4.f64 tiles; the tile layouts are sized for 4, 8 and 12 rows, so dim 1 pays for dim 4 and
-// dim 5 for dim 8 -- both in padded products and in Philox blocks generated for rows that do not exist
+// dim 5 for dim 8 -- both in padded products and in normals generated for rows that do not exist
 // (profiles/r1_bench_all_configs.jsonl: 10.5 M seeds/s for every dim 1..4, 7.2 M for dim 5 and 6).  The reference's
 // cost is proportional to the products it needs (src/matrix_utils.rs:67-85: p x d per step), and below about
 // seven rows all of a run's moments fit one thread's registers:
 //     sum c c' (upper triangle)   D (D + 1) / 2        sum c dB'   D^2        sum c, sum w1 c, sum w2 c   3 D
-// = 81 doubles at D = 6.  So here a lane owns a whole run: it generates exactly the D rows the run has (one Philox
+// = 81 doubles at D = 6.  So here a lane owns a whole run: it generates exactly the D rows the run has (one generator
 // call per row and four steps), keeps the path in registers, and every product is an FP64 FMA on two registers:
 // no padded products, no operand exchange, no time segments (the sums run left to right over the T steps, as the
 // reference's do), D known at compile time.  The moments go to global memory in a compact layout
 // (JneLaneMom<D>) and jne_lane_solve_kernel -- one warp per run, the epilogue of the tensor path unchanged
 // (jne_warp_models: assembly per model, elimination, Jacobi) -- turns them into eigenvalues.
 //
-//   K1  jne_normals4_keyed        (jne_rng.cuh)  replaces gen_normal_matrix        src/rng_matrix.rs:11-37
+//   K1  jne_sub_normals4          (jne_rng.cuh)  replaces gen_normal_matrix        src/rng_matrix.rs:11-37
 //   K2  jne_lane_moments_kernel                  replaces brownian_motion_matrix   src/rng_matrix.rs:57-141,
 //                                                dmatrix_cumsum RowWise            src/matrix_utils.rs:51-63,
 //                                                construct_f_matrix                src/johansen_statistics.rs:102-197,
@@ -484,7 +484,7 @@ jne_lane_tsolve_kernel(const double* __restrict__ mom, uint64_t n, uint32_t mode
 // Every lane keeps the WHOLE path c (D adds per step) in a frame rotated by its own first row -- own rows first,
 // then the next lane's, ... -- which makes every register index a compile-time constant while the lane dependence
 // sits in shared-memory addresses.  The only exchange is the step's increments: each lane writes the four steps of
-// its R rows of a Philox block to shared memory once per block (double-buffered, one __syncwarp per block) and reads
+// its R rows of a four-step block to shared memory once per block (double-buffered, one __syncwarp per block) and reads
 // the D increments of a step back as broadcasts; the path itself never travels.  Moments leave in the layout of
 // JneLaneMom<D>; jne_lane_solve_kernel (one warp per run) finishes.
 // ---------------------------------------------------------------------------------------------

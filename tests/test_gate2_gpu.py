@@ -1,5 +1,5 @@
 """Parity gate (2) at the BASELINE configurations (-m gpu): the trace / max-eig distributions of the device stream
-(Philox4x32-10, FP32 Box-Muller) against the C restatement of the reference path driven by f64 ziggurat normals
+(stream JNE2: Philox-keyed xoshiro128++ substreams, FP32 Box-Muller) against the C restatement of the reference path driven by f64 ziggurat normals
 (src/rng_matrix.rs:26-34), at c2 (dim 5, T 5 000) and c4 (dim 12, T 10 000), all five models.
 
 CPU side: tests/golden/gate2_cpu_dim*_T*.npz, made by tools/gate2_cpu_samples.py (4 * 10^6 runs at c2, 10^7 at c4; order-

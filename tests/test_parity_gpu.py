@@ -461,7 +461,7 @@ def test_device_normals_moments_and_tails(engine):
     """The FP32 / MUFU Box-Muller stream (32-bit radius uniform, |z| <= 6.76) as a N(0,1) sample: mean, variance,
     skewness, kurtosis and the |z| quantiles up to 1 - 1e-5 on 2^25 normals against the exact values, within 4.5
     Monte Carlo standard errors; and -- when the validation build (jne_rng.cuh, -DJNE_RNG_F64: 64-bit uniforms, FP64
-    transform of the SAME Philox blocks) is present -- element by element against it: the transform's error is ~1e-6
+    transform of the SAME uniform words) is present -- element by element against it: the transform's error is ~1e-6
     per normal and its variance deficit (-2.53e-7 before the radius-constant calibration, profiles/r2_rng_moments_before_calibration.txt)
     is gone to 3e-8.  The reference's own test is a CDF check to 1e-2 on 60 000 normals
     (src/tests/rng_matrix_test/gen_normal_matrix_test.rs:7-16)."""

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Moments and tail quantiles of the device normal stream (GPU box): the production transform (FP32 Box-Muller on MUFU,
 32-bit uniforms) against the validation build's FP64 transform on 64-bit uniforms (jne_rng.cuh, -DJNE_RNG_F64) on the
-SAME Philox blocks, element by element, plus both against the exact N(0,1) values.
+SAME uniform words, element by element, plus both against the exact N(0,1) values.
     python tools/rng_moments.py [--n-log2 28] > profiles/r2_rng_moments.txt
 The two streams share their leading 32 bits, so the differences of the sample moments are paired: their Monte Carlo
 error is that of z32 - z64 (~1e-6 per element), not that of the moments themselves."""
@@ -52,7 +52,7 @@ def main():
     x, y = z["fp32"], z["f64"]
     n = x.size
     from scipy import stats
-    print(f"# {n} normals (2^{np.log2(n):.0f}), seeds 1000.., dim 8: production FP32 transform (x) vs FP64 validation transform (y), same Philox blocks")
+    print(f"# {n} normals (2^{np.log2(n):.0f}), seeds 1000.., dim 8: production FP32 transform (x) vs FP64 validation transform (y), same uniform words")
     print(f"max |x - y| = {np.max(np.abs(x - y)):.3e}   rms(x - y) = {np.sqrt(np.mean((x - y) ** 2)):.3e}   max |x| = {np.max(np.abs(x)):.4f}   max |y| = {np.max(np.abs(y)):.4f}")
     print("moment        production        validation        exact   paired difference (x - y)   its standard error")
     for name, f, exact in (("E[z]", lambda v: v, 0.0), ("E[z^2]", lambda v: v * v, 1.0), ("E[z^3]", lambda v: v ** 3, 0.0), ("E[z^4]", lambda v: v ** 4, 3.0),
