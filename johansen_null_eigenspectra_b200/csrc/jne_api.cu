@@ -731,10 +731,12 @@ __global__ void jne_aggregate_kernel(const double* __restrict__ eigs, uint64_t n
 
 // ---- exact order statistics without a sort (row f3) ----
 // Doubles map to 64-bit keys whose unsigned order is the doubles' order.  The k-th smallest key of a sample that is
-// spread over several arrays (one per device) is found digit by digit: four passes of 16 bits, each a histogram of
+// spread over several arrays (one per device) is found digit by digit: eight passes of 8 bits, each a histogram of
 // the next digit over the keys that match the prefixes found so far.  Several ranks are resolved together (one
-// histogram row per distinct prefix).  Nothing but histograms leaves a device; the result does not depend on how the
-// sample is partitioned.
+// histogram row of 256 counters per distinct prefix), and several samples per pass (the ten statistics of a five-model
+// job share the passes).  Nothing but these histograms leaves a device -- a few KB per pass; with 16-bit digits the
+// 256 KB rows, copied and summed per device, sample and pass, were two thirds of the wall time of the 8-GPU default
+// sweep at small dims -- and the result does not depend on how the sample is partitioned.
 __device__ __forceinline__ uint64_t jne_order_key(double x) {
   const uint64_t b = (uint64_t)__double_as_longlong(x);
   return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
@@ -750,10 +752,10 @@ jne_select_hist_kernel(const double* __restrict__ vals, uint64_t n, int shift, J
     int slot = -1;
     if (i < n) {
       const uint64_t key = jne_order_key(vals[i]);
-      const uint64_t hi = shift >= 48 ? 0ull : key >> (shift + 16);
+      const uint64_t hi = shift >= 56 ? 0ull : key >> (shift + 8);
       int g = -1;
       for (int k = 0; k < pf.n; ++k) if (pf.prefix[k] == hi) g = k;
-      if (g >= 0) slot = (g << 16) | (int)((key >> shift) & 0xffffull);
+      if (g >= 0) slot = (g << 8) | (int)((key >> shift) & 0xffull);
     }
     // warp-aggregated: one atomic per distinct (group, digit) in the warp (the leading digits of a sample are few)
     const unsigned active = __ballot_sync(0xffffffffu, slot >= 0);
@@ -1215,70 +1217,86 @@ namespace {
 // One statistic of one model: its values as they lie on the context's devices (n[i] doubles at vals[i] on device i).
 struct SelSample { std::vector<const double*> vals; std::vector<uint64_t> n; };
 
-// x_(k) for every k in ranks (0-based, any order, duplicates allowed) of the union of the sample's arrays.
-int select_ranks(jne_ctx* ctx, const std::vector<int>& dev_index, const SelSample& smp, const std::vector<uint64_t>& ranks,
-                 std::vector<double>* out) {
-  const size_t nr = ranks.size(), nd = smp.vals.size();
-  std::vector<uint64_t> prefix(nr, 0), within(ranks);
+// One selection job: x_(k) for every k in ranks (0-based, any order, duplicates allowed) of the union of the sample's
+// arrays.  All jobs of a call share the eight passes: per pass every device histograms every job (one launch each, no
+// synchronisation in between), then one small copy per device brings all rows back and the host advances every rank.
+struct SelJob { SelSample smp; std::vector<uint64_t> ranks; std::vector<double> x; };
+
+int select_ranks(jne_ctx* ctx, const std::vector<int>& dev_index, std::vector<SelJob>& jobs) {
+  const size_t nd = dev_index.size(), nj = jobs.size();
+  constexpr size_t kRow = 256;
+  std::vector<std::vector<uint64_t>> prefix(nj), within(nj);
+  std::vector<std::vector<int>> group(nj);
+  for (size_t j = 0; j < nj; ++j) { prefix[j].assign(jobs[j].ranks.size(), 0); within[j] = jobs[j].ranks; group[j].resize(jobs[j].ranks.size()); }
   std::vector<unsigned int*> d_hist(nd, nullptr);
-  std::vector<unsigned int> h_hist, h_part;
+  const size_t cap_words = nj * (size_t)kSelMaxGroups * kRow;
+  std::vector<unsigned int> h_hist, h_part(cap_words);
   auto body = [&]() -> int {
     for (size_t i = 0; i < nd; ++i) {
       JNE_CUDA(ctx, cudaSetDevice(ctx->devs[dev_index[i]].id));
-      JNE_CUDA(ctx, cudaMalloc(&d_hist[i], (size_t)kSelMaxGroups * 65536 * sizeof(unsigned int)));
+      JNE_CUDA(ctx, cudaMalloc(&d_hist[i], cap_words * sizeof(unsigned int)));
     }
-    for (int pass = 0; pass < 4; ++pass) {
-      const int shift = 48 - 16 * pass;
-      JneSelPrefixes pf{};
-      std::vector<int> group(nr);
-      for (size_t r = 0; r < nr; ++r) {                  // distinct prefixes among the ranks still being resolved
-        int g = -1;
-        for (int k = 0; k < pf.n; ++k) if (pf.prefix[k] == prefix[r]) g = k;
-        if (g < 0) {
-          if (pf.n == kSelMaxGroups) return fail(ctx, JNE_ERR_INVALID_ARG, "too many distinct percentiles in one call (at most 16)");
-          g = pf.n; pf.prefix[pf.n++] = prefix[r];
+    std::vector<JneSelPrefixes> pf(nj);
+    std::vector<size_t> row0(nj);
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 56 - 8 * pass;
+      size_t words = 0;
+      for (size_t j = 0; j < nj; ++j) {                    // distinct prefixes among the job's ranks
+        pf[j] = JneSelPrefixes{};
+        for (size_t r = 0; r < prefix[j].size(); ++r) {
+          int g = -1;
+          for (int k = 0; k < pf[j].n; ++k) if (pf[j].prefix[k] == prefix[j][r]) g = k;
+          if (g < 0) {
+            if (pf[j].n == kSelMaxGroups) return fail(ctx, JNE_ERR_INVALID_ARG, "too many distinct percentiles in one call (at most 16)");
+            g = pf[j].n; pf[j].prefix[pf[j].n++] = prefix[j][r];
+          }
+          group[j][r] = g;
         }
-        group[r] = g;
+        row0[j] = words;
+        words += (size_t)pf[j].n * kRow;
       }
-      const size_t words = (size_t)pf.n * 65536;
       h_hist.assign(words, 0u);
-      h_part.resize(words);
       for (size_t i = 0; i < nd; ++i) {
-        if (smp.n[i] == 0) continue;
         Device& dv = ctx->devs[dev_index[i]];
         JNE_CUDA(ctx, cudaSetDevice(dv.id));
         JNE_CUDA(ctx, cudaMemsetAsync(d_hist[i], 0, words * sizeof(unsigned int), dv.stream));
-        const unsigned grid = (unsigned)std::min<uint64_t>((smp.n[i] + 255) / 256, (uint64_t)dv.sm_count * 16);
-        jne_select_hist_kernel<<<grid, 256, 0, dv.stream>>>(smp.vals[i], smp.n[i], shift, pf, d_hist[i]);
+        for (size_t j = 0; j < nj; ++j) {
+          const uint64_t n = jobs[j].smp.n[i];
+          if (n == 0) continue;
+          const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)dv.sm_count * 16);
+          jne_select_hist_kernel<<<grid, 256, 0, dv.stream>>>(jobs[j].smp.vals[i], n, shift, pf[j], d_hist[i] + row0[j]);
+          ctx->launches.fetch_add(1);
+        }
         JNE_CUDA(ctx, cudaGetLastError());
-        ctx->launches.fetch_add(1);
       }
-      for (size_t i = 0; i < nd; ++i) {                  // merge: the only data that leaves a device
-        if (smp.n[i] == 0) continue;
+      for (size_t i = 0; i < nd; ++i) {                    // merge: the only data that leaves a device
         Device& dv = ctx->devs[dev_index[i]];
         JNE_CUDA(ctx, cudaSetDevice(dv.id));
         JNE_CUDA(ctx, cudaMemcpyAsync(h_part.data(), d_hist[i], words * sizeof(unsigned int), cudaMemcpyDeviceToHost, dv.stream));
         JNE_CUDA(ctx, cudaStreamSynchronize(dv.stream));
         for (size_t w = 0; w < words; ++w) h_hist[w] += h_part[w];
       }
-      for (size_t r = 0; r < nr; ++r) {
-        const unsigned int* h = h_hist.data() + (size_t)group[r] * 65536;
-        uint64_t cum = 0;
-        int digit = 0;
-        for (; digit < 65536; ++digit) {
-          if (within[r] < cum + h[digit]) break;
-          cum += h[digit];
+      for (size_t j = 0; j < nj; ++j)
+        for (size_t r = 0; r < prefix[j].size(); ++r) {
+          const unsigned int* h = h_hist.data() + row0[j] + (size_t)group[j][r] * kRow;
+          uint64_t cum = 0;
+          size_t digit = 0;
+          for (; digit < kRow; ++digit) {
+            if (within[j][r] < cum + h[digit]) break;
+            cum += h[digit];
+          }
+          if (digit == kRow) return fail(ctx, JNE_ERR_INVALID_ARG, "rank outside the sample");
+          within[j][r] -= cum;
+          prefix[j][r] = (prefix[j][r] << 8) | (uint64_t)digit;
         }
-        if (digit == 65536) return fail(ctx, JNE_ERR_INVALID_ARG, "rank outside the sample");
-        within[r] -= cum;
-        prefix[r] = (prefix[r] << 16) | (uint64_t)digit;
-      }
     }
-    out->resize(nr);
-    for (size_t r = 0; r < nr; ++r) {
-      const uint64_t key = prefix[r];
-      const uint64_t bits = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
-      std::memcpy(&(*out)[r], &bits, 8);
+    for (size_t j = 0; j < nj; ++j) {
+      jobs[j].x.resize(prefix[j].size());
+      for (size_t r = 0; r < prefix[j].size(); ++r) {
+        const uint64_t key = prefix[j][r];
+        const uint64_t bits = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
+        std::memcpy(&jobs[j].x[r], &bits, 8);
+      }
     }
     return JNE_OK;
   };
@@ -1288,30 +1306,44 @@ int select_ranks(jne_ctx* ctx, const std::vector<int>& dev_index, const SelSampl
   return rc;
 }
 
-// get_percentile_value of src/simulation_analyzers.rs:4-18 for every q: rank = q (n - 1), linear interpolation between
-// the two neighbouring order statistics; two products and one sum, each rounded (no FMA contraction), as the reference.
-int percentiles_of_sample(jne_ctx* ctx, const std::vector<int>& dev_index, const SelSample& smp, const double* qs, uint32_t nq,
-                          double* out) {
-  uint64_t n = 0;
-  for (uint64_t m : smp.n) n += m;
-  if (n == 0) { for (uint32_t k = 0; k < nq; ++k) out[k] = std::nan(""); return JNE_OK; }
-  std::vector<uint64_t> ranks;
-  for (uint32_t k = 0; k < nq; ++k) {
-    const double rank = qs[k] * (double)(n - 1);
-    if (!(rank >= 0.0) || rank > (double)(n - 1)) return fail(ctx, JNE_ERR_INVALID_ARG, "percentile outside [0, 1]");
-    ranks.push_back((uint64_t)std::floor(rank));
-    ranks.push_back((uint64_t)std::ceil(rank));
+// get_percentile_value of src/simulation_analyzers.rs:4-18 for every q and every sample: rank = q (n - 1), linear
+// interpolation between the two neighbouring order statistics; two products and one sum, each rounded (no FMA
+// contraction), as the reference.  outs[j] receives the nq percentiles of samples[j].
+int percentiles_of_samples(jne_ctx* ctx, const std::vector<int>& dev_index, const std::vector<SelSample>& samples,
+                           const double* qs, uint32_t nq, const std::vector<double*>& outs) {
+  std::vector<SelJob> jobs;
+  std::vector<size_t> job_of(samples.size(), (size_t)-1);
+  std::vector<uint64_t> total(samples.size(), 0);
+  for (size_t j = 0; j < samples.size(); ++j) {
+    uint64_t n = 0;
+    for (uint64_t m : samples[j].n) n += m;
+    total[j] = n;
+    if (n == 0) { for (uint32_t k = 0; k < nq; ++k) outs[j][k] = std::nan(""); continue; }
+    SelJob job;
+    job.smp = samples[j];
+    for (uint32_t k = 0; k < nq; ++k) {
+      const double rank = qs[k] * (double)(n - 1);
+      if (!(rank >= 0.0) || rank > (double)(n - 1)) return fail(ctx, JNE_ERR_INVALID_ARG, "percentile outside [0, 1]");
+      job.ranks.push_back((uint64_t)std::floor(rank));
+      job.ranks.push_back((uint64_t)std::ceil(rank));
+    }
+    job_of[j] = jobs.size();
+    jobs.push_back(std::move(job));
   }
-  std::vector<double> x;
-  const int rc = select_ranks(ctx, dev_index, smp, ranks, &x);
+  if (jobs.empty()) return JNE_OK;
+  const int rc = select_ranks(ctx, dev_index, jobs);
   if (rc) return rc;
-  for (uint32_t k = 0; k < nq; ++k) {
-    const double rank = qs[k] * (double)(n - 1);
-    const uint64_t lo = ranks[2 * k], hi = ranks[2 * k + 1];
-    if (lo == hi) { out[k] = x[2 * k]; continue; }
-    const double w = rank - (double)lo;
-    volatile double a = x[2 * k] * (1.0 - w), b = x[2 * k + 1] * w;   // volatile: two roundings, then the sum
-    out[k] = a + b;
+  for (size_t j = 0; j < samples.size(); ++j) {
+    if (job_of[j] == (size_t)-1) continue;
+    const SelJob& job = jobs[job_of[j]];
+    for (uint32_t k = 0; k < nq; ++k) {
+      const double rank = qs[k] * (double)(total[j] - 1);
+      const uint64_t lo = job.ranks[2 * k], hi = job.ranks[2 * k + 1];
+      if (lo == hi) { outs[j][k] = job.x[2 * k]; continue; }
+      const double w = rank - (double)lo;
+      volatile double a = job.x[2 * k] * (1.0 - w), b = job.x[2 * k + 1] * w;   // volatile: two roundings, then the sum
+      outs[j][k] = a + b;
+    }
   }
   return JNE_OK;
 }
@@ -1387,16 +1419,19 @@ int simulate_percentiles_impl(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, u
   if (!rc) {
     std::vector<int> dev_index(nd);
     for (size_t i = 0; i < nd; ++i) dev_index[i] = (int)i;
-    for (int slot = 0; slot < nm && !rc; ++slot) {
+    std::vector<SelSample> samples;                        // trace and max-eig of every selected model: one selection
+    std::vector<double*> outs;
+    for (int slot = 0; slot < nm; ++slot) {
       SelSample tr, mx;
       for (size_t i = 0; i < nd; ++i) {
         const double* agg = d_agg[i] ? d_agg[i] + (size_t)slot * 2 * share[i] : nullptr;
         tr.vals.push_back(agg); tr.n.push_back(share[i]);
         mx.vals.push_back(agg ? agg + share[i] : nullptr); mx.n.push_back(share[i]);
       }
-      rc = percentiles_of_sample(ctx, dev_index, tr, qs, nq, trace_out + (size_t)slot * nq);
-      if (!rc) rc = percentiles_of_sample(ctx, dev_index, mx, qs, nq, maxeig_out + (size_t)slot * nq);
+      samples.push_back(std::move(tr)); outs.push_back(trace_out + (size_t)slot * nq);
+      samples.push_back(std::move(mx)); outs.push_back(maxeig_out + (size_t)slot * nq);
     }
+    rc = percentiles_of_samples(ctx, dev_index, samples, qs, nq, outs);
   }
   for (size_t i = 0; i < nd; ++i)
     if (d_agg[i]) { cudaSetDevice(ctx->devs[i].id); cudaFree(d_agg[i]); }
@@ -1425,10 +1460,7 @@ int jne_percentiles_device(jne_ctx* ctx, const void* d_eigs, uint64_t n, uint32_
       JNE_CUDA(ctx, cudaGetLastError());
       ctx->launches.fetch_add(1);
       JNE_CUDA(ctx, cudaStreamSynchronize(st));       // the selection runs on the context's own stream
-      SelSample tr{{d_buf}, {n}}, mx{{d_buf + n}, {n}};
-      int rc = percentiles_of_sample(ctx, {0}, tr, qs, nq, trace_out);
-      if (!rc) rc = percentiles_of_sample(ctx, {0}, mx, qs, nq, maxeig_out);
-      return rc;
+      return percentiles_of_samples(ctx, {0}, {SelSample{{d_buf}, {n}}, SelSample{{d_buf + n}, {n}}}, qs, nq, {trace_out, maxeig_out});
     };
     const int rc = body();
     cudaFree(d_buf);
