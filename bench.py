@@ -189,6 +189,10 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # host-side barrier for the stretch in which rank 0 drives EVERY GPU from one process: a rank waiting in an NCCL
+        # barrier spins a kernel on its GPU, and two processes on one device are time-sliced (measured: the in-process
+        # figure of 2 GPUs fell to that of one)
+        cpu_group = dist.new_group(backend="gloo")
 
     def barrier():
         if world > 1:
@@ -366,7 +370,7 @@ def main():
         c2["e2e_fused_runs_per_s"] = len(MODELS) * n2 / (time.perf_counter() - h0)      # host buffers, H2D + D2H inside
         extras["c2"] = c2
     if world > 1:
-        dist.barrier()          # the other ranks idle while rank 0 drives every GPU from one process
+        dist.barrier(group=cpu_group)   # the other ranks idle (on the host) while rank 0 drives every GPU from one process
     if rank == 0 and not args.no_extras:
         try:
             nvis = torch.cuda.device_count()
@@ -386,7 +390,7 @@ def main():
             extras["e2e_inprocess"] = {"value": None, "error": f"{type(exc).__name__}: {exc}"}
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
     h2d = 4 * R
     d2h = 8 * R * width
     tp = torch.tensor([pm_ms], dtype=torch.float64, device=torch.device("cuda", local_rank))
