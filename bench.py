@@ -363,7 +363,7 @@ def main():
         c2["per_model_runs_per_s"] = {str(m): n2 / (pm[m] * 1e-3) for m in MODELS}
         c2["per_model_frac_of_fp64_peak"] = {str(m): jne.flops_per_run(m, 5, 5000) * n2 / (pm[m] * 1e-3) / 1e12 / peak for m in MODELS}
         seeds2 = np.arange(1, n2 + 1, dtype=np.uint32)
-        buf2 = np.empty((n2, sum(jne.num_eigs(m, 5) for m in MODELS)))
+        buf2 = np.zeros((n2, sum(jne.num_eigs(m, 5) for m in MODELS)))    # touched: a caller's reused buffer, not fresh pages
         eng.eigs_batch_multi(MODELS, 5, 5000, seeds2[:200000], out=buf2[:200000])
         h0 = time.perf_counter()
         eng.eigs_batch_multi(MODELS, 5, 5000, seeds2, out=buf2)
