@@ -212,7 +212,7 @@ double jne_flops_per_run(uint8_t model, uint32_t dim, uint32_t steps);
 int jne_jacobi_table(uint32_t ne, uint32_t* words, uint32_t capacity);
 
 /* The trend-weight table the AUX kernels (dim <= 6 and 9..12, a model with a trend row) feed to the tensor pipe for a
- * run of `steps` steps: seg_len = 128 ceil(steps / 512) local steps (whole generator epochs) x 4 weights x 4 time segments, doubles,
+ * run of `steps` steps: seg_len local steps (128 ceil(steps / 512): whole generator epochs; short horizons 8 ceil(steps / 32), whichever wastes fewer lane-steps) x 4 weights x 4 time segments, doubles,
  * table[(j * 4 + m) * 4 + k] for local step j of segment k (global step i = k seg_len + j, segment end e_k), with
  * w1_i = 2i + 1 - T, w2_i = 3 w1_i^2 - (T^2 - 1) (the integer forms of the reference's trend regressors
  * (i+1)/T - 1/2 and the residual of ((i+1)/T)^2 on [1, (i+1)/T], src/johansen_statistics.rs:127-135,170-194):

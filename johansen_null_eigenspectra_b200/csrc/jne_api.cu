@@ -139,13 +139,21 @@ void segment_weights(uint64_t a, uint64_t b, uint64_t T, double* w1, double* w2)
 //   m = 2: w2_i        m = 3: w1_i
 // Integer-valued, evaluated in 128-bit integers and rounded once; steps outside the segment carry 0.
 constexpr uint32_t kAuxMaxSteps = 1u << 22;   // 128 MiB of table; longer runs use the scalar-sum kernels
-// Length of the four time segments of the tensor family: whole generator epochs (jne_rng.cuh), so that the lanes of a
-// warp -- one segment each -- start new substreams in the same block of the time loop.
+// Length of the four time segments of the tensor family.  Long horizons: whole generator epochs (jne_rng.cuh), so that
+// the lanes of a warp -- one segment each -- start new substreams in the same block of the time loop (a warp-uniform
+// branch, 3 Philox calls per 16 blocks).  Short horizons: whole 8-step blocks; the segments then start inside an
+// epoch, every lane skips to its place in its substreams once and re-keys in its own phase (the branch diverges: up
+// to four passes through the key generation per 16 blocks, ~5 % of the loop) -- cheaper than leaving segments empty
+// (T = 200: 89 % of the lane-steps useful instead of 39 %; T = 2 049: 98 % instead of 80 %).  The rule picks the
+// better of the two estimates: T = 1 000, 5 000, 10 000 and 100 000 run epoch-aligned.
 uint32_t seg_len_for(uint32_t steps) {
-#ifdef JNE_EXP_SEGLEN8   // experiment only: segments of whole 8-step blocks (misaligned epochs: NOT a valid stream)
-  return 8u * ((steps + 31u) / 32u);
+  const uint32_t by_block = 8u * ((steps + 31u) / 32u);
+#ifdef JNE_EXP_SEGLEN8   // experiment only: segments of whole 8-step blocks at every horizon
+  return by_block;
 #endif
-  return (uint32_t)(JNE_EPOCH_STEPS * (((uint64_t)steps + 4u * JNE_EPOCH_STEPS - 1u) / (4u * JNE_EPOCH_STEPS)));
+  const uint32_t by_epoch =
+      (uint32_t)(JNE_EPOCH_STEPS * (((uint64_t)steps + 4u * JNE_EPOCH_STEPS - 1u) / (4u * JNE_EPOCH_STEPS)));
+  return 0.95 * (double)by_epoch > (double)by_block ? by_block : by_epoch;
 }
 std::vector<double> make_aux_table(uint32_t steps) {
   const uint32_t seg_len = seg_len_for(steps);
@@ -245,7 +253,9 @@ constexpr size_t pencil_smem() { return (size_t)JNE_WARPS_PER_CTA * JneEpi<16, 1
 template <int DP, int DET, bool RNG, bool MULTI, bool AUXT = false>
 cudaError_t launch_one(const uint32_t* d_seeds, const double* d_dB, uint64_t n, const JneRunParams& prm,
                        double* d_out, unsigned int* d_err, double* d_dbg, cudaStream_t st) {
-  auto kern = jne_run_kernel<DP, DET, RNG, MULTI, AUXT>;
+  // short horizons run the instance whose lanes re-key their substreams in their own phase (seg_len_for)
+  const bool unaligned = RNG && (prm.seg_len % JNE_EPOCH_STEPS) != 0u;
+  auto kern = unaligned ? jne_run_kernel<DP, DET, RNG, MULTI, AUXT, RNG> : jne_run_kernel<DP, DET, RNG, MULTI, AUXT, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem<DP, MULTI>());
   if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)((n + JNE_WARPS_PER_CTA - 1) / JNE_WARPS_PER_CTA);

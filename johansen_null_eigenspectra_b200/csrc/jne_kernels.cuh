@@ -581,9 +581,9 @@ __device__ __forceinline__ bool jne_warp_models(double* __restrict__ wsm, const 
 // (DP = 4, 12; the last state).  Registers: keeping the states in the warp's loop-idle shared memory instead (one
 // LDS.128 / STS.128 pair per call) measured 1 % slower (profiles/r2_variants_generators.txt).
 #ifdef JNE_EXP_NORESEED   // experiment only: substreams keyed once per run and segment (NOT a valid stream)
-#define JNE_EPOCH_MASK 0xFFFFFFFFu
-#else
-#define JNE_EPOCH_MASK (JNE_EPOCH_STEPS - 1u)
+#define JNE_EPOCH_START(t, t_begin, unaligned) ((t) == (t_begin))
+#else   // aligned segments: every lane of the warp at once; unaligned ones: every lane in its own phase
+#define JNE_EPOCH_START(t, t_begin, unaligned) ((((unaligned) ? (t) : (t) - (t_begin)) & (JNE_EPOCH_STEPS - 1u)) == 0u)
 #endif
 template <int DP> struct JneGen {
   using G = JneGeo<DP>;
@@ -851,7 +851,8 @@ __device__ __forceinline__ void jne_warp_dump(JneLoopState<DP>& L, double* __res
 #else
 #define JNE_MINB(MULTI, DET) (((MULTI) ? JNE_MULTI_MINB : ((DET) == 0 ? 6 : 5)) * 4 / JNE_WARPS_PER_CTA)
 #endif
-template <int DP, int DET, bool SRC_RNG, bool MULTI, bool AUXT = false>
+// UNALIGNED (short horizons, seg_len_for in jne_api.cu): the segments are whole 8-step blocks, not whole generator epochs.
+template <int DP, int DET, bool SRC_RNG, bool MULTI, bool AUXT = false, bool UNALIGNED = false>
 __global__ void __launch_bounds__(32 * JNE_WARPS_PER_CTA, SRC_RNG ? JNE_MINB(MULTI, DET) : 1)
 jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB, uint64_t n,
                JneRunParams prm, double* __restrict__ out, unsigned int* __restrict__ err_count,
@@ -903,16 +904,29 @@ jne_run_kernel(const uint32_t* __restrict__ seeds, const double* __restrict__ dB
   // (DP = 8: lane g = 6 reads weight 3 = w1, lane g = 7 weight 2 = w2)
   const int aux_m = (G::B == 4) ? (g & 3) : (g == 7 ? 2 : 3);
   const double* aux = AUX ? prm.aux_tab + ((aux_m << 2) | k) : nullptr;
-  // segments are whole epochs long (JneRunParams::seg_len), so every lane of the warp enters a new epoch in the
-  // same block; the lanes of an empty segment (t_begin = T) compute an epoch nobody reads
+  // Long horizons: segments are whole epochs long (seg_len_for, jne_api.cu), every lane of the warp enters a new epoch
+  // in the same block and the branch below is warp-uniform.  Short horizons (the UNALIGNED instance: a kernel of its
+  // own, because the extra code cost the fused dim-12 loop 1.4 % through register allocation alone): segments of whole
+  // 8-step blocks start inside an epoch; a lane keys the epoch it starts in, skips the blocks before its own (at most 15 per substream;
+  // t_begin is a multiple of 8, so both halves are at the same block number) and from then on re-keys in its own phase.
+  // The lanes of an empty segment (t_begin = T) compute substreams nobody reads.
+  if (SRC_RNG && UNALIGNED && (t_begin & (JNE_EPOCH_STEPS - 1u)) != 0u) {
+    jne_gen_seed<DP>(gs, seed, t_begin / JNE_EPOCH_STEPS, g);
+    const uint32_t skip = ((t_begin >> 2) & (JNE_EPOCH_BLOCKS - 1u)) >> 1;
+    for (uint32_t i = 0; i < skip; ++i) {
+      jne_zt dump[4];
+#pragma unroll
+      for (int q = 0; q < JneGen<DP>::NST; ++q) jne_sub_normals4(gs.st[q], dump, 0.0f);
+    }
+  }
   for (; t < t_full; t += 8) {
-    if (SRC_RNG && ((t - t_begin) & JNE_EPOCH_MASK) == 0u) jne_gen_seed<DP>(gs, seed, t / JNE_EPOCH_STEPS, g);
+    if (SRC_RNG && JNE_EPOCH_START(t, t_begin, UNALIGNED)) jne_gen_seed<DP>(gs, seed, t / JNE_EPOCH_STEPS, g);
     jne_gen8<DP, SRC_RNG>(t, t_end, d, g, gs, rowscale, xscale, dBrun, z);
     jne_consume8<DP, DET, SRC_RNG, false, AUX>(t, t_end, g, src_lane, z, L, w2c, aux);
     if (AUX) aux += 128;
   }
   for (; t < t_stop; t += 8) {
-    if (SRC_RNG && ((t - t_begin) & JNE_EPOCH_MASK) == 0u) jne_gen_seed<DP>(gs, seed, t / JNE_EPOCH_STEPS, g);
+    if (SRC_RNG && JNE_EPOCH_START(t, t_begin, UNALIGNED)) jne_gen_seed<DP>(gs, seed, t / JNE_EPOCH_STEPS, g);
     jne_gen8<DP, SRC_RNG>(t, t_end, d, g, gs, rowscale, xscale, dBrun, z);
     jne_consume8<DP, DET, SRC_RNG, true, AUX>(t, t_end, g, src_lane, z, L, w2c, aux);
     if (AUX) aux += 128;

@@ -34,6 +34,9 @@
 #ifndef JNE_LANE_MINB5
 #define JNE_LANE_MINB5 2      // dim 5: 255 registers, 2 resident CTAs per SM; 3 = 168 registers (measured equal without
 #endif                        // the software pipeline, whose second block of normals needs the room)
+#ifndef JNE_LANE_REG_STATES
+#define JNE_LANE_REG_STATES 5   // generator states in registers up to this dim, in shared memory above (dim 6)
+#endif
 #ifndef JNE_LANE_PIPELINE
 #define JNE_LANE_PIPELINE 1   // 0: generate a block, then consume it (regression / ablation)
 #endif
@@ -106,12 +109,37 @@ jne_lane_moments_kernel(const uint32_t* __restrict__ seeds, const double* __rest
   const uint64_t run = live ? run_raw : n - 1;         // idle lanes shadow the last run (no divergence in the loop)
   // generator state: both substreams (halves) of every row of the current epoch, jne_rng.cuh
   const uint32_t seed = SRC_RNG ? seeds[run] : 0u;
-  jne_sub st[D][2];
+  // D <= JNE_LANE_REG_STATES: in registers.  Above (dim 6: 81 moments, the path and 48 state words do not fit 255
+  // registers; ptxas spilled 72 bytes of the hot loop), the states live in shared memory, one 16-byte word per thread
+  // and state: a conflict-free LDS.128 / STS.128 pair per generator call.
+  constexpr bool ST_SMEM = SRC_RNG && D > JNE_LANE_REG_STATES && sizeof(jne_sub) == 16;
+  __shared__ uint4 st_sm[ST_SMEM ? 2 * D : 1][ST_SMEM ? JneLaneGeo<D>::THREADS : 1];
+  jne_sub st[ST_SMEM ? 1 : D][2];
   auto seed_all = [&](uint32_t epoch) {
 #pragma unroll
     for (int r = 0; r < D; ++r) {
-      jne_sub_seed(st[r][0], seed, (uint32_t)r, epoch, 0u);
-      jne_sub_seed(st[r][1], seed, (uint32_t)r, epoch, 1u);
+      if constexpr (ST_SMEM) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          jne_sub x;
+          jne_sub_seed(x, seed, (uint32_t)r, epoch, (uint32_t)h);
+          st_sm[2 * r + h][threadIdx.x] = make_uint4(x.s0, x.s1, x.s2, x.s3);
+        }
+      } else {
+        jne_sub_seed(st[r][0], seed, (uint32_t)r, epoch, 0u);
+        jne_sub_seed(st[r][1], seed, (uint32_t)r, epoch, 1u);
+      }
+    }
+  };
+  auto draw4 = [&](int r, int h, jne_zt* z) {            // the next four-step block of row r, half h (constants after unrolling)
+    if constexpr (ST_SMEM) {
+      const uint4 v = st_sm[2 * r + h][threadIdx.x];
+      jne_sub x;
+      x.s0 = v.x; x.s1 = v.y; x.s2 = v.z; x.s3 = v.w;
+      jne_sub_normals4(x, z);
+      st_sm[2 * r + h][threadIdx.x] = make_uint4(x.s0, x.s1, x.s2, x.s3);
+    } else {
+      jne_sub_normals4(st[r][h], z);
     }
   };
   const double* dBrun = SRC_RNG ? nullptr : dB + run * (uint64_t)D * T;
@@ -143,7 +171,7 @@ jne_lane_moments_kernel(const uint32_t* __restrict__ seeds, const double* __rest
     jne_zt zc[D][4], zn[D][4];
     seed_all(0u);
 #pragma unroll
-    for (int r = 0; r < D; ++r) jne_sub_normals4(st[r][0], zc[r]);
+    for (int r = 0; r < D; ++r) draw4(r, 0, zc[r]);
     // block tb (parity H) is consumed from zc while block tb + 1 (parity 1 - H) is generated into zn
     auto block = [&](auto Hc, uint32_t tb) {
       constexpr int H = decltype(Hc)::value;
@@ -152,7 +180,7 @@ jne_lane_moments_kernel(const uint32_t* __restrict__ seeds, const double* __rest
       for (int s = 0; s < 4; ++s) {
 #pragma unroll
         for (int r = 0; r < D; ++r)
-          if (r * 4 / D == s) jne_sub_normals4(st[r][1 - H], zn[r]);
+          if (r * 4 / D == s) draw4(r, 1 - H, zn[r]);
         double zz[D];
 #pragma unroll
         for (int r = 0; r < D; ++r) zz[r] = (double)zc[r][s];
@@ -568,6 +596,7 @@ jne_group_moments_kernel(const uint32_t* __restrict__ seeds, const double* __res
   double* zs = zs_all[warp];
   // generator state: both substreams (halves) of this lane's R rows for the current epoch, jne_rng.cuh
   const uint32_t seed = SRC_RNG ? seeds[run] : 0u;
+  // (registers: the same states in shared memory, as in the dim-6 lane kernel, cost this kernel 9 %)
   jne_sub st[R][2];
   auto seed_all = [&](uint32_t epoch) {
 #pragma unroll

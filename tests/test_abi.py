@@ -142,7 +142,7 @@ def test_jacobi_table_rejects_bad_sizes():
             jne.jacobi_table(ne)
 
 
-@pytest.mark.parametrize("T", [1, 2, 7, 31, 32, 33, 100, 1000, 10000])
+@pytest.mark.parametrize("T", [1, 2, 7, 31, 32, 33, 100, 960, 961, 1000, 2049, 10000])
 def test_trend_weight_table(T):
     """Host logic of the AUX kernels (make_aux_table): the table fed to the tensor pipe holds, per local step of each
     of the four time segments, the exact integer tail sums of w1 / w2 and the weights themselves -- and with them
@@ -150,7 +150,8 @@ def test_trend_weight_table(T):
     which is the identity the kernels rely on (summation by parts)."""
     import johansen_null_eigenspectra_b200 as jne
     tab = jne.trend_weight_table(T)
-    seg_len = 128 * ((T + 511) // 512)          # whole generator epochs (jne_rng.cuh)
+    by_block, by_epoch = 8 * ((T + 31) // 32), 128 * ((T + 511) // 512)
+    seg_len = by_block if 0.95 * by_epoch > by_block else by_epoch    # seg_len_for (jne_api.cu)
     assert tab.shape == (seg_len, 4, 4)
     w1 = [2 * i + 1 - T for i in range(T)]
     w2 = [3 * w * w - (T * T - 1) for w in w1]

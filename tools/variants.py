@@ -15,6 +15,7 @@ VARIANTS = {
     "noreseed": ["-DJNE_EXP_NORESEED"],            # tensor family: substreams keyed once per run (NOT a valid stream): cost of the in-loop key generation
     "seglen8_noreseed": ["-DJNE_EXP_SEGLEN8", "-DJNE_EXP_NORESEED"],
     "minb4": ["-DJNE_MULTI_MINB=4"],               # fused tensor kernel at 4 CTAs per SM (116 registers: no spill of the substream states)
+    "lane6_reg_states": ["-DJNE_LANE_REG_STATES=6"],     # lane family dim 6: generator states in registers (spills 72 bytes)
     "lane_minb_hi": ["-DJNE_LANE_MINB3=5", "-DJNE_LANE_MINB4=4"],   # lane family dims 3 / 4 at 102 / 128 registers (the substream states spill)
     "group78": ["-DJNE_EXP_GROUP_78"],             # dims 7, 8 on the group kernel (2 lanes x 4 rows), dim 10 as 5 x 2
     "lane_nopipe": ["-DJNE_LANE_PIPELINE=0"],      # lane family without the software pipeline (generate a block, then consume it)
