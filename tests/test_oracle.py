@@ -225,6 +225,30 @@ def test_stream_words_layout():
         assert [int(philox_ref.xoshiro128pp(st)[0]) for _ in range(4)] == [int(x) for x in w[row, b]]
 
 
+def test_stream_has_no_structure_across_blocks_halves_and_epochs():
+    """The stream interleaves two generators per row (the halves) and re-keys them every 128 steps.  Serial correlations
+    of the normals and of their squares at the lags that structure could show at (neighbouring steps, the four-step
+    block, the other half, the epoch and its neighbours), correlations between rows, and the byte frequencies of the
+    words: all at the level of independent N(0, 1) / uniform draws.  (The words are bit-exact with the device, so this
+    CPU test speaks for the device stream.)"""
+    zs = [philox_ref.normal_matrix(8, 1 << 15, seed) for seed in (1, 2, 3)]
+    n = zs[0].shape[1]
+    for f in (lambda v: v, lambda v: v * v):
+        for lag in (1, 2, 4, 8, 127, 128, 129, 256):
+            r = np.array([np.corrcoef(f(z[i, :-lag]), f(z[i, lag:]))[0, 1] for z in zs for i in range(8)]) * np.sqrt(n)
+            assert abs(r.mean()) < 4.0 / np.sqrt(r.size), (lag, r.mean())      # no systematic correlation (4 sigma of the mean)
+            assert np.abs(r).max() < 4.5, (lag, np.abs(r).max())
+    for z in zs:
+        c = np.corrcoef(z)
+        np.fill_diagonal(c, 0.0)
+        assert np.abs(c).max() * np.sqrt(n) < 4.5
+    w = philox_ref.stream_words(8, 1 << 15, 7).ravel()
+    for shift in (0, 8, 16, 24):
+        cnt = np.bincount((w >> np.uint32(shift)) & np.uint32(0xFF), minlength=256)
+        chi2 = ((cnt - w.size / 256) ** 2 / (w.size / 256)).sum()
+        assert stats.chi2.sf(chi2, 255) > 1e-4, (shift, chi2)
+
+
 def test_philox_normal_matrix_is_standard_normal():
     z = philox_ref.normal_matrix(200, 300, 42)
     qs = np.arange(1, 100) / 100
