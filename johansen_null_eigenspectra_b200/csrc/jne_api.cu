@@ -1380,11 +1380,16 @@ int simulate_percentiles_impl(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, u
     JneRunParams prm = prm0;
     prm.jtab = jtab_for(dv, dim);
     const uint64_t chunk = 1ull << 19;
-    uint32_t* d_seeds = nullptr;
-    double* d_eigs = nullptr;
-    JNE_CUDA(ctx, cudaMalloc(&d_agg[i], (size_t)nm * 2 * ni * sizeof(double)));
-    JNE_CUDA(ctx, cudaMalloc(&d_seeds, chunk * sizeof(uint32_t)));
-    if (cudaMalloc(&d_eigs, chunk * prm.out_stride * sizeof(double)) != cudaSuccess) { cudaFree(d_seeds); return fail(ctx, JNE_ERR_CUDA, "out of device memory"); }
+    // one region of the device's grow-only scratch buffer: [statistics | eigenvalues of a chunk | seeds of a chunk].  A sweep
+    // calls this once per dim; allocating and freeing ~1 GB per call cost the one-GPU default sweep a second
+    const size_t agg_doubles = ((size_t)nm * 2 * ni + 31) & ~(size_t)31, eig_doubles = (size_t)chunk * prm.out_stride;   // 256-byte aligned parts
+    {
+      const int rc = ensure_scratch(ctx, dv, (agg_doubles + eig_doubles) * sizeof(double) + chunk * sizeof(uint32_t));
+      if (rc) return rc;
+    }
+    d_agg[i] = dv.d_scratch;
+    double* d_eigs = dv.d_scratch + agg_doubles;
+    uint32_t* d_seeds = reinterpret_cast<uint32_t*>(d_eigs + eig_doubles);
     auto body = [&]() -> int {
       JNE_CUDA(ctx, cudaMemsetAsync(dv.d_err, 0, sizeof(unsigned int), dv.stream));
       for (uint64_t off = 0; off < ni; off += chunk) {
@@ -1409,9 +1414,7 @@ int simulate_percentiles_impl(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, u
       if (*dv.h_err) return fail(ctx, JNE_ERR_NONFINITE, "non-finite eigenvalues");
       return JNE_OK;
     };
-    const int rc = body();
-    cudaFree(d_seeds); cudaFree(d_eigs);
-    return rc;
+    return body();
   };
   if (nd == 1) {
     rcs[0] = device_part(0);
@@ -1443,9 +1446,7 @@ int simulate_percentiles_impl(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, u
     }
     rc = percentiles_of_samples(ctx, dev_index, samples, qs, nq, outs);
   }
-  for (size_t i = 0; i < nd; ++i)
-    if (d_agg[i]) { cudaSetDevice(ctx->devs[i].id); cudaFree(d_agg[i]); }
-  return rc;
+  return rc;     // the statistics stay in the devices' scratch buffers (reused by the next call)
 }
 
 }  // namespace
