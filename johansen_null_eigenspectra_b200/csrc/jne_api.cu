@@ -484,9 +484,14 @@ cudaError_t launch_lane(jne_ctx* ctx, Device& dv, const uint32_t* s, const doubl
       dv.d_mom[ms] = nullptr; dv.mom_doubles[ms] = 0;
       if (f != cudaSuccess) return f;
     }
-    cudaError_t a = cudaMalloc(&dv.d_mom[ms], need * sizeof(double));
+    // a full chunk asks for the largest layout of the family at once (dim 9: 180 doubles per run, 377 MB): a sweep over
+    // the dims would otherwise free and re-allocate the buffer at every dim, and each such pair synchronises the device
+    const size_t cap = n >= chunk ? std::max(need, (size_t)kMomChunk * (size_t)jne_lane_mom_size(9)) : need;
+    size_t got = cap;
+    cudaError_t a = cudaMalloc(&dv.d_mom[ms], cap * sizeof(double));
+    if (a != cudaSuccess && cap > need) { cudaGetLastError(); got = need; a = cudaMalloc(&dv.d_mom[ms], need * sizeof(double)); }
     if (a != cudaSuccess) return a;
-    dv.mom_doubles[ms] = need;
+    dv.mom_doubles[ms] = got;
   }
   double* d_mom = dv.d_mom[ms];
   const bool multi = (prm.model_mask & (prm.model_mask - 1u)) != 0;
@@ -1383,8 +1388,9 @@ int simulate_percentiles_impl(jne_ctx* ctx, uint32_t model_mask, uint32_t dim, u
     // one region of the device's grow-only scratch buffer: [statistics | eigenvalues of a chunk | seeds of a chunk].  A sweep
     // calls this once per dim; allocating and freeing ~1 GB per call cost the one-GPU default sweep a second
     const size_t agg_doubles = ((size_t)nm * 2 * ni + 31) & ~(size_t)31, eig_doubles = (size_t)chunk * prm.out_stride;   // 256-byte aligned parts
+    const size_t eig_reserve = (size_t)chunk * mask_width(model_mask, JNE_MAX_DIM);   // sized for any dim: no regrowth along a sweep
     {
-      const int rc = ensure_scratch(ctx, dv, (agg_doubles + eig_doubles) * sizeof(double) + chunk * sizeof(uint32_t));
+      const int rc = ensure_scratch(ctx, dv, (agg_doubles + std::max(eig_doubles, eig_reserve)) * sizeof(double) + chunk * sizeof(uint32_t));
       if (rc) return rc;
     }
     d_agg[i] = dv.d_scratch;
