@@ -2,12 +2,15 @@
 //! One `Gpu` per process; a context serves one caller thread at a time.
 
 use std::ffi::{CStr, CString};
-use std::os::raw::{c_char, c_int};
+use std::os::raw::{c_char, c_int, c_void};
 
 #[repr(C)]
 pub struct JneCtx {
     _private: [u8; 0],
 }
+
+/// `jne_rows_sink` of include/jne.h: rows of seeds[first .. first + count), valid during the call only.
+pub type JneRowsSink = extern "C" fn(user: *mut c_void, first: u64, count: u64, rows: *const f64) -> c_int;
 
 extern "C" {
     fn jne_init(device_ids: *const c_int, n_devices: c_int, out: *mut *mut JneCtx) -> c_int;
@@ -20,6 +23,8 @@ extern "C" {
     fn jne_submit(ctx: *mut JneCtx, model: u8, dim: u32, steps: u32, seeds: *const u32, n: u64, out: *mut f64) -> i64;
     fn jne_submit_multi(ctx: *mut JneCtx, model_mask: u32, dim: u32, steps: u32, seeds: *const u32, n: u64, out: *mut f64) -> i64;
     fn jne_wait(ctx: *mut JneCtx, ticket: i64) -> c_int;
+    fn jne_eigs_batch_multi_stream(ctx: *mut JneCtx, model_mask: u32, dim: u32, steps: u32, seeds: *const u32, n: u64,
+                                   sink: JneRowsSink, user: *mut c_void) -> c_int;
     fn jne_run_models_simulation(ctx: *mut JneCtx, model_mask: u32, dim: u32, steps: u32, num_runs: u64,
                                  filenames: *const *const c_char, quiet: c_int, device_ids: *const c_int,
                                  n_devices: c_int, stats: *mut u64) -> c_int;
@@ -115,6 +120,42 @@ impl Gpu {
             return Err(last_error(self.0));
         }
         Ok(p.rows)
+    }
+
+    /// Streaming form of the fused batch -- the reference's own protocol (every finished record is SENT to a consumer,
+    /// parallel_compute.rs:33-39): `on_rows(first, rows)` receives the rows of `seeds[first ..]` (a multiple of the row
+    /// width, `jne_multi_width`) as soon as they are on the host, straight from the library's staging memory.  It runs
+    /// on the library's per-device threads, possibly concurrently for disjoint ranges; returning `false` aborts.
+    pub fn eigs_batch_multi_stream<F>(&self, mask: u32, dim: usize, steps: usize, seeds: &[u32], on_rows: F) -> Result<(), String>
+    where
+        F: Fn(usize, &[f64]) -> bool + Sync,
+    {
+        let w = unsafe { jne_multi_width(mask, dim as u32) };
+        if w <= 0 {
+            return Err("invalid model mask / dim".into());
+        }
+        struct Ctx<F> {
+            f: F,
+            width: usize,
+        }
+        extern "C" fn tramp<F: Fn(usize, &[f64]) -> bool + Sync>(user: *mut c_void, first: u64, count: u64, rows: *const f64) -> c_int {
+            let cx = unsafe { &*(user as *const Ctx<F>) };
+            let slice = unsafe { std::slice::from_raw_parts(rows, count as usize * cx.width) };
+            // a panic must not unwind across the C ABI: it becomes an aborted batch
+            match std::panic::catch_unwind(std::panic::AssertUnwindSafe(|| (cx.f)(first as usize, slice))) {
+                Ok(true) => 0,
+                _ => 1,
+            }
+        }
+        let cx = Ctx { f: on_rows, width: w as usize };
+        let rc = unsafe {
+            jne_eigs_batch_multi_stream(self.0, mask, dim as u32, steps as u32, seeds.as_ptr(), seeds.len() as u64,
+                                        tramp::<F>, &cx as *const Ctx<F> as *mut c_void)
+        };
+        if rc != 0 {
+            return Err(last_error(self.0));
+        }
+        Ok(())
     }
 
     /// main.rs:109-114 as one fused job: every selected model's EIGENVALS_V6 file for (dim, steps, num_runs),

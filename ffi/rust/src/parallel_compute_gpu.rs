@@ -34,3 +34,31 @@ pub(crate) fn calculate_eigenvalues_parallel(
         }
     }
 }
+
+// The same through the streaming entry point: no chunk loop and no intermediate Vec of rows on this side -- the
+// library hands every finished range to the closure from its own host threads, and the closure forwards the records
+// to the writer thread exactly as the rayon tasks of the reference do (`mpsc::Sender` is `Send`; one clone per call
+// keeps the closure `Sync`).
+pub(crate) fn calculate_eigenvalues_parallel_streaming(
+    dim: usize,
+    steps: usize,
+    seeds: &[u32],
+    model: JohansenModel,
+    sender: mpsc::Sender<(u32, Vec<f64>)>,
+    quiet: bool,
+) {
+    let gpu = Gpu::new().unwrap_or_else(|e| panic!("GPU init failed: {e}"));
+    let m = model.to_number();
+    let p = Gpu::num_eigs(m, dim);
+    let sender = std::sync::Mutex::new(sender);
+    gpu.eigs_batch_multi_stream(1u32 << m, dim, steps, seeds, |first, rows| {
+        let tx = sender.lock().unwrap().clone();
+        for (i, row) in rows.chunks_exact(p).enumerate() {
+            if tx.send((seeds[first + i], row.to_vec())).is_err() && !quiet {
+                eprintln!("Failed to send results to writer thread");
+            }
+        }
+        true
+    })
+    .unwrap_or_else(|e| panic!("GPU batch failed: {e}"));
+}
